@@ -1,0 +1,126 @@
+"""CPU: the oracle restatement (oracle/mvptr_oracle.py) reproduces the outputs the
+REAL reference produced in the authoring container (tests/golden/*.pt, written
+by oracle/make_golden.py)."""
+import os
+
+import torch
+
+from oracle import mvptr_oracle as O
+
+TOL = 2e-5
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def _close(a, b, tol=TOL):
+    err = (a.double() - b.double()).abs().max().item()
+    assert err <= tol * max(1.0, b.double().abs().max().item()), err
+
+
+def _sum(ts):
+    return sum(float(t.double().abs().sum()) for t in ts)
+
+
+def test_rep_matches_reference(golden_dir):
+    g = _load(golden_dir, "rep_tiny.pt")
+    cfg = O.Cfg(**g["cfg"])
+    sd = O.random_state_dict(cfg, g["head"], seed=g["wseed"])
+    assert abs(_sum(sd.values()) - g["wsum"]) < 1e-6 * g["wsum"], "weight generator drifted"
+    B, La, Lt, R = g["dims"]
+    batch = O.synthetic_batch(cfg, B, La, Lt, R, seed=g["bseed"], ragged=True)
+    assert abs(_sum([batch["img_feats"], batch["input_ids_a"]]) - g["bsum"]) < 1e-6 * g["bsum"]
+    with torch.no_grad():
+        seq, pooled, (txt, vis) = O.rep_forward(sd, cfg, max_tag_length=Lt, **batch)
+    _close(seq, g["seq"]); _close(pooled, g["pooled"]); _close(txt, g["txt"]); _close(vis, g["vis"])
+
+
+def test_retrieval_matches_reference(golden_dir):
+    g = _load(golden_dir, "retrieval_tiny.pt")
+    cfg = O.Cfg(**g["cfg"])
+    sd = O.random_state_dict(cfg, g["head"], seed=g["wseed"])
+    B, La, Lt, R = g["dims"]
+    b = O.synthetic_batch(cfg, B, La, Lt, R, seed=g["bseed"], ragged=True)
+    with torch.no_grad():
+        gt, gi = O.forward_single(sd, cfg, **b)
+        fine = O.retrieval_fine_forward(sd, cfg, b["input_ids_a"], b["token_type_ids_a"], b["attention_mask_a"],
+                                        max_tag_length=Lt, input_ids_b=b["input_ids_b"],
+                                        token_type_ids_b=b["token_type_ids_b"],
+                                        attention_mask_b=b["attention_mask_b"], img_feats=b["img_feats"])
+        total, logits, vsc, itm, labels = O.retrieval_train_forward(
+            sd, cfg, b["input_ids_a"], b["token_type_ids_a"], b["attention_mask_a"], b["input_ids_b"],
+            b["token_type_ids_b"], b["attention_mask_b"], b["img_feats"], max_tag_length=Lt, dice_index=g["dice"])
+    _close(gt, g["global_txt"]); _close(gi, g["global_img"]); _close(fine, g["fine_logits"])
+    _close(total, g["train_total"]); _close(logits, g["train_logits"])
+    assert torch.equal(labels, g["train_labels"])
+    # caching stage 1 and re-running only stage 2 == forward_fine
+    with torch.no_grad():
+        txt, vis, ma, mb = O.stage1(sd, cfg, **b)
+        joint = torch.cat([txt, vis[:, Lt:]], 1)
+        jm = torch.cat([ma, mb[..., Lt:]], -1)
+        seq, _ = O.encoder(sd, "bert.mul_encoder", joint, jm, cfg.num_hidden_layers // 2,
+                           cfg.num_attention_heads, cfg.layer_norm_eps)
+        again = O.linear(O.pooler(sd, "bert.pooler", seq), sd, "classifier")
+    assert torch.equal(again, fine)
+
+
+def test_pretrain_losses_and_grads_match_reference(golden_dir):
+    g = _load(golden_dir, "pretrain_tiny.pt")
+    cfg = O.Cfg(**g["cfg"])
+    sd = {k: v.requires_grad_(True) for k, v in O.random_state_dict(cfg, g["head"], seed=g["wseed"]).items()}
+    B, La, Lt, R = g["dims"]
+    b = O.synthetic_batch(cfg, B, La, Lt, R, seed=g["bseed"], ragged=True, with_labels=True)
+    losses = O.pretrain_forward(sd, cfg, b["input_ids_a"], b["token_type_ids_a"], b["attention_mask_a"],
+                                b["masked_lm_labels_a"], b["input_ids_b"], b["token_type_ids_b"],
+                                b["attention_mask_b"], b["masked_lm_labels_b"], b["img_feats"], max_tag_length=Lt,
+                                img_index=b["img_index"], phrase_index=b["phrase_index"],
+                                dice_index=b["dice_index"], neg_img=b["neg_img"], rand_pos=b["rand_pos"],
+                                rand_neg=b["rand_neg"])
+    assert len(losses) == 6  # run_pretrain_ml.py:536 unpacks exactly six
+    for a, r in zip(losses, g["losses"]):
+        _close(a.detach(), r)
+    losses[0].backward()
+    for k, gr in g["grads"].items():
+        _close(sd[k].grad, gr, tol=5e-5)
+    for k, n in g["grad_norms"].items():
+        assert abs(float(sd[k].grad.norm()) - n) <= 1e-4 * max(1.0, n), k
+    for k in g["no_grad"]:
+        assert sd[k].grad is None
+
+
+def test_vqa_matches_reference(golden_dir):
+    g = _load(golden_dir, "vqa_tiny.pt")
+    cfg = O.Cfg(**g["cfg"])
+    sd = {k: v.requires_grad_(True) for k, v in O.random_state_dict(cfg, g["head"], seed=g["wseed"]).items()}
+    B, La, Lt, R = g["dims"]
+    b = O.synthetic_batch(cfg, B, La, Lt, R, seed=g["bseed"], ragged=True)
+    loss, logits = O.vqa_forward(sd, cfg, b["input_ids_a"], b["token_type_ids_a"], b["attention_mask_a"],
+                                 g["labels"], b["input_ids_b"], b["token_type_ids_b"], b["attention_mask_b"],
+                                 b["img_feats"], max_tag_length=Lt)
+    _close(loss.detach(), g["loss"]); _close(logits.detach(), g["logits"])
+    loss.backward()
+    for k, gr in g["grads"].items():
+        _close(sd[k].grad, gr, tol=5e-5)
+
+
+def test_rank_order_matches_numpy_argsort_reversed(golden_dir):
+    g = _load(golden_dir, "rank_order.pt")
+    assert torch.equal(O.topk_desc(g["sims"], g["sims"].shape[1]), g["order"])
+    # documented tie rule: equal scores -> larger index first
+    t = torch.tensor([[1.0, 3.0, 3.0, 0.5, 3.0]])
+    assert O.topk_desc(t, 5).tolist() == [[4, 2, 1, 0, 3]]
+
+
+def test_adamw_known_answers(golden_dir):
+    g = _load(golden_dir, "adamw_traj.pt")
+    w = torch.tensor([0.1, -0.2, -0.1, 0.7])
+    m, v = torch.zeros(4), torch.zeros(4)
+    for it, lr in enumerate([0.0] + g["lrs"][:-1]):
+        pass
+    # WarmupLinear(warmup=2,t_total=10) on base lr 0.02: lr used at step i is schedule(i)
+    used = [0.02 * x for x in (0.0, 0.5, 1.0, 0.875, 0.75)]
+    for it in range(5):
+        grad = (w - torch.tensor([0.4, 0.2, -0.5, 0.1])) * 2
+        O.adamw_step(w, grad, m, v, it + 1, used[it], weight_decay=0.01)
+        _close(w, g["traj"][it], tol=1e-6)
