@@ -1,0 +1,206 @@
+/* mvptr_b200.h -- C-ABI of the B200-native MVPTR hot path (libmvptr_b200.so).
+ *
+ * The reference (Junction4Nako/mvp_pytorch) has no FFI: its seam is the Python
+ * class layer in oscar/modeling/modeling_vlbert.py.  Each entry point below is
+ * the device-side replacement of one group of ATen calls made by those classes;
+ * the comment above each function names the reference lines it replaces.
+ * Python (mvp_pytorch_b200/_lib.py, ctypes) is the only caller.
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     the name ends in _host; `stream` is a cudaStream_t passed as void*;
+ *   - return 0 on success, a negative MVPTR_ERR_* otherwise; never throw, never
+ *     allocate device memory, never synchronise the device;
+ *   - mvptr_last_error() returns a thread-local message for the last failure;
+ *   - bf16 tensors are row-major with explicit leading dimensions in ELEMENTS.
+ */
+#ifndef MVPTR_B200_H
+#define MVPTR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVPTR_OK 0
+#define MVPTR_ERR_ARG (-1)      /* bad shape / alignment / unsupported option */
+#define MVPTR_ERR_CUDA (-2)     /* CUDA runtime or driver error (see mvptr_last_error) */
+#define MVPTR_ERR_UNSUPPORTED (-3)
+
+#define MVPTR_ABI_VERSION 1
+
+int mvptr_abi_version(void);
+const char* mvptr_last_error(void);
+
+/* ---- dense contraction (tcgen05 + TMEM + TMA) --------------------------------
+ * D[M,N] (+)= epilogue( alpha * A[M,K] . B[N,K]^T )
+ * Replaces every nn.Linear / matmul on the path: modeling_bert.py:293-295 (Q/K/V),
+ * :349 (attention output dense), :395 (intermediate), :408 (output dense), :471
+ * (pooler), :488 (head transform), :514/:531 (vocab / answer decoder);
+ * modeling_vlbert.py:498 (region projection), :525-527 (txt/vis proj, sim_mat);
+ * and their autograd dgrad / wgrad products.
+ *
+ * A and B are bf16.  a_mn / b_mn select the storage of the operand:
+ *   0: "K-major"  -- A is [M rows][K contiguous] with pitch lda  (an activation, an nn.Linear weight)
+ *   1: "MN-major" -- A is [K rows][M contiguous] with pitch lda  (the transposed view, used by wgrad / dgrad)
+ * Pitches must be multiples of 8 elements and base pointers 16-byte aligned.
+ *
+ * Epilogue, applied per element in this order (null pointer = skipped):
+ *   v = alpha*acc;  v += bias[n] (fp32 or bf16 per bias_is_bf16);
+ *   pre_act[m,n] = bf16(v)                       (saved for backward)
+ *   v = act(v)            act: 0 none, 1 erf-GELU, 2 tanh
+ *   v *= gelu'(gelu_grad_of[m,n])                (backward of act=1)
+ *   v = keep(seed, m*N+n) ? v/keep_prob : 0      (dropout, p_drop > 0)
+ *   v += residual[m,n]
+ *   D[m,n] = v   or   D[m,n] += v  (accumulate=1: TMA reduce-add; required when split_k > 1)
+ * D is bf16 (d_is_f32=0) or fp32 (d_is_f32=1).
+ */
+typedef struct {
+  const void* A;
+  const void* B;
+  void* D;
+  int M, N, K;
+  int lda, ldb, ldd;
+  int a_mn, b_mn;
+  int d_is_f32;
+  int accumulate;
+  int split_k; /* <=1: no split */
+  float alpha;
+  const void* bias;
+  int bias_is_bf16;
+  void* pre_act; /* bf16 [M,N], pitch ld_aux */
+  int act;
+  const void* gelu_grad_of; /* bf16 [M,N], pitch ld_aux */
+  const void* residual;     /* bf16 [M,N], pitch ld_aux */
+  int ld_aux;
+  float p_drop;
+  uint32_t seed;
+  int block_n; /* 0 = auto, else 128 or 256 */
+} mvptr_gemm_args;
+
+int mvptr_gemm(const mvptr_gemm_args* args, void* stream);
+
+
+/* ---- embeddings + LayerNorm ---------------------------------------------------
+ * y = dropout(LN(word[ids] + pos[pos_ids or arange(L)] + type[type_ids]))
+ * Replaces BertEmbeddings.forward, modeling_bert.py:262-277 (called twice per forward,
+ * modeling_vlbert.py:479-482).  ids/type_ids/pos_ids int64 [B,L]; tables bf16.
+ * y row (b,t) is written at y + b*y_batch_stride + t*H when y_rows_per_batch > 0
+ * (lets the tag embeddings land directly inside the [B, Lt+R, H] visual sequence,
+ * replacing the torch.cat of modeling_vlbert.py:506); otherwise densely.
+ * pre/mean/rstd (nullable) are saved for backward. */
+int mvptr_embed_ln_fwd(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, const void* word,
+                       const void* pos, const void* type, const void* gamma, const void* beta, void* y,
+                       int y_rows_per_batch, long long y_batch_stride, void* pre, float* mean, float* rstd, int B,
+                       int L, int H, float eps, int vocab, int max_pos, int n_types, float p_drop, uint32_t seed,
+                       void* stream);
+/* Backward of the gather: word rows by fp32 atomics (row padding_idx gets none, as
+ * nn.Embedding(padding_idx=0), modeling_bert.py:253), position/type rows by per-position reduction. */
+int mvptr_embed_bwd(const void* dpre, const int64_t* ids, const int64_t* type_ids, float* dword, float* dpos,
+                    float* dtype, int B, int L, int H, int vocab, int n_types, int padding_idx, void* stream);
+
+/* y = dropout(LN(x)), TF-style eps inside the sqrt.  Replaces BertLayerNorm.forward,
+ * modeling_bert.py:242-246 (9 ATen kernels) at :351, :410, :490 and modeling_vlbert.py:499-503. */
+int mvptr_ln_fwd(const void* x, const void* gamma, const void* beta, void* y, int y_rows_per_batch,
+                 long long y_batch_stride, float* mean, float* rstd, int rows, int H, float eps, float p_drop,
+                 uint32_t seed, void* stream);
+/* LayerNorm backward; also emits dx with the dense-output dropout mask re-applied (dx_drop)
+ * and accumulates dgamma / dbeta / dbias (fp32, atomics). */
+int mvptr_ln_bwd(const void* dy, int dy_rows_per_batch, long long dy_batch_stride, const void* x, const float* mean,
+                 const float* rstd, const void* gamma, void* dx, void* dx_drop, float* dgamma, float* dbeta,
+                 float* dbias, int rows, int H, float out_p_drop, uint32_t out_seed, float in_p_drop,
+                 uint32_t in_seed, void* stream);
+/* out[n] += sum_m x[m,n]  (bias gradient of a dense layer) */
+int mvptr_colsum(const void* x, int ldx, float* out, int M, int N, void* stream);
+
+/* region features [rows,K] fp32|bf16 (any pitch) -> bf16 [rows, ld_dst] zero padded so that the
+ * K=2054 projection (modeling_vlbert.py:498) has a 16-byte aligned pitch for TMA. */
+int mvptr_pad_cast(const void* src, int src_is_f32, long long ld_src, void* dst, int ld_dst, int rows, int K,
+                   void* stream);
+/* additive mask (1-mask)*-10000 of modeling_vlbert.py:430-460 for the sequence
+ * [a(row_a[r], 0..La) | b(row_b[r], b_col0..Lb)] -- also assembles the joint and
+ * hard-negative masks of :542-566, :587 (row_a/row_b nullable = identity). */
+int mvptr_mask_prepare(const int64_t* mask_a, int La, const int64_t* mask_b, int Lb, int b_col0, const int64_t* row_a,
+                       const int64_t* row_b, float* out, int rows, void* stream);
+/* out[r] = cat(a[row_a[r]], b[row_b[r], b_col0:])  -- torch.cat + index_select of
+ * modeling_vlbert.py:542-566 and :586 as one gather; and its backward (fp32 scatter-add). */
+int mvptr_concat_rows(const void* a, int La, const void* b, int Lb, int b_col0, const int64_t* row_a,
+                      const int64_t* row_b, void* out, int rows, int H, void* stream);
+int mvptr_concat_rows_bwd(const void* dout, int La, int Lb, int b_col0, const int64_t* row_a, const int64_t* row_b,
+                          float* da, float* db, int rows, int H, void* stream);
+/* masked_select of MLM rows (modeling_vlbert.py:1232, 1246) and its backward */
+int mvptr_gather_rows(const void* src, const int64_t* idx, void* out, int n, int H, void* stream);
+int mvptr_scatter_rows_add(const void* src, const int64_t* idx, float* dst, int n, int H, void* stream);
+int mvptr_cast_f32_bf16(const float* src, void* dst, size_t n, void* stream);
+int mvptr_add_cast(const float* a, const void* b, void* d, size_t n, void* stream);
+
+/* ---- fused masked attention, head_dim 64, L <= 256 ---------------------------------
+ * ctx = dropout(softmax(q k^T / 8 + maskadd)) v per head, reading the fused QKV projection
+ * [B*L, 3H] and writing head-merged context [B*L, H].  Replaces CaptionBertSelfAttention.forward
+ * modeling_vlbert.py:79-100 (2 bmm + div + add + softmax + dropout + permute) and
+ * transpose_for_scores modeling_bert.py:299-303.  lse [B,nh,L] (nullable) is saved for backward. */
+int mvptr_attn_fwd(const void* qkv, int ld_qkv, const float* maskadd, void* ctx, int ld_ctx, float* lse, int B, int L,
+                   int nh, int H, float p_drop, uint32_t seed, void* stream);
+int mvptr_attn_bwd(const void* qkv, int ld_qkv, const float* maskadd, const void* ctx, const void* dctx, int ld_ctx,
+                   const float* lse, void* dqkv, int B, int L, int nh, int H, float p_drop, uint32_t seed,
+                   void* stream);
+
+/* ---- losses -------------------------------------------------------------------------
+ * CrossEntropyLoss(ignore_index=-1) over fp32 logits [n,V]: modeling_vlbert.py:1229,1235,1249.
+ * fwd accumulates sum of row losses and the valid-row count; bwd writes bf16 dlogits. */
+int mvptr_ce_fwd(const float* logits, int ld, const int64_t* labels, int n, int V, int ignore_index, float* row_lse,
+                 float* loss_sum, float* n_valid, void* stream);
+int mvptr_ce_bwd(const float* logits, int ld, const int64_t* labels, int n, int V, int ignore_index,
+                 const float* row_lse, const float* n_valid, const float* gscale, void* dlogits, int ld_d,
+                 void* stream);
+/* F.normalize(p=2) of modeling_vlbert.py:525-526 */
+int mvptr_l2norm_fwd(const float* x, float* y, void* y16, float* norm, int n, int H, void* stream);
+int mvptr_l2norm_bwd(const float* dy, const float* y, const float* norm, void* dx16, int n, int H, void* stream);
+/* VSC loss (modeling_vlbert.py:1238-1241) fused with the in-batch hardest-negative argmax (:530-534) */
+int mvptr_vsc_fwd(const float* sim, int B, const float* logit_scale, float* row_lse, float* col_lse, float* loss,
+                  int64_t* hard_img, int64_t* hard_txt, void* stream);
+int mvptr_vsc_bwd(const float* sim, int B, const float* logit_scale, const float* row_lse, const float* col_lse,
+                  const float* gscale, float* dsim, float* dlogit_scale, void* stream);
+/* ITM / retrieval classifier [n,H]x[C,H]^T, C small (modeling_vlbert.py:1247, 1680, 1708) + CE (:1251, :1682) */
+int mvptr_small_head_fwd(const void* x, int ldx, const void* W, const void* bias, float* logits, int n, int H, int C,
+                         void* stream);
+int mvptr_small_head_bwd(const float* dlogits, const void* x, int ldx, const void* W, void* dx, int ld_dx, float* dW,
+                         float* db, int n, int H, int C, void* stream);
+int mvptr_small_ce(const float* logits, const int64_t* labels, int n, int C, float* loss, float* dlogits,
+                   const float* gscale, void* stream);
+
+/* ---- optimizer ------------------------------------------------------------------------
+ * AdamW.step of transformers/pytorch_transformers/optimization.py:130-189 over one flat fp32
+ * arena (decay-first layout), also refreshing the bf16 compute copy; grad clipping folded in. */
+int mvptr_adamw(float* p, const float* g, float* m, float* v, void* p16, size_t n, size_t decay_end, float lr,
+                float beta1, float beta2, float eps, float weight_decay, int step, int correct_bias,
+                const float* grad_sumsq, float max_norm, void* stream);
+int mvptr_sumsq(const float* g, size_t n, float* out, void* stream);
+
+/* ---- weakly-supervised phrase grounding (WRA), batched ----------------------------------
+ * Replaces the per-sample Python loops of modeling_vlbert.py:1288-1300 and helpers
+ * mask_slice_and_stack :1502-1508, t2i_sim :1543-1550, get_pos_neg_sims :1553-1596.
+ * seq bf16 [B,Ltot,H]; phrase_index/img_index int64 [B,2]; neg_img int64 [B] (the
+ * random.choice of :1573); rand_pos/rand_neg int64 [B,P] in [0,3) (the torch.randint of
+ * :1548).  Outputs pos/neg mean cosine similarity per sample and the selected region
+ * token of every phrase (sel_*, int32 [B, mvptr_wra_max_phrases()], -1 = none). */
+int mvptr_wra_max_phrases(void);
+int mvptr_wra_fwd(const void* seq, int B, int Ltot, int H, const int64_t* phrase_index, const int64_t* img_index,
+                  const int64_t* neg_img, const int64_t* rand_pos, const int64_t* rand_neg, int P, float* pos_out,
+                  float* neg_out, int* sel_pos, int* sel_neg, void* stream);
+int mvptr_wra_bwd(const void* seq, int B, int Ltot, int H, const int64_t* phrase_index, const int64_t* neg_img,
+                  const int* sel_pos, const int* sel_neg, const float* dpos, const float* dneg, float* dseq,
+                  void* stream);
+/* dx = dy * gelu'(pre): backward of the head-transform activation, modeling_bert.py:489 */
+int mvptr_gelu_bwd(const void* dy, const void* pre, void* dx, size_t n, void* stream);
+/* instance_bce_with_logits, modeling_vlbert.py:878-883 (VQA loss): loss += sum BCE / n */
+int mvptr_bce_fwd(const float* logits, int ld, const float* labels, int n, int C, float* loss, void* stream);
+int mvptr_bce_bwd(const float* logits, int ld, const float* labels, int n, int C, const float* gscale, void* dlogits,
+                  int ld_d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVPTR_B200_H */

@@ -1,0 +1,151 @@
+"""ctypes binding of libmvptr_b200.so (the C-ABI declared in include/mvptr_b200.h).
+
+There is no CPU fallback: importing succeeds without the library so that CPU-only
+tooling can introspect the package, but any compute call raises if the CUDA
+library cannot be loaded.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmvptr_b200.so")
+_lib = None
+
+
+class MvptrError(RuntimeError):
+    pass
+
+
+class GemmArgs(ctypes.Structure):
+    _fields_ = [
+        ("A", ctypes.c_void_p), ("B", ctypes.c_void_p), ("D", ctypes.c_void_p),
+        ("M", ctypes.c_int), ("N", ctypes.c_int), ("K", ctypes.c_int),
+        ("lda", ctypes.c_int), ("ldb", ctypes.c_int), ("ldd", ctypes.c_int),
+        ("a_mn", ctypes.c_int), ("b_mn", ctypes.c_int),
+        ("d_is_f32", ctypes.c_int), ("accumulate", ctypes.c_int), ("split_k", ctypes.c_int),
+        ("alpha", ctypes.c_float),
+        ("bias", ctypes.c_void_p), ("bias_is_bf16", ctypes.c_int),
+        ("pre_act", ctypes.c_void_p), ("act", ctypes.c_int),
+        ("gelu_grad_of", ctypes.c_void_p), ("residual", ctypes.c_void_p), ("ld_aux", ctypes.c_int),
+        ("p_drop", ctypes.c_float), ("seed", ctypes.c_uint32), ("block_n", ctypes.c_int),
+    ]
+
+
+_CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "f": ctypes.c_float,
+       "u": ctypes.c_uint32, "z": ctypes.c_size_t}
+# argument kinds of every entry point declared in include/mvptr_b200.h (stream last)
+SIGNATURES = {
+    "mvptr_gemm": "pp",
+    "mvptr_embed_ln_fwd": "ppppppppp" + "il" + "ppp" + "iiifiii" + "fup",
+    "mvptr_embed_bwd": "pppppp" + "iiiiii" + "p",
+    "mvptr_ln_fwd": "pppp" + "il" + "pp" + "iif" + "fup",
+    "mvptr_ln_bwd": "p" + "il" + "pppp" + "pp" + "ppp" + "ii" + "fufu" + "p",
+    "mvptr_colsum": "pipiip",
+    "mvptr_pad_cast": "pilpiiip",
+    "mvptr_mask_prepare": "pipiipppip",
+    "mvptr_concat_rows": "pipiipppiip",
+    "mvptr_concat_rows_bwd": "piiipppp" + "iip",
+    "mvptr_gather_rows": "pppiip",
+    "mvptr_scatter_rows_add": "pppiip",
+    "mvptr_cast_f32_bf16": "ppzp",
+    "mvptr_add_cast": "pppzp",
+    "mvptr_attn_fwd": "pippip" + "iiii" + "fup",
+    "mvptr_attn_bwd": "pipppipp" + "iiii" + "fup",
+    "mvptr_ce_fwd": "pipiiipppp",
+    "mvptr_ce_bwd": "pipiii" + "ppp" + "pip",
+    "mvptr_l2norm_fwd": "ppppiip",
+    "mvptr_l2norm_bwd": "ppppiip",
+    "mvptr_vsc_fwd": "pipppppp" + "p",
+    "mvptr_vsc_bwd": "pippppppp",
+    "mvptr_small_head_fwd": "pipppiiip",
+    "mvptr_small_head_bwd": "ppippippiiip",
+    "mvptr_small_ce": "ppiipppp",
+    "mvptr_adamw": "ppppp" + "zz" + "fffff" + "ii" + "pf" + "p",
+    "mvptr_sumsq": "pzpp",
+    "mvptr_wra_fwd": "piiippppp" + "ipppp" + "p",
+    "mvptr_wra_bwd": "piiipppppp" + "p" + "p",
+    "mvptr_gelu_bwd": "pppzp",
+    "mvptr_bce_fwd": "pipiipp",
+    "mvptr_bce_bwd": "pipiippip",
+}
+
+
+def call(name, *args):
+    """Call an entry point; torch tensors are passed as device pointers, None as NULL,
+    and the current CUDA stream is appended."""
+    L = lib()
+    conv = []
+    for a in args:
+        if a is None:
+            conv.append(None)
+        elif isinstance(a, torch.Tensor):
+            conv.append(a.data_ptr())
+        else:
+            conv.append(a)
+    conv.append(torch.cuda.current_stream().cuda_stream)
+    rc = getattr(L, name)(*conv)
+    if rc != 0:
+        raise MvptrError(f"{name} failed (rc={rc}): {L.mvptr_last_error().decode()}")
+
+
+def lib():
+    """The loaded shared library; raises loudly when it is missing (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MvptrError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). mvp_pytorch_b200 has no CPU or eager fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        L.mvptr_last_error.restype = ctypes.c_char_p
+        L.mvptr_abi_version.restype = ctypes.c_int
+        for name, spec in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError here = header/library mismatch: fail loudly
+            fn.argtypes = [_CT[c] for c in spec]
+            fn.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise MvptrError(f"{what} failed (rc={rc}): {lib().mvptr_last_error().decode()}")
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+ACT = {None: 0, "none": 0, "gelu": 1, "tanh": 2}
+
+
+def gemm(A, B, D, M, N, K, *, lda, ldb, ldd, a_mn=False, b_mn=False, accumulate=False, split_k=1, alpha=1.0,
+         bias=None, pre_act=None, act=None, gelu_grad_of=None, residual=None, ld_aux=0, p_drop=0.0, seed=0,
+         block_n=0):
+    """D[M,N] (+)= epilogue(alpha * A . B^T); see include/mvptr_b200.h."""
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
+    assert D.dtype in (torch.bfloat16, torch.float32)
+    g = GemmArgs()
+    g.A, g.B, g.D = A.data_ptr(), B.data_ptr(), D.data_ptr()
+    g.M, g.N, g.K = M, N, K
+    g.lda, g.ldb, g.ldd = lda, ldb, ldd
+    g.a_mn, g.b_mn = int(a_mn), int(b_mn)
+    g.d_is_f32 = int(D.dtype == torch.float32)
+    g.accumulate, g.split_k, g.alpha = int(accumulate), int(split_k), float(alpha)
+    if bias is not None:
+        g.bias, g.bias_is_bf16 = bias.data_ptr(), int(bias.dtype == torch.bfloat16)
+        assert bias.dtype in (torch.bfloat16, torch.float32)
+    for name, t in (("pre_act", pre_act), ("gelu_grad_of", gelu_grad_of), ("residual", residual)):
+        if t is not None:
+            assert t.dtype == torch.bfloat16
+            setattr(g, name, t.data_ptr())
+    g.act = ACT[act]
+    g.ld_aux, g.p_drop, g.seed, g.block_n = ld_aux, float(p_drop), int(seed) & 0xFFFFFFFF, block_n
+    check(lib().mvptr_gemm(ctypes.byref(g), stream_ptr()), "mvptr_gemm")
+    return D

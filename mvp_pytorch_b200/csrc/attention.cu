@@ -1,0 +1,492 @@
+// Fused masked multi-head attention, head_dim 64, sequence length <= 256
+// (modeling_vlbert.py:63-103 + transpose_for_scores modeling_bert.py:299-303).
+//
+// One CTA per (batch, head).  Whole K/V (and Q) of the head live in shared memory, so the
+// softmax is single pass (no online rescale).  Scores never touch HBM.  Reads Q/K/V
+// straight out of the fused QKV projection [B*L, 3H] and writes the context already
+// head-merged [B*L, H], so neither transpose_for_scores nor permute/contiguous exist.
+// The additive mask is the reference's (1-mask)*-10000 per key (any 0/1 pattern, i.e.
+// the two or three disjoint valid segments of the joint sequence).
+//
+// Tensor-core path: mma.sync m16n8k16 bf16 (legacy HMMA).  Attention is 2-4 % of the
+// path's FLOPs; the tcgen05 budget went to the GEMMs first.
+//
+// Backward is recompute-based (flash style): pass 1 (warp owns 16 queries) produces dQ,
+// pass 2 (warp owns 16 keys) produces dK, dV.  No atomics, no [L,L] buffers.
+#include "common.cuh"
+
+namespace mvptr {
+namespace attn {
+
+constexpr int D = 64;        // head dim
+constexpr int LDS = D + 8;   // padded smem row (144 B): conflict-free ldmatrix
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// load `rows` x 64 bf16 (row pitch ld) into padded smem, zero-filling rows >= valid
+__device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, int ld, int rows, int valid) {
+  for (int i = threadIdx.x; i < rows * 8; i += blockDim.x) {
+    const int r = i >> 3, c = i & 7;
+    cp_async16(smem_u32(dst + r * LDS + c * 8), src + (size_t)(r < valid ? r : 0) * ld + c * 8, r < valid);
+  }
+}
+
+// A fragments (16 x 64) of rows [row0, row0+16) of a padded smem tile
+__device__ __forceinline__ void load_a_frags(const bf16* tile, int row0, int lane, uint32_t (&a)[4][4]) {
+  const int r = row0 + (lane & 7) + 8 * ((lane >> 3) & 1);
+  const int c = 8 * (lane >> 4);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) ldsm_x4(smem_u32(tile + r * LDS + kk * 16 + c), a[kk][0], a[kk][1], a[kk][2], a[kk][3]);
+}
+
+// acc[2 n-tiles] += A(16x64, regs) . T[n0..n0+16, 0..64]^T   where T is a [rows][64] smem tile
+// (the "non-transposed B" case: S = Q K^T, dP = dO V^T, S^T = K Q^T, dP^T = V dO^T)
+__device__ __forceinline__ void mma_a_rowsT(float (&acc)[2][4], const uint32_t (&a)[4][4], const bf16* tile, int n0,
+                                            int lane) {
+  const int r = n0 + (lane & 7) + 8 * (lane >> 4);
+  const int c = 8 * ((lane >> 3) & 1);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t b0, b1, b2, b3;
+    ldsm_x4(smem_u32(tile + r * LDS + kk * 16 + c), b0, b1, b2, b3);
+    mma16816(acc[0], a[kk], b0, b1);
+    mma16816(acc[1], a[kk], b2, b3);
+  }
+}
+
+// out[8 d-tiles] += P(16 x 16, regs) . T[k0..k0+16, 0..64]   (the "transposed B" case:
+// O = P V, dQ = dS K, dV = P^T dO, dK = dS^T Q)
+__device__ __forceinline__ void mma_p_rows(float (&out)[8][4], const uint32_t (&p)[4], const bf16* tile, int k0,
+                                           int lane) {
+  const int r = k0 + (lane & 7) + 8 * ((lane >> 3) & 1);
+#pragma unroll
+  for (int dp = 0; dp < 4; ++dp) {
+    uint32_t b0, b1, b2, b3;
+    ldsm_x4_t(smem_u32(tile + r * LDS + dp * 16 + 8 * (lane >> 4)), b0, b1, b2, b3);
+    mma16816(out[2 * dp], p, b0, b1);
+    mma16816(out[2 * dp + 1], p, b2, b3);
+  }
+}
+
+struct FwdParams {
+  const bf16* qkv;  // [B*L, ld_qkv], q | k | v each H wide
+  int ld_qkv;
+  const float* maskadd;  // [B, L]
+  bf16* ctx;             // [B*L, ld_ctx]
+  int ld_ctx;
+  float* lse;  // [B, nh, L] or null
+  int B, L, nh, H;
+  float scale;
+  uint32_t keep_thr;
+  float inv_keep;
+  uint32_t seed;
+};
+
+// NT = number of 8-key tiles covered (keys padded to NT*8, NT even)
+template <int NT>
+__global__ void __launch_bounds__(256) attn_fwd_kernel(const FwdParams p) {
+  constexpr int LP = NT * 8;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  bf16* Qs = reinterpret_cast<bf16*>(smem_attn);
+  bf16* Ks = Qs + LP * LDS;
+  bf16* Vs = Ks + LP * LDS;
+  float* Ms = reinterpret_cast<float*>(Vs + LP * LDS);
+  const int b = blockIdx.y, h = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int L = p.L;
+  const bf16* base = p.qkv + (size_t)b * L * p.ld_qkv + h * D;
+  load_tile(Qs, base, p.ld_qkv, LP, L);
+  load_tile(Ks, base + p.H, p.ld_qkv, LP, L);
+  load_tile(Vs, base + 2 * p.H, p.ld_qkv, LP, L);
+  for (int i = threadIdx.x; i < LP; i += blockDim.x) Ms[i] = i < L ? p.maskadd[(size_t)b * L + i] : -INFINITY;
+  cp_async_wait_all();
+  __syncthreads();
+
+  const int g = lane >> 2, t = lane & 3;
+  const int n_qtiles = (L + 15) >> 4;
+  const float sc = p.scale * kLog2e;
+  for (int qt = warp; qt < n_qtiles; qt += nwarps) {
+    uint32_t qa[4][4];
+    load_a_frags(Qs, qt * 16, lane, qa);
+    float s[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NT; j += 2) mma_a_rowsT(*reinterpret_cast<float(*)[2][4]>(&s[j]), qa, Ks, j * 8, lane);
+    // scores -> log2 domain: (qk/sqrt(d) + mask) * log2e
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const float m0 = Ms[j * 8 + 2 * t] * kLog2e, m1 = Ms[j * 8 + 2 * t + 1] * kLog2e;
+      s[j][0] = s[j][0] * sc + m0;
+      s[j][1] = s[j][1] * sc + m1;
+      s[j][2] = s[j][2] * sc + m0;
+      s[j][3] = s[j][3] * sc + m1;
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      s[j][0] = exp2f(s[j][0] - mx0);
+      s[j][1] = exp2f(s[j][1] - mx0);
+      s[j][2] = exp2f(s[j][2] - mx1);
+      s[j][3] = exp2f(s[j][3] - mx1);
+      sum0 += s[j][0] + s[j][1];
+      sum1 += s[j][2] + s[j][3];
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+    const int q0 = qt * 16 + g, q1 = q0 + 8;
+    if (p.lse && t == 0) {
+      float* l = p.lse + ((size_t)b * p.nh + h) * L;
+      if (q0 < L) l[q0] = (mx0 + log2f(sum0)) / kLog2e;
+      if (q1 < L) l[q1] = (mx1 + log2f(sum1)) / kLog2e;
+    }
+    const bool drop = p.keep_thr != 0xffffffffu;
+    const uint32_t rbase0 = (((uint32_t)b * p.nh + h) * L + q0) * L, rbase1 = (((uint32_t)b * p.nh + h) * L + q1) * L;
+    float o[8][4];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < NT / 2; ++kk) {
+      float pv[8];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int j = 2 * kk + u;
+        pv[4 * u + 0] = s[j][0] * inv0;
+        pv[4 * u + 1] = s[j][1] * inv0;
+        pv[4 * u + 2] = s[j][2] * inv1;
+        pv[4 * u + 3] = s[j][3] * inv1;
+        if (drop) {
+          const uint32_t k = j * 8 + 2 * t;
+          pv[4 * u + 0] = dropout_keep(p.seed, rbase0 + k, p.keep_thr) ? pv[4 * u + 0] * p.inv_keep : 0.f;
+          pv[4 * u + 1] = dropout_keep(p.seed, rbase0 + k + 1, p.keep_thr) ? pv[4 * u + 1] * p.inv_keep : 0.f;
+          pv[4 * u + 2] = dropout_keep(p.seed, rbase1 + k, p.keep_thr) ? pv[4 * u + 2] * p.inv_keep : 0.f;
+          pv[4 * u + 3] = dropout_keep(p.seed, rbase1 + k + 1, p.keep_thr) ? pv[4 * u + 3] * p.inv_keep : 0.f;
+        }
+      }
+      const uint32_t pa[4] = {pack2(pv[0], pv[1]), pack2(pv[2], pv[3]), pack2(pv[4], pv[5]), pack2(pv[6], pv[7])};
+      mma_p_rows(o, pa, Vs, kk * 16, lane);
+    }
+    // stage the 16x64 output tile in this warp's own (already consumed) Q rows, then store 16-byte rows
+    __syncwarp();
+    bf16* stg = Qs + qt * 16 * LDS;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      *reinterpret_cast<uint32_t*>(stg + g * LDS + d * 8 + 2 * t) = pack2(o[d][0], o[d][1]);
+      *reinterpret_cast<uint32_t*>(stg + (g + 8) * LDS + d * 8 + 2 * t) = pack2(o[d][2], o[d][3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int id = lane + 32 * i, r = id >> 3, c = id & 7;
+      const int q = qt * 16 + r;
+      if (q < L)
+        *reinterpret_cast<uint4*>(p.ctx + ((size_t)b * L + q) * p.ld_ctx + h * D + c * 8) =
+            *reinterpret_cast<const uint4*>(stg + r * LDS + c * 8);
+    }
+  }
+}
+
+struct BwdParams {
+  const bf16* qkv;
+  int ld_qkv;
+  const float* maskadd;
+  const bf16* ctx;   // forward output O  [B*L, ld_ctx]
+  const bf16* dctx;  // dO               [B*L, ld_ctx]
+  int ld_ctx;
+  const float* lse;  // [B, nh, L]
+  bf16* dqkv;        // [B*L, ld_qkv]
+  int B, L, nh, H;
+  float scale;
+  uint32_t keep_thr;
+  float inv_keep;
+  uint32_t seed;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(256) attn_bwd_kernel(const BwdParams p) {
+  constexpr int LP = NT * 8;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  bf16* Qs = reinterpret_cast<bf16*>(smem_attn);
+  bf16* Ks = Qs + LP * LDS;
+  bf16* Vs = Ks + LP * LDS;
+  bf16* dOs = Vs + LP * LDS;
+  bf16* Stg = dOs + LP * LDS;                              // [8 warps][16][LDS]
+  float* Ms = reinterpret_cast<float*>(Stg + 8 * 16 * LDS);  // additive mask, log2 domain
+  float* Ls = Ms + LP;                                       // lse, log2 domain (+inf for padded queries)
+  float* Ds = Ls + LP;                                       // rowsum(dO * O)
+  const int b = blockIdx.y, h = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int L = p.L;
+  const size_t row0 = (size_t)b * L;
+  const bf16* base = p.qkv + row0 * p.ld_qkv + h * D;
+  load_tile(Qs, base, p.ld_qkv, LP, L);
+  load_tile(Ks, base + p.H, p.ld_qkv, LP, L);
+  load_tile(Vs, base + 2 * p.H, p.ld_qkv, LP, L);
+  load_tile(dOs, p.dctx + row0 * p.ld_ctx + h * D, p.ld_ctx, LP, L);
+  const float* lse = p.lse + ((size_t)b * p.nh + h) * L;
+  for (int i = threadIdx.x; i < LP; i += blockDim.x) {
+    Ms[i] = i < L ? p.maskadd[row0 + i] * kLog2e : -INFINITY;
+    Ls[i] = i < L ? lse[i] * kLog2e : INFINITY;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  // D[q] = sum_d dO[q,d] * O[q,d]
+  for (int q = threadIdx.x; q < LP; q += blockDim.x) {
+    float acc = 0.f;
+    if (q < L) {
+      const bf16* orow = p.ctx + (row0 + q) * p.ld_ctx + h * D;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float ov[8], dv[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(orow + c * 8), ov);
+        unpack8(*reinterpret_cast<const bf16x8*>(dOs + q * LDS + c * 8), dv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += ov[j] * dv[j];
+      }
+    }
+    Ds[q] = acc;
+  }
+  __syncthreads();
+
+  const int g = lane >> 2, t = lane & 3;
+  const int n_tiles = (L + 15) >> 4;
+  const float sc = p.scale * kLog2e;
+  const bool drop = p.keep_thr != 0xffffffffu;
+  const uint32_t hb = ((uint32_t)b * p.nh + h) * L;
+  bf16* stg = Stg + warp * 16 * LDS;
+
+  // ---------------- pass 1: dQ (warp owns 16 queries, loops over key pairs) ----------------
+  for (int qt = warp; qt < n_tiles; qt += nwarps) {
+    uint32_t qa[4][4], da[4][4];
+    load_a_frags(Qs, qt * 16, lane, qa);
+    load_a_frags(dOs, qt * 16, lane, da);
+    const int q0 = qt * 16 + g, q1 = q0 + 8;
+    const float l0 = Ls[q0], l1 = Ls[q1], d0 = Ds[q0], d1 = Ds[q1];
+    float dq[8][4];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) dq[d][0] = dq[d][1] = dq[d][2] = dq[d][3] = 0.f;
+    for (int kp = 0; kp < NT / 2; ++kp) {
+      if (kp * 16 >= L) break;
+      float s[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, dp[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+      mma_a_rowsT(s, qa, Ks, kp * 16, lane);
+      mma_a_rowsT(dp, da, Vs, kp * 16, lane);
+      float ds[8];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int k = kp * 16 + u * 8 + 2 * t;
+        const float m0 = Ms[k], m1 = Ms[k + 1];
+        float pr[4] = {exp2f(s[u][0] * sc + m0 - l0), exp2f(s[u][1] * sc + m1 - l0), exp2f(s[u][2] * sc + m0 - l1),
+                       exp2f(s[u][3] * sc + m1 - l1)};
+        float dpp[4] = {dp[u][0], dp[u][1], dp[u][2], dp[u][3]};
+        if (drop) {
+          dpp[0] = dropout_keep(p.seed, (hb + q0) * L + k, p.keep_thr) ? dpp[0] * p.inv_keep : 0.f;
+          dpp[1] = dropout_keep(p.seed, (hb + q0) * L + k + 1, p.keep_thr) ? dpp[1] * p.inv_keep : 0.f;
+          dpp[2] = dropout_keep(p.seed, (hb + q1) * L + k, p.keep_thr) ? dpp[2] * p.inv_keep : 0.f;
+          dpp[3] = dropout_keep(p.seed, (hb + q1) * L + k + 1, p.keep_thr) ? dpp[3] * p.inv_keep : 0.f;
+        }
+        ds[4 * u + 0] = pr[0] * (dpp[0] - d0);
+        ds[4 * u + 1] = pr[1] * (dpp[1] - d0);
+        ds[4 * u + 2] = pr[2] * (dpp[2] - d1);
+        ds[4 * u + 3] = pr[3] * (dpp[3] - d1);
+      }
+      const uint32_t pa[4] = {pack2(ds[0], ds[1]), pack2(ds[2], ds[3]), pack2(ds[4], ds[5]), pack2(ds[6], ds[7])};
+      mma_p_rows(dq, pa, Ks, kp * 16, lane);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      *reinterpret_cast<uint32_t*>(stg + g * LDS + d * 8 + 2 * t) = pack2(dq[d][0] * p.scale, dq[d][1] * p.scale);
+      *reinterpret_cast<uint32_t*>(stg + (g + 8) * LDS + d * 8 + 2 * t) = pack2(dq[d][2] * p.scale, dq[d][3] * p.scale);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int id = lane + 32 * i, r = id >> 3, c = id & 7;
+      const int q = qt * 16 + r;
+      if (q < L)
+        *reinterpret_cast<uint4*>(p.dqkv + (row0 + q) * p.ld_qkv + h * D + c * 8) =
+            *reinterpret_cast<const uint4*>(stg + r * LDS + c * 8);
+    }
+  }
+
+  // ---------------- pass 2: dK, dV (warp owns 16 keys, loops over query pairs) ----------------
+  for (int kt = warp; kt < n_tiles; kt += nwarps) {
+    uint32_t ka[4][4], va[4][4];
+    load_a_frags(Ks, kt * 16, lane, ka);
+    load_a_frags(Vs, kt * 16, lane, va);
+    const int k0 = kt * 16 + g, k1 = k0 + 8;
+    const float m0 = Ms[k0], m1 = Ms[k1];
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      dk[d][0] = dk[d][1] = dk[d][2] = dk[d][3] = 0.f;
+      dv[d][0] = dv[d][1] = dv[d][2] = dv[d][3] = 0.f;
+    }
+    for (int qp = 0; qp < NT / 2; ++qp) {
+      if (qp * 16 >= L) break;
+      float s[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, dp[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+      mma_a_rowsT(s, ka, Qs, qp * 16, lane);    // S^T[key, query]
+      mma_a_rowsT(dp, va, dOs, qp * 16, lane);  // dP^T[key, query]
+      float pt[8], ds[8];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int q = qp * 16 + u * 8 + 2 * t;
+        const float la = Ls[q], lb = Ls[q + 1], da_ = Ds[q], db_ = Ds[q + 1];
+        float pr[4] = {exp2f(s[u][0] * sc + m0 - la), exp2f(s[u][1] * sc + m0 - lb), exp2f(s[u][2] * sc + m1 - la),
+                       exp2f(s[u][3] * sc + m1 - lb)};
+        float dpp[4] = {dp[u][0], dp[u][1], dp[u][2], dp[u][3]};
+        float pd[4] = {pr[0], pr[1], pr[2], pr[3]};
+        if (drop) {
+          const bool kp0 = dropout_keep(p.seed, (hb + q) * L + k0, p.keep_thr);
+          const bool kp1 = dropout_keep(p.seed, (hb + q + 1) * L + k0, p.keep_thr);
+          const bool kp2 = dropout_keep(p.seed, (hb + q) * L + k1, p.keep_thr);
+          const bool kp3 = dropout_keep(p.seed, (hb + q + 1) * L + k1, p.keep_thr);
+          dpp[0] = kp0 ? dpp[0] * p.inv_keep : 0.f; pd[0] = kp0 ? pd[0] * p.inv_keep : 0.f;
+          dpp[1] = kp1 ? dpp[1] * p.inv_keep : 0.f; pd[1] = kp1 ? pd[1] * p.inv_keep : 0.f;
+          dpp[2] = kp2 ? dpp[2] * p.inv_keep : 0.f; pd[2] = kp2 ? pd[2] * p.inv_keep : 0.f;
+          dpp[3] = kp3 ? dpp[3] * p.inv_keep : 0.f; pd[3] = kp3 ? pd[3] * p.inv_keep : 0.f;
+        }
+        pt[4 * u + 0] = pd[0]; pt[4 * u + 1] = pd[1]; pt[4 * u + 2] = pd[2]; pt[4 * u + 3] = pd[3];
+        ds[4 * u + 0] = pr[0] * (dpp[0] - da_);
+        ds[4 * u + 1] = pr[1] * (dpp[1] - db_);
+        ds[4 * u + 2] = pr[2] * (dpp[2] - da_);
+        ds[4 * u + 3] = pr[3] * (dpp[3] - db_);
+      }
+      const uint32_t pa[4] = {pack2(pt[0], pt[1]), pack2(pt[2], pt[3]), pack2(pt[4], pt[5]), pack2(pt[6], pt[7])};
+      const uint32_t sa[4] = {pack2(ds[0], ds[1]), pack2(ds[2], ds[3]), pack2(ds[4], ds[5]), pack2(ds[6], ds[7])};
+      mma_p_rows(dv, pa, dOs, qp * 16, lane);
+      mma_p_rows(dk, sa, Qs, qp * 16, lane);
+    }
+    // dK then dV through the per-warp staging tile
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      __syncwarp();
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        const float f = which == 0 ? p.scale : 1.f;
+        const float(&src)[4] = which == 0 ? dk[d] : dv[d];
+        *reinterpret_cast<uint32_t*>(stg + g * LDS + d * 8 + 2 * t) = pack2(src[0] * f, src[1] * f);
+        *reinterpret_cast<uint32_t*>(stg + (g + 8) * LDS + d * 8 + 2 * t) = pack2(src[2] * f, src[3] * f);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int id = lane + 32 * i, r = id >> 3, c = id & 7;
+        const int k = kt * 16 + r;
+        if (k < L)
+          *reinterpret_cast<uint4*>(p.dqkv + (row0 + k) * p.ld_qkv + (which + 1) * p.H + h * D + c * 8) =
+              *reinterpret_cast<const uint4*>(stg + r * LDS + c * 8);
+      }
+    }
+  }
+}
+
+template <int NT>
+static int launch_fwd(const FwdParams& p, cudaStream_t s) {
+  constexpr int LP = NT * 8;
+  constexpr int smem = 3 * LP * LDS * 2 + LP * 4;
+  auto kern = attn_fwd_kernel<NT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) MVPTR_FAIL(MVPTR_ERR_CUDA, "attn fwd smem attr: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  int warps = (p.L + 15) / 16;
+  if (warps > 8) warps = (warps + 1) / 2 > 8 ? 8 : (warps + 1) / 2;
+  kern<<<dim3(p.nh, p.B), warps * 32, smem, s>>>(p);
+  MVPTR_CHECK_LAUNCH("attn_fwd");
+  return 0;
+}
+template <int NT>
+static int launch_bwd(const BwdParams& p, cudaStream_t s) {
+  constexpr int LP = NT * 8;
+  constexpr int smem = 4 * LP * LDS * 2 + 8 * 16 * LDS * 2 + 3 * LP * 4;
+  auto kern = attn_bwd_kernel<NT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) MVPTR_FAIL(MVPTR_ERR_CUDA, "attn bwd smem attr: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  int warps = (p.L + 15) / 16;
+  if (warps > 8) warps = (warps + 1) / 2 > 8 ? 8 : (warps + 1) / 2;
+  kern<<<dim3(p.nh, p.B), warps * 32, smem, s>>>(p);
+  MVPTR_CHECK_LAUNCH("attn_bwd");
+  return 0;
+}
+
+}  // namespace attn
+}  // namespace mvptr
+
+using namespace mvptr;
+
+static int attn_check(int B, int L, int nh, int H, int ld_qkv, int ld_ctx) {
+  if (H != nh * attn::D) MVPTR_FAIL(MVPTR_ERR_UNSUPPORTED, "attention: head size must be 64 (hidden %d, heads %d)", H, nh);
+  if (L <= 0 || L > 256) MVPTR_FAIL(MVPTR_ERR_UNSUPPORTED, "attention: sequence length %d unsupported (1..256)", L);
+  if ((ld_qkv & 7) || (ld_ctx & 7)) MVPTR_FAIL(MVPTR_ERR_ARG, "attention: pitches must be multiples of 8");
+  if (B <= 0) MVPTR_FAIL(MVPTR_ERR_ARG, "attention: empty batch");
+  return 0;
+}
+
+extern "C" int mvptr_attn_fwd(const void* qkv, int ld_qkv, const float* maskadd, void* ctx, int ld_ctx, float* lse,
+                              int B, int L, int nh, int H, float p_drop, uint32_t seed, void* stream) {
+  if (int rc = attn_check(B, L, nh, H, ld_qkv, ld_ctx)) return rc;
+  attn::FwdParams p{(const bf16*)qkv, ld_qkv, maskadd, (bf16*)ctx, ld_ctx, lse, B, L, nh, H, 0.125f,
+                    keep_threshold(p_drop), p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f, seed};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (L <= 64) return attn::launch_fwd<8>(p, s);
+  if (L <= 96) return attn::launch_fwd<12>(p, s);
+  if (L <= 128) return attn::launch_fwd<16>(p, s);
+  if (L <= 192) return attn::launch_fwd<24>(p, s);
+  return attn::launch_fwd<32>(p, s);
+}
+
+extern "C" int mvptr_attn_bwd(const void* qkv, int ld_qkv, const float* maskadd, const void* ctx, const void* dctx,
+                              int ld_ctx, const float* lse, void* dqkv, int B, int L, int nh, int H, float p_drop,
+                              uint32_t seed, void* stream) {
+  if (int rc = attn_check(B, L, nh, H, ld_qkv, ld_ctx)) return rc;
+  attn::BwdParams p{(const bf16*)qkv, ld_qkv, maskadd, (const bf16*)ctx, (const bf16*)dctx, ld_ctx, lse, (bf16*)dqkv,
+                    B, L, nh, H, 0.125f, keep_threshold(p_drop), p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f, seed};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (L <= 64) return attn::launch_bwd<8>(p, s);
+  if (L <= 96) return attn::launch_bwd<12>(p, s);
+  if (L <= 128) return attn::launch_bwd<16>(p, s);
+  if (L <= 192) return attn::launch_bwd<24>(p, s);
+  return attn::launch_bwd<32>(p, s);
+}

@@ -1,0 +1,94 @@
+// Shared device/host helpers for the mvptr_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mvptr_b200.h"
+
+namespace mvptr {
+
+// ---- error plumbing: C-ABI entry points return 0 / negative code, never throw ----
+void set_last_error(const char* fmt, ...);
+#define MVPTR_FAIL(code, ...)            \
+  do {                                   \
+    ::mvptr::set_last_error(__VA_ARGS__); \
+    return (code);                       \
+  } while (0)
+#define MVPTR_CHECK_LAUNCH(name)                                                          \
+  do {                                                                                    \
+    cudaError_t e__ = cudaGetLastError();                                                 \
+    if (e__ != cudaSuccess) MVPTR_FAIL(MVPTR_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+typedef __nv_bfloat16 bf16;
+typedef __nv_bfloat162 bf162;
+
+constexpr int kNumSMs = 148;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// 8 bf16 <-> 8 float through one 16-byte access
+struct alignas(16) bf16x8 {
+  bf162 v[4];
+};
+__device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float* f) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  bf162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// exact-erf GELU (reference modeling_bert.py:142-148) and its derivative
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// Stateless per-element dropout RNG: a 32-bit integer hash of (site seed, element
+// index).  Layout independent, so forward epilogues and backward kernels regenerate
+// the same keep mask without storing it.
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ bool dropout_keep(uint32_t seed, uint32_t idx, uint32_t keep_thr) {
+  // keep_thr = floor(keep_prob * 2^32); keep iff hash < thr
+  return hash32(idx * 0x9E3779B9u + seed) < keep_thr;
+}
+static inline uint32_t keep_threshold(float p_drop) {
+  double kp = 1.0 - (double)p_drop;
+  if (kp >= 1.0) return 0xffffffffu;
+  return (uint32_t)(kp * 4294967296.0);
+}
+
+}  // namespace mvptr

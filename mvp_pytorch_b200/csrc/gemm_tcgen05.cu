@@ -1,0 +1,537 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:
+//   TMA (cp.async.bulk.tensor, 128B swizzle) -> smem ring -> tcgen05.mma (UMMA 128xBNx16,
+//   fp32 accumulators in TMEM, two accumulator stages) -> tcgen05.ld epilogue ->
+//   swizzled smem slabs -> TMA store / TMA reduce-add.
+// One CTA per SM, 8 warps: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator,
+// 4..7 = epilogue (warp%4 selects the TMEM lane quarter).
+// Operands may be K-major or MN-major (transposed views for dgrad/wgrad) -- both use
+// the canonical SWIZZLE_128B UMMA layouts, so no transposed copies are ever made.
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace mvptr {
+namespace gemm {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 256;
+constexpr int kAccStages = 2;
+constexpr int kSlabBytes = 4096;  // 32 rows x 128 B, one TMA-store box
+
+struct Params {
+  int M, N, K;
+  int m_tiles, n_tiles, num_tiles;
+  int kb_total, kb_per_split, split_k;
+  int accumulate;
+  float alpha;
+  const void* bias;
+  int bias_is_bf16;
+  bf16* pre_act;
+  int act;
+  const bf16* gelu_grad_of;
+  const bf16* residual;
+  int ld_aux;
+  float inv_keep;
+  uint32_t keep_thr;
+  uint32_t seed;
+  int use_dropout;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---------------- mbarrier ----------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// ---------------- TMA ----------------
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+// ---------------- tcgen05 ----------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, SWIZZLE_128B (cute/arch/mma_sm100_desc.hpp bit layout):
+// [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout=2.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int kABytes = BM * BK * 2;   // 16 KB
+  static constexpr int kBBytes = BN * BK * 2;   // 16/32 KB
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kOutBytes = 4 * 2 * kSlabBytes;  // 4 epilogue warps x 2 slabs
+  static constexpr int kBarBytes = 256;
+  static constexpr int kTotal = kStages * kStageBytes + kOutBytes + kBarBytes + 1024;  // + alignment slack
+};
+
+template <int BN, bool A_MN, bool B_MN, bool F32OUT>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmD, const Params p) {
+  using L = SmemLayout<BN>;
+  constexpr int kStages = L::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* out_stage = smem + kStages * L::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + L::kOutBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kAccStages);
+
+  const uint32_t full_bar = smem_u32(bars);
+  const uint32_t empty_bar = smem_u32(bars + kStages);
+  const uint32_t tfull_bar = smem_u32(bars + 2 * kStages);
+  const uint32_t tempty_bar = smem_u32(bars + 2 * kStages + kAccStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmD) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(full_bar + 8 * i, 1);
+      mbar_init(empty_bar + 8 * i, 1);
+    }
+    for (int i = 0; i < kAccStages; ++i) {
+      mbar_init(tfull_bar + 8 * i, 1);
+      mbar_init(tempty_bar + 8 * i, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)(kAccStages * BN))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_mn = p.m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int split = t / tiles_mn;
+        const int mn = t - split * tiles_mn;
+        const int m_blk = mn / p.n_tiles, n_blk = mn - m_blk * p.n_tiles;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+          const uint32_t fb = full_bar + 8 * stage;
+          mbar_expect_tx(fb, L::kStageBytes);
+          if constexpr (!A_MN) {
+            tma_load_2d(sa, &tmA, fb, kb * BK, m_blk * BM);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * (BK * 128), &tmA, fb, m_blk * BM + c * 64, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sb, &tmB, fb, kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * (BK * 128), &tmB, fb, n_blk * BN + c * 64, kb * BK);
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN, A_MN, B_MN);
+      // K-major: 8-row groups 1024 B apart (SBO); MN-major: 8 k-rows per 1024 B (SBO),
+      // 64-wide MN chunks BK*128 B apart (LBO).
+      constexpr uint32_t a_lbo = A_MN ? BK * 128 : 16, a_sbo = 1024, a_kstep = A_MN ? UMMA_K * 128 : UMMA_K * 2;
+      constexpr uint32_t b_lbo = B_MN ? BK * 128 : 16, b_sbo = 1024, b_kstep = B_MN ? UMMA_K * 128 : UMMA_K * 2;
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++local) {
+        const int split = t / tiles_mn;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int as = local & 1;
+        const uint32_t aph = (local >> 1) & 1;
+        mbar_wait(tempty_bar + 8 * as, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo);
+            const uint64_t db = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo);
+            tc_mma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(empty_bar + 8 * stage);  // frees the smem slot when these MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(tfull_bar + 8 * as);  // accumulator ready for the epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================= epilogue =======================
+    const int q = warp - 4;  // TMEM lane quarter == warp % 4
+    uint8_t* slab0 = out_stage + q * 2 * kSlabBytes;
+    constexpr int kColsPerStore = F32OUT ? 32 : 64;
+    int local = 0;
+    int n_stores = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++local) {
+      const int split = t / tiles_mn;
+      const int mn = t - split * tiles_mn;
+      const int m_blk = mn / p.n_tiles, n_blk = mn - m_blk * p.n_tiles;
+      const int as = local & 1;
+      const uint32_t aph = (local >> 1) & 1;
+      const int m = m_blk * BM + q * 32 + lane;
+      const bool row_ok = m < p.M;
+      const bool lead = (split == 0);  // bias / residual are added by the first K-split only
+      mbar_wait(tfull_bar + 8 * as, aph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+
+      for (int g = 0; g < BN / kColsPerStore; ++g) {
+        const int ng0 = n_blk * BN + g * kColsPerStore;
+        if (ng0 >= p.N) break;
+        uint8_t* slab = slab0 + (n_stores & 1) * kSlabBytes;
+        if (n_stores >= 2) {
+          if (lane == 0) tma_wait_read<1>();
+          __syncwarp();
+        }
+#pragma unroll
+        for (int h = 0; h < kColsPerStore / 32; ++h) {
+          const int n0 = ng0 + h * 32;
+          if (n0 >= p.N) break;
+          uint32_t r[32];
+          tc_ld32(t_row + g * kColsPerStore + h * 32, r);
+          tc_wait_ld();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+          if (p.bias != nullptr && lead) {
+            if (p.bias_is_bf16) {
+              const bf16* b = reinterpret_cast<const bf16*>(p.bias);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.N) v[j] += __bfloat162float(__ldg(b + n0 + j));
+            } else {
+              const float* b = reinterpret_cast<const float*>(p.bias);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.N) v[j] += __ldg(b + n0 + j);
+            }
+          }
+          const size_t aux_off = (size_t)m * p.ld_aux + n0;
+          if (p.pre_act != nullptr && row_ok) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (n0 + u * 8 + 8 <= p.N) *reinterpret_cast<bf16x8*>(p.pre_act + aux_off + u * 8) = pack8(v + u * 8);
+          }
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          } else if (p.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+          }
+          if (p.gelu_grad_of != nullptr && row_ok) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (n0 + u * 8 + 8 <= p.N) {
+                float x[8];
+                unpack8(*reinterpret_cast<const bf16x8*>(p.gelu_grad_of + aux_off + u * 8), x);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[u * 8 + j] *= gelu_erf_grad(x[j]);
+              }
+          }
+          if (p.use_dropout) {
+            const uint32_t base = (uint32_t)m * (uint32_t)p.N + (uint32_t)n0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = dropout_keep(p.seed, base + j, p.keep_thr) ? v[j] * p.inv_keep : 0.f;
+          }
+          if (p.residual != nullptr && row_ok && lead) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (n0 + u * 8 + 8 <= p.N) {
+                float x[8];
+                unpack8(*reinterpret_cast<const bf16x8*>(p.residual + aux_off + u * 8), x);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[u * 8 + j] += x[j];
+              }
+          }
+          // registers -> 128B-swizzled slab (16-byte unit u of row r lands at unit u ^ (r & 7))
+          uint8_t* row = slab + lane * 128;
+          if constexpr (F32OUT) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              *reinterpret_cast<float4*>(row + ((u ^ (lane & 7)) << 4)) =
+                  make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              *reinterpret_cast<bf16x8*>(row + (((h * 4 + u) ^ (lane & 7)) << 4)) = pack8(v + u * 8);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          if (p.accumulate)
+            tma_reduce_add_2d(&tmD, smem_u32(slab), ng0, m_blk * BM + q * 32);
+          else
+            tma_store_2d(&tmD, smem_u32(slab), ng0, m_blk * BM + q * 32);
+          tma_commit();
+        }
+        ++n_stores;
+      }
+      // all TMEM reads of this accumulator stage are complete (wait::ld above)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8 * as);
+    }
+    if (lane == 0) tma_wait_read<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)(kAccStages * BN))
+                 : "memory");
+  }
+}
+
+// ---------------- host side ----------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  });
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* base, bool f32, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                    uint32_t box_inner, uint32_t box_outer) {
+  auto enc = get_encode();
+  if (!enc) MVPTR_FAIL(MVPTR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    MVPTR_FAIL(MVPTR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): base=%p inner=%llu outer=%llu pitch=%llu box=%ux%u",
+               (int)r, base, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch_bytes,
+               box_inner, box_outer);
+  return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN, bool F32OUT>
+static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, const Params& p,
+                  cudaStream_t stream) {
+  auto kern = gemm_kernel<BN, A_MN, B_MN, F32OUT>;
+  constexpr int smem = SmemLayout<BN>::kTotal;
+  static bool configured = false;  // per template instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) MVPTR_FAIL(MVPTR_ERR_CUDA, "gemm smem attr: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  kern<<<grid, kThreads, smem, stream>>>(a, b, d, p);
+  MVPTR_CHECK_LAUNCH("gemm_kernel");
+  return 0;
+}
+
+template <int BN>
+static int dispatch(const mvptr_gemm_args* g, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d,
+                    const Params& p, cudaStream_t s) {
+  const int key = (g->a_mn ? 4 : 0) | (g->b_mn ? 2 : 0) | (g->d_is_f32 ? 1 : 0);
+  switch (key) {
+    case 0: return launch<BN, false, false, false>(a, b, d, p, s);
+    case 1: return launch<BN, false, false, true>(a, b, d, p, s);
+    case 2: return launch<BN, false, true, false>(a, b, d, p, s);
+    case 3: return launch<BN, false, true, true>(a, b, d, p, s);
+    case 4: return launch<BN, true, false, false>(a, b, d, p, s);
+    case 5: return launch<BN, true, false, true>(a, b, d, p, s);
+    case 6: return launch<BN, true, true, false>(a, b, d, p, s);
+    default: return launch<BN, true, true, true>(a, b, d, p, s);
+  }
+}
+
+}  // namespace gemm
+}  // namespace mvptr
+
+extern "C" int mvptr_gemm(const mvptr_gemm_args* g, void* stream_) {
+  using namespace mvptr;
+  using namespace mvptr::gemm;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!g || !g->A || !g->B || !g->D) MVPTR_FAIL(MVPTR_ERR_ARG, "gemm: null operand");
+  if (g->M <= 0 || g->N <= 0 || g->K <= 0) MVPTR_FAIL(MVPTR_ERR_ARG, "gemm: empty problem %dx%dx%d", g->M, g->N, g->K);
+  if ((g->lda & 7) || (g->ldb & 7) || (g->ldd & (g->d_is_f32 ? 3 : 7)))
+    MVPTR_FAIL(MVPTR_ERR_ARG, "gemm: pitches must be 16-byte multiples (lda=%d ldb=%d ldd=%d)", g->lda, g->ldb, g->ldd);
+  if ((reinterpret_cast<uintptr_t>(g->A) | reinterpret_cast<uintptr_t>(g->B) | reinterpret_cast<uintptr_t>(g->D)) & 15)
+    MVPTR_FAIL(MVPTR_ERR_ARG, "gemm: operands must be 16-byte aligned");
+  if ((g->pre_act || g->gelu_grad_of || g->residual) && (g->ld_aux & 7))
+    MVPTR_FAIL(MVPTR_ERR_ARG, "gemm: ld_aux must be a multiple of 8");
+  int split = g->split_k > 1 ? g->split_k : 1;
+  if (split > 1 && !g->accumulate) MVPTR_FAIL(MVPTR_ERR_ARG, "gemm: split_k needs accumulate=1");
+  if (split > 1 && (g->pre_act || g->act || g->gelu_grad_of || g->p_drop > 0.f))
+    MVPTR_FAIL(MVPTR_ERR_ARG, "gemm: split_k supports only bias/residual epilogues");
+
+  int bn = g->block_n;
+  if (bn == 0) bn = (g->N <= 128) ? 128 : 256;
+  if (bn != 128 && bn != 256) MVPTR_FAIL(MVPTR_ERR_ARG, "gemm: block_n must be 128 or 256");
+
+  Params p;
+  p.M = g->M; p.N = g->N; p.K = g->K;
+  p.m_tiles = (g->M + BM - 1) / BM;
+  p.n_tiles = (g->N + bn - 1) / bn;
+  p.kb_total = (g->K + BK - 1) / BK;
+  if (split > p.kb_total) split = p.kb_total;
+  p.kb_per_split = (p.kb_total + split - 1) / split;
+  split = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
+  p.split_k = split;
+  p.num_tiles = p.m_tiles * p.n_tiles * split;
+  p.accumulate = g->accumulate;
+  p.alpha = g->alpha;
+  p.bias = g->bias; p.bias_is_bf16 = g->bias_is_bf16;
+  p.pre_act = reinterpret_cast<bf16*>(g->pre_act);
+  p.act = g->act;
+  p.gelu_grad_of = reinterpret_cast<const bf16*>(g->gelu_grad_of);
+  p.residual = reinterpret_cast<const bf16*>(g->residual);
+  p.ld_aux = g->ld_aux;
+  p.use_dropout = g->p_drop > 0.f;
+  p.inv_keep = p.use_dropout ? 1.0f / (1.0f - g->p_drop) : 1.0f;
+  p.keep_thr = keep_threshold(g->p_drop);
+  p.seed = g->seed;
+
+  CUtensorMap ta, tb, td;
+  int rc;
+  if (!g->a_mn) rc = make_map(&ta, g->A, false, g->K, g->M, (uint64_t)g->lda * 2, BK, BM);
+  else          rc = make_map(&ta, g->A, false, g->M, g->K, (uint64_t)g->lda * 2, 64, BK);
+  if (rc) return rc;
+  if (!g->b_mn) rc = make_map(&tb, g->B, false, g->K, g->N, (uint64_t)g->ldb * 2, BK, bn);
+  else          rc = make_map(&tb, g->B, false, g->N, g->K, (uint64_t)g->ldb * 2, 64, BK);
+  if (rc) return rc;
+  if (g->d_is_f32) rc = make_map(&td, g->D, true, g->N, g->M, (uint64_t)g->ldd * 4, 32, 32);
+  else             rc = make_map(&td, g->D, false, g->N, g->M, (uint64_t)g->ldd * 2, 64, 32);
+  if (rc) return rc;
+
+  return bn == 256 ? dispatch<256>(g, ta, tb, td, p, stream) : dispatch<128>(g, ta, tb, td, p, stream);
+}

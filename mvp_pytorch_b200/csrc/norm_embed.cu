@@ -1,0 +1,616 @@
+// HBM-bound row kernels: embedding gather + LayerNorm, LayerNorm fwd/bwd, column sums,
+// embedding scatter-add, region-feature pad/cast, mask preparation, row gathers.
+// One warp per row, 16-byte vector accesses, warp-shuffle reductions.
+#include "common.cuh"
+
+namespace mvptr {
+
+constexpr int kMaxChunks = 4;  // hidden <= 32 lanes * 4 chunks * 8 = 1024
+
+struct RowMap {
+  // logical row r = b * rows_per_batch + t  ->  element offset b * batch_stride + t * H
+  int rows_per_batch;
+  long long batch_stride;
+  __device__ __forceinline__ size_t off(int r, int H) const {
+    const int b = r / rows_per_batch;
+    return (size_t)b * batch_stride + (size_t)(r - b * rows_per_batch) * H;
+  }
+};
+
+__device__ __forceinline__ void ln_row(float (&x)[kMaxChunks][8], int nchunk, int lane, int H, float eps, float& mean,
+                                       float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c)
+    if (lane + 32 * c < nchunk)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += x[c][j];
+  mean = warp_sum(s) / H;
+  float v = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c)
+    if (lane + 32 * c < nchunk)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = x[c][j] - mean;
+        v += d * d;
+      }
+  rstd = rsqrtf(warp_sum(v) / H + eps);  // TF-style: eps inside the sqrt (modeling_bert.py:245)
+}
+
+// ---------------------------------------------------------------------------------
+// y = dropout(LN(word[ids] + pos[p] + type[seg]))      modeling_bert.py:262-277
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+embed_ln_fwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ type_ids,
+                    const int64_t* __restrict__ pos_ids, const bf16* __restrict__ word,
+                    const bf16* __restrict__ pos, const bf16* __restrict__ type, const bf16* __restrict__ gamma,
+                    const bf16* __restrict__ beta, bf16* __restrict__ y, RowMap ymap, bf16* __restrict__ pre,
+                    float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int L, int H, float eps,
+                    int vocab, int max_pos, int n_types, uint32_t keep_thr, float inv_keep, uint32_t seed) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int nchunk = H >> 3;
+  long long id = ids[r];
+  long long ty = type_ids ? type_ids[r] : 0;
+  long long ps = pos_ids ? pos_ids[r] : (r % L);
+  // out-of-range indices would be a hard device fault in the reference; clamp so the
+  // kernel stays memory-safe (the host wrapper validates ranges in debug mode)
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  ty = ty < 0 ? 0 : (ty >= n_types ? n_types - 1 : ty);
+  ps = ps < 0 ? 0 : (ps >= max_pos ? max_pos - 1 : ps);
+  const bf16* w = word + (size_t)id * H;
+  const bf16* p = pos + (size_t)ps * H;
+  const bf16* t = type + (size_t)ty * H;
+  float x[kMaxChunks][8];
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nchunk) {
+      float a[8], b2[8], c2[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(w + ch * 8), a);
+      unpack8(*reinterpret_cast<const bf16x8*>(p + ch * 8), b2);
+      unpack8(*reinterpret_cast<const bf16x8*>(t + ch * 8), c2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[c][j] = a[j] + b2[j] + c2[j];
+      if (pre) *reinterpret_cast<bf16x8*>(pre + (size_t)r * H + ch * 8) = pack8(x[c]);
+    }
+  }
+  float mean, rstd;
+  ln_row(x, nchunk, lane, H, eps, mean, rstd);
+  if (mean_out && lane == 0) {
+    mean_out[r] = mean;
+    rstd_out[r] = rstd;
+  }
+  bf16* yo = y + ymap.off(r, H);
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nchunk) {
+      float g[8], b2[8], o[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(gamma + ch * 8), g);
+      unpack8(*reinterpret_cast<const bf16x8*>(beta + ch * 8), b2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j] = g[j] * ((x[c][j] - mean) * rstd) + b2[j];
+        if (keep_thr != 0xffffffffu)
+          o[j] = dropout_keep(seed, (uint32_t)r * (uint32_t)H + ch * 8 + j, keep_thr) ? o[j] * inv_keep : 0.f;
+      }
+      *reinterpret_cast<bf16x8*>(yo + ch * 8) = pack8(o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// y = dropout(LN(x))                    modeling_bert.py:242-246 (+ modeling_vlbert.py:499-503)
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+ln_fwd_kernel(const bf16* __restrict__ x_in, const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
+              bf16* __restrict__ y, RowMap ymap, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
+              int H, float eps, uint32_t keep_thr, float inv_keep, uint32_t seed) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int nchunk = H >> 3;
+  float x[kMaxChunks][8];
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nchunk) unpack8(*reinterpret_cast<const bf16x8*>(x_in + (size_t)r * H + ch * 8), x[c]);
+  }
+  float mean, rstd;
+  ln_row(x, nchunk, lane, H, eps, mean, rstd);
+  if (mean_out && lane == 0) {
+    mean_out[r] = mean;
+    rstd_out[r] = rstd;
+  }
+  bf16* yo = y + ymap.off(r, H);
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nchunk) {
+      float g[8], b2[8], o[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(gamma + ch * 8), g);
+      unpack8(*reinterpret_cast<const bf16x8*>(beta + ch * 8), b2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j] = g[j] * ((x[c][j] - mean) * rstd) + b2[j];
+        if (keep_thr != 0xffffffffu)
+          o[j] = dropout_keep(seed, (uint32_t)r * (uint32_t)H + ch * 8 + j, keep_thr) ? o[j] * inv_keep : 0.f;
+      }
+      *reinterpret_cast<bf16x8*>(yo + ch * 8) = pack8(o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// LayerNorm backward.  dy may live in a strided (batch-mapped) buffer.
+//   g = dy (* output-dropout mask) ; dx = rstd * (g*gamma - mean(g*gamma) - xhat*mean(g*gamma*xhat))
+//   dgamma += sum_r g*xhat ; dbeta += sum_r g
+//   dx_drop = dx * input-dropout mask (the dropout that sat between the dense and the
+//             residual add, modeling_bert.py:350-351) ; dbias += sum_r dx_drop
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const bf16* __restrict__ dy, RowMap dymap, const bf16* __restrict__ x_in,
+              const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const bf16* __restrict__ gamma,
+              bf16* __restrict__ dx, bf16* __restrict__ dx_drop, float* __restrict__ dgamma,
+              float* __restrict__ dbeta, float* __restrict__ dbias, int rows, int H, uint32_t out_keep_thr,
+              float out_inv_keep, uint32_t out_seed, uint32_t in_keep_thr, float in_inv_keep, uint32_t in_seed) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarp_total = gridDim.x * 8;
+  const int nchunk = H >> 3;
+  float gam[kMaxChunks][8], ag[kMaxChunks][8], ab[kMaxChunks][8], abias[kMaxChunks][8];
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nchunk) unpack8(*reinterpret_cast<const bf16x8*>(gamma + ch * 8), gam[c]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ag[c][j] = ab[c][j] = abias[c][j] = 0.f;
+  }
+  for (int r = blockIdx.x * 8 + warp; r < rows; r += nwarp_total) {
+    const float mean = mean_in[r], rstd = rstd_in[r];
+    const bf16* dyr = dy + dymap.off(r, H);
+    float g[kMaxChunks][8], xh[kMaxChunks][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunk) {
+        float xv[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(dyr + ch * 8), g[c]);
+        unpack8(*reinterpret_cast<const bf16x8*>(x_in + (size_t)r * H + ch * 8), xv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (out_keep_thr != 0xffffffffu)
+            g[c][j] = dropout_keep(out_seed, (uint32_t)r * (uint32_t)H + ch * 8 + j, out_keep_thr)
+                          ? g[c][j] * out_inv_keep : 0.f;
+          xh[c][j] = (xv[j] - mean) * rstd;
+          ag[c][j] += g[c][j] * xh[c][j];
+          ab[c][j] += g[c][j];
+          const float gg = g[c][j] * gam[c][j];
+          s1 += gg;
+          s2 += gg * xh[c][j];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / H;
+    s2 = warp_sum(s2) / H;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunk) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (g[c][j] * gam[c][j] - s1 - xh[c][j] * s2);
+        if (dx) *reinterpret_cast<bf16x8*>(dx + (size_t)r * H + ch * 8) = pack8(o);
+        if (dx_drop) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            o[j] = dropout_keep(in_seed, (uint32_t)r * (uint32_t)H + ch * 8 + j, in_keep_thr) ? o[j] * in_inv_keep : 0.f;
+          *reinterpret_cast<bf16x8*>(dx_drop + (size_t)r * H + ch * 8) = pack8(o);
+        }
+        if (dbias) {
+          // bias grad sees what the dense output saw: bf16-rounded, dropped dx
+          bf16x8 pk = pack8(o);
+          float q[8];
+          unpack8(pk, q);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) abias[c][j] += q[j];
+        }
+      }
+    }
+  }
+  // block reduce over the 8 warps, then one atomic per column per block
+  __shared__ float red[8][33 * 8];
+  for (int pass = 0; pass < 3; ++pass) {
+    float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dbias);
+    if (!dst) continue;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int ch = lane + 32 * c;
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = pass == 0 ? ag[c][j] : (pass == 1 ? ab[c][j] : abias[c][j]);
+      __syncthreads();
+      if (warp == 0 && ch < nchunk) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float s = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) s += red[w][lane * 8 + j];
+          atomicAdd(dst + ch * 8 + j, s);
+        }
+      }
+    }
+  }
+}
+
+// out[n] += sum_m X[m,n]   (bias gradients of a dense layer: column sum of dY)
+__global__ void __launch_bounds__(256)
+colsum_kernel(const bf16* __restrict__ x, int ldx, float* __restrict__ out, int M, int N, int rows_per_block) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + tx) * 8;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (col < N) {
+    for (int r = r0 + ty; r < r1; r += 8) {
+      float v[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(x + (size_t)r * ldx + col), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  }
+  __shared__ float red[8][32 * 8 + 1];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[ty][tx * 8 + j] = acc[j];
+  __syncthreads();
+  if (ty == 0 && col < N) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w][tx * 8 + j];
+      if (col + j < N) atomicAdd(out + col + j, s);
+    }
+  }
+}
+
+// Embedding backward (modeling_bert.py:262-277): word rows by atomics (padding_idx row
+// gets no gradient, as nn.Embedding(padding_idx=0)), position / type rows by a
+// per-position block reduction over the batch.
+__global__ void __launch_bounds__(128)
+embed_word_bwd_kernel(const bf16* __restrict__ dpre, const int64_t* __restrict__ ids, float* __restrict__ dword,
+                      int rows, int H, int vocab, int padding_idx) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const long long id = ids[r];
+  if (id == padding_idx || id < 0 || id >= vocab) return;
+  float* dst = dword + (size_t)id * H;
+  for (int ch = lane; ch < (H >> 3); ch += 32) {
+    float v[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(dpre + (size_t)r * H + ch * 8), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(dst + ch * 8 + j, v[j]);
+  }
+}
+__global__ void __launch_bounds__(128)
+embed_pos_type_bwd_kernel(const bf16* __restrict__ dpre, const int64_t* __restrict__ type_ids,
+                          float* __restrict__ dpos, float* __restrict__ dtype, int B, int L, int H, int n_types) {
+  // block = one position p; thread = 8 columns; loop over the batch
+  const int p = blockIdx.x;
+  for (int col = threadIdx.x * 8; col < H; col += blockDim.x * 8) {
+    float accp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float acct[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};
+    for (int b = 0; b < B; ++b) {
+      const int r = b * L + p;
+      float v[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(dpre + (size_t)r * H + col), v);
+      const long long ty = type_ids ? type_ids[r] : 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        accp[j] += v[j];
+        if (ty == 0) acct[0][j] += v[j];
+        else if (ty == 1) acct[1][j] += v[j];
+      }
+      if (ty > 1 && ty < n_types)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(dtype + (size_t)ty * H + col + j, v[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(dpos + (size_t)p * H + col + j, accp[j]);
+      atomicAdd(dtype + col + j, acct[0][j]);
+      if (n_types > 1) atomicAdd(dtype + H + col + j, acct[1][j]);
+    }
+  }
+}
+
+// fp32/bf16 [rows, K] (any pitch) -> bf16 [rows, Kp] zero padded  (region features, K=2054)
+template <typename T>
+__global__ void pad_cast_kernel(const T* __restrict__ src, long long ld_src, bf16* __restrict__ dst, int ld_dst,
+                                int rows, int K) {
+  const int r = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ld_dst) return;
+  float v = 0.f;
+  if (c < K) v = (float)src[(size_t)r * ld_src + c];
+  dst[(size_t)r * ld_dst + c] = __float2bfloat16(v);
+}
+
+// additive attention mask: (1 - mask) * -10000   (modeling_vlbert.py:430-460), with an
+// optional per-row source remap and column window so the joint / hard-negative masks
+// are assembled without torch.cat / index_select (modeling_vlbert.py:542-566, 587)
+__global__ void mask_prepare_kernel(const int64_t* __restrict__ mask_a, int La, const int64_t* __restrict__ mask_b,
+                                    int Lb, int b_col0, const int64_t* __restrict__ row_a,
+                                    const int64_t* __restrict__ row_b, float* __restrict__ out, int rows) {
+  const int Lout = La + (Lb - b_col0);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * Lout) return;
+  const int r = i / Lout, c = i - r * Lout;
+  long long m;
+  if (c < La) m = mask_a[(size_t)(row_a ? row_a[r] : r) * La + c];
+  else m = mask_b[(size_t)(row_b ? row_b[r] : r) * Lb + b_col0 + (c - La)];
+  out[i] = (1.0f - (float)m) * -10000.0f;
+}
+
+// out[r, t, :] = t < La ? a[row_a[r], t, :] : b[row_b[r], b_col0 + t - La, :]
+// (torch.cat + index_select of modeling_vlbert.py:542-566, 586 as one gather)
+__global__ void __launch_bounds__(128)
+concat_rows_kernel(const bf16* __restrict__ a, int La, const bf16* __restrict__ b, int Lb, int b_col0,
+                   const int64_t* __restrict__ row_a, const int64_t* __restrict__ row_b, bf16* __restrict__ out,
+                   int rows, int H) {
+  const int Lout = La + (Lb - b_col0);
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (i >= rows * Lout) return;
+  const int r = i / Lout, t = i - r * Lout;
+  const bf16* src;
+  if (t < La) src = a + ((size_t)(row_a ? row_a[r] : r) * La + t) * H;
+  else src = b + ((size_t)(row_b ? row_b[r] : r) * Lb + b_col0 + (t - La)) * H;
+  bf16* dst = out + (size_t)i * H;
+  for (int ch = lane; ch < (H >> 3); ch += 32)
+    *reinterpret_cast<uint4*>(dst + ch * 8) = *reinterpret_cast<const uint4*>(src + ch * 8);
+}
+// backward of the gather: da[row_a[r], t] += dout[r, t] ; db[row_b[r], b_col0 + t - La] += ...
+__global__ void __launch_bounds__(128)
+concat_rows_bwd_kernel(const bf16* __restrict__ dout, int La, int Lb, int b_col0, const int64_t* __restrict__ row_a,
+                       const int64_t* __restrict__ row_b, float* __restrict__ da, float* __restrict__ db, int rows,
+                       int H) {
+  const int Lout = La + (Lb - b_col0);
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (i >= rows * Lout) return;
+  const int r = i / Lout, t = i - r * Lout;
+  float* dst;
+  if (t < La) dst = da + ((size_t)(row_a ? row_a[r] : r) * La + t) * H;
+  else dst = db + ((size_t)(row_b ? row_b[r] : r) * Lb + b_col0 + (t - La)) * H;
+  const bf16* src = dout + (size_t)i * H;
+  for (int ch = lane; ch < (H >> 3); ch += 32) {
+    float v[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(src + ch * 8), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(dst + ch * 8 + j, v[j]);
+  }
+}
+
+// out[i, :] = src[rows[i], :]   (masked_select of MLM rows, modeling_vlbert.py:1232,1246)
+__global__ void __launch_bounds__(128)
+gather_rows_kernel(const bf16* __restrict__ src, const int64_t* __restrict__ idx, bf16* __restrict__ out, int n, int H) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const bf16* s = src + (size_t)idx[i] * H;
+  for (int ch = lane; ch < (H >> 3); ch += 32)
+    *reinterpret_cast<uint4*>(out + (size_t)i * H + ch * 8) = *reinterpret_cast<const uint4*>(s + ch * 8);
+}
+// dst[rows[i], :] += src[i, :]  (fp32 accumulate; indexes are unique for masked_select)
+__global__ void __launch_bounds__(128)
+scatter_rows_add_kernel(const bf16* __restrict__ src, const int64_t* __restrict__ idx, float* __restrict__ dst, int n,
+                        int H) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (i >= n) return;
+  float* d = dst + (size_t)idx[i] * H;
+  for (int ch = lane; ch < (H >> 3); ch += 32) {
+    float v[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(src + (size_t)i * H + ch * 8), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(d + ch * 8 + j, v[j]);
+  }
+}
+
+// elementwise helpers on flat buffers
+__global__ void cast_f32_to_bf16_kernel(const float* __restrict__ s, bf16* __restrict__ d, size_t n) {
+  size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  const size_t stride = (size_t)gridDim.x * blockDim.x * 8;
+  for (; i + 8 <= n; i += stride) {
+    const float4 a = *reinterpret_cast<const float4*>(s + i);
+    const float4 b = *reinterpret_cast<const float4*>(s + i + 4);
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    *reinterpret_cast<bf16x8*>(d + i) = pack8(v);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (size_t k = n & ~size_t(7); k < n; ++k) d[k] = __float2bfloat16(s[k]);
+}
+// d = bf16(a + b) for two fp32 gradient buffers (or b == nullptr)
+__global__ void add_cast_kernel(const float* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ d, size_t n) {
+  size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  const size_t stride = (size_t)gridDim.x * blockDim.x * 8;
+  for (; i + 8 <= n; i += stride) {
+    const float4 x = *reinterpret_cast<const float4*>(a + i);
+    const float4 y = *reinterpret_cast<const float4*>(a + i + 4);
+    float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+    if (b) {
+      float w[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(b + i), w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += w[j];
+    }
+    *reinterpret_cast<bf16x8*>(d + i) = pack8(v);
+  }
+}
+
+static inline uint32_t thr(float p) { return keep_threshold(p); }
+static inline float invk(float p) { return p > 0.f ? 1.f / (1.f - p) : 1.f; }
+
+}  // namespace mvptr
+
+using namespace mvptr;
+
+#define CHECK_H(H)                                                                         \
+  if ((H) <= 0 || ((H)&7) || (H) > 32 * kMaxChunks * 8) MVPTR_FAIL(MVPTR_ERR_ARG, "hidden size %d unsupported (multiple of 8, <= 1024)", (H))
+
+extern "C" int mvptr_embed_ln_fwd(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids,
+                                  const void* word, const void* pos, const void* type, const void* gamma,
+                                  const void* beta, void* y, int y_rows_per_batch, long long y_batch_stride, void* pre,
+                                  float* mean, float* rstd, int B, int L, int H, float eps, int vocab, int max_pos,
+                                  int n_types, float p_drop, uint32_t seed, void* stream) {
+  CHECK_H(H);
+  if (L > max_pos && !pos_ids) MVPTR_FAIL(MVPTR_ERR_ARG, "sequence length %d exceeds position table %d", L, max_pos);
+  const int rows = B * L;
+  if (rows == 0) return 0;
+  RowMap ym{y_rows_per_batch > 0 ? y_rows_per_batch : L, y_rows_per_batch > 0 ? y_batch_stride : (long long)L * H};
+  embed_ln_fwd_kernel<<<(rows + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
+      ids, type_ids, pos_ids, (const bf16*)word, (const bf16*)pos, (const bf16*)type, (const bf16*)gamma,
+      (const bf16*)beta, (bf16*)y, ym, (bf16*)pre, mean, rstd, rows, L, H, eps, vocab, max_pos, n_types, thr(p_drop),
+      invk(p_drop), seed);
+  MVPTR_CHECK_LAUNCH("embed_ln_fwd");
+  return 0;
+}
+
+extern "C" int mvptr_ln_fwd(const void* x, const void* gamma, const void* beta, void* y, int y_rows_per_batch,
+                            long long y_batch_stride, float* mean, float* rstd, int rows, int H, float eps,
+                            float p_drop, uint32_t seed, void* stream) {
+  CHECK_H(H);
+  if (rows == 0) return 0;
+  RowMap ym{y_rows_per_batch > 0 ? y_rows_per_batch : rows, y_rows_per_batch > 0 ? y_batch_stride : 0};
+  ln_fwd_kernel<<<(rows + 3) / 4, 128, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gamma,
+                                                                   (const bf16*)beta, (bf16*)y, ym, mean, rstd, rows,
+                                                                   H, eps, thr(p_drop), invk(p_drop), seed);
+  MVPTR_CHECK_LAUNCH("ln_fwd");
+  return 0;
+}
+
+extern "C" int mvptr_ln_bwd(const void* dy, int dy_rows_per_batch, long long dy_batch_stride, const void* x,
+                            const float* mean, const float* rstd, const void* gamma, void* dx, void* dx_drop,
+                            float* dgamma, float* dbeta, float* dbias, int rows, int H, float out_p_drop,
+                            uint32_t out_seed, float in_p_drop, uint32_t in_seed, void* stream) {
+  CHECK_H(H);
+  if (rows == 0) return 0;
+  if (dx_drop && in_p_drop <= 0.f) MVPTR_FAIL(MVPTR_ERR_ARG, "ln_bwd: dx_drop given without in_p_drop");
+  RowMap dm{dy_rows_per_batch > 0 ? dy_rows_per_batch : rows, dy_rows_per_batch > 0 ? dy_batch_stride : 0};
+  int grid = (rows + 7) / 8;
+  if (grid > kNumSMs * 4) grid = kNumSMs * 4;
+  ln_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dy, dm, (const bf16*)x, mean, rstd, (const bf16*)gamma, (bf16*)dx, (bf16*)dx_drop, dgamma, dbeta,
+      dbias, rows, H, thr(out_p_drop), invk(out_p_drop), out_seed, thr(in_p_drop), invk(in_p_drop), in_seed);
+  MVPTR_CHECK_LAUNCH("ln_bwd");
+  return 0;
+}
+
+extern "C" int mvptr_colsum(const void* x, int ldx, float* out, int M, int N, void* stream) {
+  if (M <= 0 || N <= 0) return 0;
+  if ((N & 7) || (ldx & 7)) MVPTR_FAIL(MVPTR_ERR_ARG, "colsum: N and ldx must be multiples of 8");
+  const int rpb = 512;
+  dim3 grid((N + 255) / 256, (M + rpb - 1) / rpb);
+  colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, out, M, N, rpb);
+  MVPTR_CHECK_LAUNCH("colsum");
+  return 0;
+}
+
+extern "C" int mvptr_embed_bwd(const void* dpre, const int64_t* ids, const int64_t* type_ids, float* dword,
+                               float* dpos, float* dtype, int B, int L, int H, int vocab, int n_types,
+                               int padding_idx, void* stream) {
+  CHECK_H(H);
+  const int rows = B * L;
+  if (rows == 0) return 0;
+  embed_word_bwd_kernel<<<(rows + 3) / 4, 128, 0, (cudaStream_t)stream>>>((const bf16*)dpre, ids, dword, rows, H,
+                                                                          vocab, padding_idx);
+  MVPTR_CHECK_LAUNCH("embed_word_bwd");
+  embed_pos_type_bwd_kernel<<<L, 128, 0, (cudaStream_t)stream>>>((const bf16*)dpre, type_ids, dpos, dtype, B, L, H,
+                                                                 n_types);
+  MVPTR_CHECK_LAUNCH("embed_pos_type_bwd");
+  return 0;
+}
+
+extern "C" int mvptr_pad_cast(const void* src, int src_is_f32, long long ld_src, void* dst, int ld_dst, int rows, int K,
+                              void* stream) {
+  if (rows <= 0) return 0;
+  dim3 grid((ld_dst + 255) / 256, rows);
+  if (src_is_f32)
+    pad_cast_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src, ld_src, (bf16*)dst, ld_dst, rows, K);
+  else
+    pad_cast_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, ld_src, (bf16*)dst, ld_dst, rows, K);
+  MVPTR_CHECK_LAUNCH("pad_cast");
+  return 0;
+}
+
+extern "C" int mvptr_mask_prepare(const int64_t* mask_a, int La, const int64_t* mask_b, int Lb, int b_col0,
+                                  const int64_t* row_a, const int64_t* row_b, float* out, int rows, void* stream) {
+  if (rows <= 0) return 0;
+  if (Lb > 0 && !mask_b) MVPTR_FAIL(MVPTR_ERR_ARG, "mask_prepare: mask_b missing");
+  const int n = rows * (La + (Lb - b_col0));
+  mask_prepare_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mask_a, La, mask_b, Lb, b_col0, row_a, row_b,
+                                                                         out, rows);
+  MVPTR_CHECK_LAUNCH("mask_prepare");
+  return 0;
+}
+
+extern "C" int mvptr_concat_rows(const void* a, int La, const void* b, int Lb, int b_col0, const int64_t* row_a,
+                                 const int64_t* row_b, void* out, int rows, int H, void* stream) {
+  if (rows <= 0) return 0;
+  if (H & 7) MVPTR_FAIL(MVPTR_ERR_ARG, "concat_rows: H must be a multiple of 8");
+  const int n = rows * (La + (Lb - b_col0));
+  concat_rows_kernel<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>((const bf16*)a, La, (const bf16*)b, Lb, b_col0,
+                                                                    row_a, row_b, (bf16*)out, rows, H);
+  MVPTR_CHECK_LAUNCH("concat_rows");
+  return 0;
+}
+
+extern "C" int mvptr_concat_rows_bwd(const void* dout, int La, int Lb, int b_col0, const int64_t* row_a,
+                                     const int64_t* row_b, float* da, float* db, int rows, int H, void* stream) {
+  if (rows <= 0) return 0;
+  const int n = rows * (La + (Lb - b_col0));
+  concat_rows_bwd_kernel<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>((const bf16*)dout, La, Lb, b_col0, row_a,
+                                                                        row_b, da, db, rows, H);
+  MVPTR_CHECK_LAUNCH("concat_rows_bwd");
+  return 0;
+}
+
+extern "C" int mvptr_gather_rows(const void* src, const int64_t* idx, void* out, int n, int H, void* stream) {
+  if (n <= 0) return 0;
+  gather_rows_kernel<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>((const bf16*)src, idx, (bf16*)out, n, H);
+  MVPTR_CHECK_LAUNCH("gather_rows");
+  return 0;
+}
+
+extern "C" int mvptr_scatter_rows_add(const void* src, const int64_t* idx, float* dst, int n, int H, void* stream) {
+  if (n <= 0) return 0;
+  scatter_rows_add_kernel<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>((const bf16*)src, idx, dst, n, H);
+  MVPTR_CHECK_LAUNCH("scatter_rows_add");
+  return 0;
+}
+
+extern "C" int mvptr_cast_f32_bf16(const float* src, void* dst, size_t n, void* stream) {
+  if (n == 0) return 0;
+  size_t blocks = (n / 8 + 255) / 256;
+  if (blocks > (size_t)kNumSMs * 8) blocks = (size_t)kNumSMs * 8;
+  if (blocks == 0) blocks = 1;
+  cast_f32_to_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+  MVPTR_CHECK_LAUNCH("cast_f32_bf16");
+  return 0;
+}
+
+extern "C" int mvptr_add_cast(const float* a, const void* b, void* d, size_t n, void* stream) {
+  if (n == 0) return 0;
+  if (n & 7) MVPTR_FAIL(MVPTR_ERR_ARG, "add_cast: n must be a multiple of 8");
+  size_t blocks = (n / 8 + 255) / 256;
+  if (blocks > (size_t)kNumSMs * 8) blocks = (size_t)kNumSMs * 8;
+  add_cast_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, (const bf16*)b, (bf16*)d, n);
+  MVPTR_CHECK_LAUNCH("add_cast");
+  return 0;
+}

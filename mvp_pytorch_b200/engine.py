@@ -1,0 +1,756 @@
+"""Host-side orchestration of the CUDA hot path: torch.autograd.Functions whose forward and
+backward are sequences of libmvptr_b200.so calls.  PyTorch supplies device memory, streams
+and the autograd tape; all arithmetic on activations happens in the C-ABI kernels.
+
+Weight gradients are never returned to autograd: the wgrad GEMMs reduce-add directly into
+the model's flat fp32 gradient arena (arena.py), whose slices are the parameters' ``.grad``.
+"""
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from .arena import ParamArena
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+NUM_SMS = 148
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+class Runtime:
+    """Per-model state shared by all Functions of one forward/backward."""
+
+    def __init__(self, model, config):
+        self.model = model
+        self.cfg = config
+        self.arena = ParamArena(model)
+        self.H = config.hidden_size
+        self.I = config.intermediate_size
+        self.nh = config.num_attention_heads
+        if self.H != self.nh * 64:
+            raise _lib.MvptrError(f"hidden_size {self.H} / heads {self.nh}: the attention kernel needs head_dim 64")
+        self.eps = float(config.layer_norm_eps)
+        self.seed_base = int(torch.initial_seed()) & 0x7FFFFFFF
+        self.seed_ctr = 0
+        self.img_w16 = None
+        self._img_w_version = -1
+        self.launches = 0
+
+    # ---- bookkeeping -------------------------------------------------------------------
+    def next_seed(self):
+        self.seed_ctr += 1
+        return (self.seed_base * 2654435761 + self.seed_ctr * 974711) & 0xFFFFFFFF
+
+    def call(self, name, *args):
+        self.launches += 1
+        _lib.call(name, *args)
+
+    def gemm(self, *a, **kw):
+        self.launches += 1
+        return _lib.gemm(*a, **kw)
+
+    def begin_forward(self, training):
+        a = self.arena
+        if not a.valid():
+            raise _lib.MvptrError("parameters were moved or re-typed after the first forward; call "
+                                  "model.rebuild_arena() after .to()/.half()/.bfloat16()")
+        # optimizers that update through p.data do not bump version counters -> recast every training step
+        a.refresh_shadow(force=training and a.shadow is not a.master and not getattr(self, "shadow_managed", False))
+        self.training = training
+
+    def img_weight(self, name):
+        """bf16 copy of the region projection weight with the K=2054 pitch padded to 16 bytes."""
+        a = self.arena
+        m = a.master_of(name)
+        K = m.shape[1]
+        Kp = _pad8(K)
+        if self.img_w16 is None:
+            self.img_w16 = torch.zeros(m.shape[0], Kp, device=m.device, dtype=BF16)
+        if self.training or self._img_w_version != a.master._version:
+            self.call("mvptr_pad_cast", m, int(m.dtype == F32), K, self.img_w16, Kp, m.shape[0], K)
+            self._img_w_version = a.master._version
+        return self.img_w16
+
+
+def split_k_for(m_out, n_out, k, bn=256):
+    """Enough K-splits to put ~2 waves of CTAs on 148 SMs (wgrad outputs are small, K is the token count)."""
+    tiles = ((m_out + 127) // 128) * ((n_out + bn - 1) // bn)
+    kb = (k + 63) // 64
+    s = max(1, (2 * NUM_SMS) // tiles)
+    return max(1, min(s, kb // 4 if kb >= 4 else 1))
+
+
+def wgrad(rt, dY, ld_dy, X, ld_x, n_out, k_in, tokens, dW, ldw=None):
+    """dW[n_out, k_in] += dY[tokens, n_out]^T . X[tokens, k_in]   (fp32 reduce-add, split-K)"""
+    rt.gemm(dY, X, dW, n_out, k_in, tokens, lda=ld_dy, ldb=ld_x, ldd=ldw or k_in, a_mn=True, b_mn=True,
+            accumulate=True, split_k=split_k_for(n_out, k_in, tokens))
+
+
+def dgrad(rt, dY, ld_dy, W, ld_w, tokens, n_out, k_in, dX, **epi):
+    """dX[tokens, k_in] = dY[tokens, n_out] . W[n_out, k_in]"""
+    rt.gemm(dY, W, dX, tokens, k_in, n_out, lda=ld_dy, ldb=ld_w, ldd=k_in, b_mn=True, **epi)
+
+
+# ======================================================================================
+# Encoder stack: CaptionBertEncoder.forward (modeling_vlbert.py:134-178) over
+# CaptionBertLayer (:191-199) = attention (:63-103) + BertSelfOutput / BertIntermediate /
+# BertOutput (modeling_bert.py:348-352, 394-397, 407-411)
+# ======================================================================================
+class EncoderFn(Function):
+    @staticmethod
+    def forward(ctx, h, maskadd, rt, prefix, layer_lo, layer_hi, save, anchor):
+        B, L, H = h.shape
+        M, I, nh = B * L, rt.I, rt.nh
+        a = rt.arena
+        dev = h.device
+        p_h = rt.cfg.hidden_dropout_prob if rt.training else 0.0
+        p_a = rt.cfg.attention_probs_dropout_prob if rt.training else 0.0
+        x = h.reshape(M, H)
+        if not x.is_contiguous():
+            x = x.contiguous()
+        saved = []
+        for li in range(layer_lo, layer_hi):
+            pf = f"{prefix}.layer.{li}."
+            s_attn, s1, s2 = rt.next_seed(), rt.next_seed(), rt.next_seed()
+            wqkv = a.w_span(pf + "attention.self.query.weight", 3 * H, H)
+            bqkv = a.w_span(pf + "attention.self.query.bias", 3 * H)
+            qkv = torch.empty(M, 3 * H, device=dev, dtype=BF16)
+            rt.gemm(x, wqkv, qkv, M, 3 * H, H, lda=H, ldb=H, ldd=3 * H, bias=bqkv)
+            att = torch.empty(M, H, device=dev, dtype=BF16)
+            lse = torch.empty(B, nh, L, device=dev, dtype=F32) if save else None
+            rt.call("mvptr_attn_fwd", qkv, 3 * H, maskadd, att, H, lse, B, L, nh, H, p_a, s_attn)
+            pre1 = torch.empty(M, H, device=dev, dtype=BF16)
+            rt.gemm(att, a.w(pf + "attention.output.dense.weight"), pre1, M, H, H, lda=H, ldb=H, ldd=H,
+                    bias=a.w(pf + "attention.output.dense.bias"), residual=x, ld_aux=H, p_drop=p_h, seed=s1)
+            a1 = torch.empty(M, H, device=dev, dtype=BF16)
+            st1 = torch.empty(2, M, device=dev, dtype=F32) if save else None
+            rt.call("mvptr_ln_fwd", pre1, a.w(pf + "attention.output.LayerNorm.weight"),
+                    a.w(pf + "attention.output.LayerNorm.bias"), a1, 0, 0, st1[0] if save else None,
+                    st1[1] if save else None, M, H, rt.eps, 0.0, 0)
+            inter = torch.empty(M, I, device=dev, dtype=BF16)
+            pre_g = torch.empty(M, I, device=dev, dtype=BF16) if save else None
+            rt.gemm(a1, a.w(pf + "intermediate.dense.weight"), inter, M, I, H, lda=H, ldb=H, ldd=I,
+                    bias=a.w(pf + "intermediate.dense.bias"), act="gelu", pre_act=pre_g, ld_aux=I)
+            pre2 = torch.empty(M, H, device=dev, dtype=BF16)
+            rt.gemm(inter, a.w(pf + "output.dense.weight"), pre2, M, H, I, lda=I, ldb=I, ldd=H,
+                    bias=a.w(pf + "output.dense.bias"), residual=a1, ld_aux=H, p_drop=p_h, seed=s2)
+            out = torch.empty(M, H, device=dev, dtype=BF16)
+            st2 = torch.empty(2, M, device=dev, dtype=F32) if save else None
+            rt.call("mvptr_ln_fwd", pre2, a.w(pf + "output.LayerNorm.weight"), a.w(pf + "output.LayerNorm.bias"), out,
+                    0, 0, st2[0] if save else None, st2[1] if save else None, M, H, rt.eps, 0.0, 0)
+            if save:
+                saved.append((pf, x, qkv, att, lse, pre1, st1, a1, pre_g, inter, pre2, st2, s_attn, s1, s2))
+            x = out
+        ctx.rt, ctx.saved, ctx.dims, ctx.maskadd, ctx.p = rt, saved, (B, L, H), maskadd, (p_h, p_a)
+        return x.view(B, L, H)
+
+    @staticmethod
+    def backward(ctx, dout):
+        rt, (B, L, H), maskadd, (p_h, p_a) = ctx.rt, ctx.dims, ctx.maskadd, ctx.p
+        M, I, nh = B * L, rt.I, rt.nh
+        a = rt.arena
+        dev = dout.device
+        dy = dout.reshape(M, H)
+        if not dy.is_contiguous():
+            dy = dy.contiguous()
+        for (pf, x, qkv, att, lse, pre1, st1, a1, pre_g, inter, pre2, st2, s_attn, s1, s2) in reversed(ctx.saved):
+            # ---- BertOutput: LN(dropout(dense(inter)) + a1)
+            dpre2 = torch.empty(M, H, device=dev, dtype=BF16)
+            dpre2d = torch.empty(M, H, device=dev, dtype=BF16) if p_h > 0 else None
+            rt.call("mvptr_ln_bwd", dy, 0, 0, pre2, st2[0], st2[1], a.w(pf + "output.LayerNorm.weight"), dpre2, dpre2d,
+                    a.g(pf + "output.LayerNorm.weight"), a.g(pf + "output.LayerNorm.bias"),
+                    a.g(pf + "output.dense.bias"), M, H, 0.0, 0, p_h, s2)
+            dY2 = dpre2d if p_h > 0 else dpre2
+            wgrad(rt, dY2, H, inter, I, H, I, M, a.g(pf + "output.dense.weight"))
+            dpre_g = torch.empty(M, I, device=dev, dtype=BF16)
+            dgrad(rt, dY2, H, a.w(pf + "output.dense.weight"), I, M, H, I, dpre_g, gelu_grad_of=pre_g, ld_aux=I)
+            # ---- BertIntermediate
+            rt.call("mvptr_colsum", dpre_g, I, a.g(pf + "intermediate.dense.bias"), M, I)
+            wgrad(rt, dpre_g, I, a1, H, I, H, M, a.g(pf + "intermediate.dense.weight"))
+            da1 = torch.empty(M, H, device=dev, dtype=BF16)
+            dgrad(rt, dpre_g, I, a.w(pf + "intermediate.dense.weight"), H, M, I, H, da1, residual=dpre2, ld_aux=H)
+            # ---- BertSelfOutput: LN(dropout(dense(att)) + x)
+            dpre1 = torch.empty(M, H, device=dev, dtype=BF16)
+            dpre1d = torch.empty(M, H, device=dev, dtype=BF16) if p_h > 0 else None
+            rt.call("mvptr_ln_bwd", da1, 0, 0, pre1, st1[0], st1[1], a.w(pf + "attention.output.LayerNorm.weight"),
+                    dpre1, dpre1d, a.g(pf + "attention.output.LayerNorm.weight"),
+                    a.g(pf + "attention.output.LayerNorm.bias"), a.g(pf + "attention.output.dense.bias"), M, H, 0.0, 0,
+                    p_h, s1)
+            dY1 = dpre1d if p_h > 0 else dpre1
+            wgrad(rt, dY1, H, att, H, H, H, M, a.g(pf + "attention.output.dense.weight"))
+            datt = torch.empty(M, H, device=dev, dtype=BF16)
+            dgrad(rt, dY1, H, a.w(pf + "attention.output.dense.weight"), H, M, H, H, datt)
+            # ---- attention
+            dqkv = torch.empty(M, 3 * H, device=dev, dtype=BF16)
+            rt.call("mvptr_attn_bwd", qkv, 3 * H, maskadd, att, datt, H, lse, dqkv, B, L, nh, H, p_a, s_attn)
+            rt.call("mvptr_colsum", dqkv, 3 * H, a.g_span(pf + "attention.self.query.bias", 3 * H), M, 3 * H)
+            wgrad(rt, dqkv, 3 * H, x, H, 3 * H, H, M, a.g_span(pf + "attention.self.query.weight", 3 * H, H))
+            dx = torch.empty(M, H, device=dev, dtype=BF16)
+            dgrad(rt, dqkv, 3 * H, a.w_span(pf + "attention.self.query.weight", 3 * H, H), H, M, 3 * H, H, dx,
+                  residual=dpre1, ld_aux=H)
+            dy = dx
+        ctx.saved = None
+        return dy.view(B, L, H), None, None, None, None, None, None, None
+
+
+def encoder(rt, prefix, h, maskadd, n_layers, anchor, layer_lo=0, layer_hi=None):
+    hi = n_layers if layer_hi is None else layer_hi
+    save = torch.is_grad_enabled() and (h.requires_grad or anchor.requires_grad)
+    return EncoderFn.apply(h, maskadd, rt, prefix, layer_lo, hi, save, anchor)
+
+
+# ======================================================================================
+# Input embeddings
+# ======================================================================================
+class EmbedFn(Function):
+    """BertEmbeddings.forward, modeling_bert.py:262-277."""
+
+    @staticmethod
+    def forward(ctx, ids, type_ids, pos_ids, rt, prefix, save, anchor):
+        B, L = ids.shape
+        H, a, cfg = rt.H, rt.arena, rt.cfg
+        dev = ids.device
+        p = cfg.hidden_dropout_prob if rt.training else 0.0
+        seed = rt.next_seed()
+        y = torch.empty(B, L, H, device=dev, dtype=BF16)
+        pre = torch.empty(B * L, H, device=dev, dtype=BF16) if save else None
+        st = torch.empty(2, B * L, device=dev, dtype=F32) if save else None
+        rt.call("mvptr_embed_ln_fwd", ids, type_ids, pos_ids, a.w(prefix + ".word_embeddings.weight"),
+                a.w(prefix + ".position_embeddings.weight"), a.w(prefix + ".token_type_embeddings.weight"),
+                a.w(prefix + ".LayerNorm.weight"), a.w(prefix + ".LayerNorm.bias"), y, 0, 0, pre,
+                st[0] if save else None, st[1] if save else None, B, L, H, rt.eps, cfg.vocab_size,
+                cfg.max_position_embeddings, cfg.type_vocab_size, p, seed)
+        ctx.rt, ctx.s = rt, (prefix, ids, type_ids, pos_ids, pre, st, p, seed)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        rt = ctx.rt
+        prefix, ids, type_ids, pos_ids, pre, st, p, seed = ctx.s
+        B, L = ids.shape
+        embed_backward(rt, prefix, dy.contiguous(), 0, 0, ids, type_ids, pos_ids, pre, st, p, seed, B, L)
+        return (None,) * 7
+
+
+def embed_backward(rt, prefix, dy, rows_per_batch, batch_stride, ids, type_ids, pos_ids, pre, st, p, seed, B, L):
+    a, H, cfg = rt.arena, rt.H, rt.cfg
+    if pos_ids is not None:
+        raise NotImplementedError("backward through explicit position_ids is not supported")
+    dpre = torch.empty(B * L, H, device=dy.device, dtype=BF16)
+    rt.call("mvptr_ln_bwd", dy, rows_per_batch, batch_stride, pre, st[0], st[1], a.w(prefix + ".LayerNorm.weight"),
+            dpre, None, a.g(prefix + ".LayerNorm.weight"), a.g(prefix + ".LayerNorm.bias"), None, B * L, H, p, seed,
+            0.0, 0)
+    rt.call("mvptr_embed_bwd", dpre, ids, type_ids, a.g(prefix + ".word_embeddings.weight"),
+            a.g(prefix + ".position_embeddings.weight"), a.g(prefix + ".token_type_embeddings.weight"), B, L, H,
+            cfg.vocab_size, cfg.type_vocab_size, 0)
+
+
+class VisInputFn(Function):
+    """Tag embeddings + region projection + LN + dropout, written into one [B, Lt+R, H]
+    buffer (modeling_vlbert.py:481-482, 498-506: embeddings(b), img_embedding, LayerNorm,
+    dropout, torch.cat)."""
+
+    @staticmethod
+    def forward(ctx, ids_b, type_b, pos_b, img_feats, rt, bert, save, anchor):
+        B, Lt = ids_b.shape
+        R, Kimg = img_feats.shape[1], img_feats.shape[2]
+        H, a, cfg = rt.H, rt.arena, rt.cfg
+        dev = ids_b.device
+        Lv = Lt + R
+        p = cfg.hidden_dropout_prob if rt.training else 0.0
+        s_tag, s_img = rt.next_seed(), rt.next_seed()
+        out = torch.empty(B, Lv, H, device=dev, dtype=BF16)
+        emb = bert + "embeddings"
+        pre_t = torch.empty(B * Lt, H, device=dev, dtype=BF16) if save else None
+        st_t = torch.empty(2, B * Lt, device=dev, dtype=F32) if save else None
+        rt.call("mvptr_embed_ln_fwd", ids_b, type_b, pos_b, a.w(emb + ".word_embeddings.weight"),
+                a.w(emb + ".position_embeddings.weight"), a.w(emb + ".token_type_embeddings.weight"),
+                a.w(emb + ".LayerNorm.weight"), a.w(emb + ".LayerNorm.bias"), out, Lt, Lv * H, pre_t,
+                st_t[0] if save else None, st_t[1] if save else None, B, Lt, H, rt.eps, cfg.vocab_size,
+                cfg.max_position_embeddings, cfg.type_vocab_size, p, s_tag)
+        # region features -> bf16 with a 16-byte aligned pitch, then the K=2054 projection
+        Kp = _pad8(Kimg)
+        if img_feats.dtype not in (F32, BF16):
+            raise _lib.MvptrError(f"img_feats dtype {img_feats.dtype} unsupported (float32 or bfloat16)")
+        feats = img_feats if img_feats.is_contiguous() else img_feats.contiguous()
+        x16 = torch.empty(B * R, Kp, device=dev, dtype=BF16)
+        rt.call("mvptr_pad_cast", feats, int(feats.dtype == F32), Kimg, x16, Kp, B * R, Kimg)
+        w16 = rt.img_weight(bert + "img_embedding.weight")
+        pre_i = torch.empty(B * R, H, device=dev, dtype=BF16)
+        rt.gemm(x16, w16, pre_i, B * R, H, Kimg, lda=Kp, ldb=Kp, ldd=H, bias=a.w(bert + "img_embedding.bias"))
+        st_i = torch.empty(2, B * R, device=dev, dtype=F32) if save else None
+        img_rows = out.view(B * Lv, H)[Lt:]  # row (b, r) lives at b*Lv*H + (Lt + r)*H
+        if cfg.use_img_layernorm:
+            rt.call("mvptr_ln_fwd", pre_i, a.w(bert + "LayerNorm.weight"), a.w(bert + "LayerNorm.bias"), img_rows, R,
+                    Lv * H, st_i[0] if save else None, st_i[1] if save else None, B * R, H,
+                    float(cfg.img_layer_norm_eps), p, s_img)
+        else:
+            raise NotImplementedError("use_img_layernorm=0 is not supported by the CUDA path")
+        ctx.rt = rt
+        ctx.s = (bert, ids_b, type_b, pos_b, pre_t, st_t, x16, pre_i, st_i, p, s_tag, s_img, (B, Lt, R, Kimg, Kp))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        rt = ctx.rt
+        bert, ids_b, type_b, pos_b, pre_t, st_t, x16, pre_i, st_i, p, s_tag, s_img, (B, Lt, R, Kimg, Kp) = ctx.s
+        a, H = rt.arena, rt.H
+        Lv = Lt + R
+        dout = dout.contiguous()
+        embed_backward(rt, bert + "embeddings", dout, Lt, Lv * H, ids_b, type_b, pos_b, pre_t, st_t, p, s_tag, B, Lt)
+        d_img_rows = dout.view(B * Lv, H)[Lt:]
+        dpre = torch.empty(B * R, H, device=dout.device, dtype=BF16)
+        rt.call("mvptr_ln_bwd", d_img_rows, R, Lv * H, pre_i, st_i[0], st_i[1], a.w(bert + "LayerNorm.weight"), dpre,
+                None, a.g(bert + "LayerNorm.weight"), a.g(bert + "LayerNorm.bias"), a.g(bert + "img_embedding.bias"),
+                B * R, H, p, s_img, 0.0, 0)
+        # dW[H, 2054]: fp32 pitch 2054*4 B is not 16-byte aligned -> padded scratch, then add
+        scratch = torch.zeros(H, Kp, device=dout.device, dtype=F32)
+        wgrad(rt, dpre, H, x16, Kp, H, Kp, B * R, scratch, ldw=Kp)
+        a.g(bert + "img_embedding.weight").add_(scratch[:, :Kimg])
+        return (None,) * 8
+
+
+# ======================================================================================
+# Small dense heads on the [CLS] rows
+# ======================================================================================
+class ClsProjNormFn(Function):
+    """normalize(seq[:,0] @ proj): modeling_vlbert.py:525-526 / :717-718 -> fp32 [B,H]."""
+
+    @staticmethod
+    def forward(ctx, seq, rt, proj_name, anchor):
+        B, L, H = seq.shape
+        a = rt.arena
+        x32 = torch.empty(B, H, device=seq.device, dtype=F32)
+        # x @ P : B operand is P[k, n] with n contiguous -> MN-major
+        rt.gemm(seq, a.w(proj_name), x32, B, H, H, lda=L * H, ldb=H, ldd=H, b_mn=True)
+        y32 = torch.empty(B, H, device=seq.device, dtype=F32)
+        norm = torch.empty(B, device=seq.device, dtype=F32)
+        rt.call("mvptr_l2norm_fwd", x32, y32, None, norm, B, H)
+        ctx.rt, ctx.s = rt, (seq, proj_name, y32, norm)
+        return y32
+
+    @staticmethod
+    def backward(ctx, dy):
+        rt = ctx.rt
+        seq, proj_name, y32, norm = ctx.s
+        B, L, H = seq.shape
+        a = rt.arena
+        dx16 = torch.empty(B, H, device=dy.device, dtype=BF16)
+        rt.call("mvptr_l2norm_bwd", dy.contiguous(), y32, norm, dx16, B, H)
+        # dP[k, n] += sum_b x[b,k] dx[b,n]  ->  "out rows" = k (x is the A operand)
+        rt.gemm(seq, dx16, a.g(proj_name), H, H, B, lda=L * H, ldb=H, ldd=H, a_mn=True, b_mn=True, accumulate=True)
+        dcls = torch.empty(B, H, device=dy.device, dtype=BF16)
+        # dx_cls[b, k] = sum_n dx[b,n] P[k,n]  -> B operand P is K-major here
+        rt.gemm(dx16, a.w(proj_name), dcls, B, H, H, lda=H, ldb=H, ldd=H)
+        dseq = torch.zeros_like(seq)
+        dseq[:, 0] = dcls
+        return dseq, None, None, None
+
+
+class ClsDenseFn(Function):
+    """act(seq[:, 0] W^T + b) on the first token of every sequence: BertPooler
+    (modeling_bert.py:468-474, act=tanh) without materialising the gathered rows."""
+
+    @staticmethod
+    def forward(ctx, seq, rt, wname, bname, act, anchor):
+        B, L, H = seq.shape
+        a = rt.arena
+        N = a.w(wname).shape[0]
+        y = torch.empty(B, N, device=seq.device, dtype=BF16)
+        rt.gemm(seq, a.w(wname), y, B, N, H, lda=L * H, ldb=H, ldd=N, bias=a.w(bname), act=act)
+        ctx.rt, ctx.s = rt, (seq, wname, bname, act, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        rt = ctx.rt
+        seq, wname, bname, act, y = ctx.s
+        B, L, H = seq.shape
+        a = rt.arena
+        N = y.shape[1]
+        if act == "tanh":
+            yf = y.float()
+            dpre = (dy.float() * (1.0 - yf * yf)).to(BF16)
+        elif act is None:
+            dpre = dy.contiguous()
+        else:
+            raise NotImplementedError(act)
+        rt.call("mvptr_colsum", dpre, N, a.g(bname), B, N)
+        rt.gemm(dpre, seq, a.g(wname), N, H, B, lda=N, ldb=L * H, ldd=H, a_mn=True, b_mn=True, accumulate=True)
+        dcls = torch.empty(B, H, device=dy.device, dtype=BF16)
+        dgrad(rt, dpre, N, a.w(wname), H, B, N, H, dcls)
+        dseq = torch.zeros_like(seq)
+        dseq[:, 0] = dcls
+        return dseq, None, None, None, None, None
+
+
+class HeadTransformFn(Function):
+    """BertPredictionHeadTransform: LN(gelu(x W^T + b)), modeling_bert.py:487-491."""
+
+    @staticmethod
+    def forward(ctx, x, rt, prefix, anchor):
+        n, H = x.shape
+        a = rt.arena
+        dev = x.device
+        x = x.contiguous()
+        t = torch.empty(n, H, device=dev, dtype=BF16)
+        pre = torch.empty(n, H, device=dev, dtype=BF16)
+        rt.gemm(x, a.w(prefix + ".dense.weight"), t, n, H, H, lda=H, ldb=H, ldd=H, bias=a.w(prefix + ".dense.bias"),
+                act="gelu", pre_act=pre, ld_aux=H)
+        y = torch.empty(n, H, device=dev, dtype=BF16)
+        st = torch.empty(2, n, device=dev, dtype=F32)
+        rt.call("mvptr_ln_fwd", t, a.w(prefix + ".LayerNorm.weight"), a.w(prefix + ".LayerNorm.bias"), y, 0, 0, st[0],
+                st[1], n, H, rt.eps, 0.0, 0)
+        ctx.rt, ctx.s = rt, (x, prefix, t, pre, st)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        rt = ctx.rt
+        x, prefix, t, pre, st = ctx.s
+        n, H = x.shape
+        a = rt.arena
+        dev = dy.device
+        dt = torch.empty(n, H, device=dev, dtype=BF16)
+        rt.call("mvptr_ln_bwd", dy.contiguous(), 0, 0, t, st[0], st[1], a.w(prefix + ".LayerNorm.weight"), dt, None,
+                a.g(prefix + ".LayerNorm.weight"), a.g(prefix + ".LayerNorm.bias"), None, n, H, 0.0, 0, 0.0, 0)
+        dpre = torch.empty(n, H, device=dev, dtype=BF16)
+        rt.call("mvptr_gelu_bwd", dt, pre, dpre, n * H)
+        rt.call("mvptr_colsum", dpre, H, a.g(prefix + ".dense.bias"), n, H)
+        wgrad(rt, dpre, H, x, H, H, H, n, a.g(prefix + ".dense.weight"))
+        dx = torch.empty(n, H, device=dev, dtype=BF16)
+        dgrad(rt, dpre, H, a.w(prefix + ".dense.weight"), H, n, H, H, dx)
+        return dx, None, None, None
+
+
+def decoder_logits(rt, t, wname, n_out, bias_name):
+    """fp32 logits [n, pad8(n_out)] = t W[:n_out]^T + bias  (modeling_bert.py:514 / :531)."""
+    n, H = t.shape
+    a = rt.arena
+    pitch = _pad8(n_out)
+    logits = torch.empty(n, pitch, device=t.device, dtype=F32)
+    rt.gemm(t, a.w(wname), logits, n, n_out, H, lda=H, ldb=H, ldd=pitch, bias=a.w_span(bias_name, n_out))
+    return logits
+
+
+def decoder_backward(rt, t, dlogits, wname, n_out, bias_name):
+    n, H = t.shape
+    a = rt.arena
+    pitch = dlogits.shape[1]
+    # bias slot in the arena is padded to 8 elements, so the padded columns (zeros) are harmless
+    rt.call("mvptr_colsum", dlogits, pitch, a.g_span(bias_name, pitch), n, pitch)
+    wgrad(rt, dlogits, pitch, t, H, n_out, H, n, a.g(wname))
+    dt = torch.empty(n, H, device=t.device, dtype=BF16)
+    dgrad(rt, dlogits, pitch, a.w(wname), H, n, n_out, H, dt)
+    return dt
+
+
+class VocabCEFn(Function):
+    """decoder (tied to word_embeddings[:only_word_size]) + bias + CrossEntropy(ignore_index=-1):
+    modeling_bert.py:513-516 with modeling_vlbert.py:1212-1216 (tie), :1235 / :1249 (loss)."""
+
+    @staticmethod
+    def forward(ctx, t, labels, rt, wname, n_out, bias_name, anchor):
+        t = t.contiguous()
+        n = t.shape[0]
+        logits = decoder_logits(rt, t, wname, n_out, bias_name)
+        lse = torch.empty(n, device=t.device, dtype=F32)
+        acc = torch.zeros(2, device=t.device, dtype=F32)
+        rt.call("mvptr_ce_fwd", logits, logits.shape[1], labels, n, n_out, -1, lse, acc[0:1], acc[1:2])
+        ctx.rt, ctx.s = rt, (t, labels, wname, n_out, bias_name, logits, lse, acc)
+        return acc[0] / acc[1]
+
+    @staticmethod
+    def backward(ctx, g):
+        rt = ctx.rt
+        t, labels, wname, n_out, bias_name, logits, lse, acc = ctx.s
+        n = t.shape[0]
+        pitch = logits.shape[1]
+        dlogits = torch.empty(n, pitch, device=t.device, dtype=BF16)
+        gs = g.reshape(1).to(F32).contiguous()
+        rt.call("mvptr_ce_bwd", logits, pitch, labels, n, n_out, -1, lse, acc[1:2], gs, dlogits, pitch)
+        dt = decoder_backward(rt, t, dlogits, wname, n_out, bias_name)
+        ctx.s = None
+        return dt, None, None, None, None, None, None
+
+
+class DecoderFn(Function):
+    """Plain decoder logits (VQA answers / MLM inference): modeling_bert.py:514, :531."""
+
+    @staticmethod
+    def forward(ctx, t, rt, wname, n_out, bias_name, anchor):
+        t = t.contiguous()
+        logits = decoder_logits(rt, t, wname, n_out, bias_name)
+        ctx.rt, ctx.s = rt, (t, wname, n_out, bias_name, logits.shape[1])
+        return logits[:, :n_out]
+
+    @staticmethod
+    def backward(ctx, dl):
+        rt = ctx.rt
+        t, wname, n_out, bias_name, pitch = ctx.s
+        d16 = torch.zeros(t.shape[0], pitch, device=t.device, dtype=BF16)
+        d16[:, :n_out] = dl
+        return decoder_backward(rt, t, d16, wname, n_out, bias_name), None, None, None, None, None
+
+
+class BCEFn(Function):
+    """instance_bce_with_logits (modeling_vlbert.py:878-883) fused with the answer decoder."""
+
+    @staticmethod
+    def forward(ctx, t, labels, rt, wname, n_out, bias_name, anchor):
+        t = t.contiguous()
+        n = t.shape[0]
+        logits = decoder_logits(rt, t, wname, n_out, bias_name)
+        lab = labels.to(F32).contiguous()
+        loss = torch.zeros(1, device=t.device, dtype=F32)
+        rt.call("mvptr_bce_fwd", logits, logits.shape[1], lab, n, n_out, loss)
+        ctx.rt, ctx.s = rt, (t, lab, wname, n_out, bias_name, logits)
+        ctx.mark_non_differentiable(logits)
+        return loss[0], logits
+
+    @staticmethod
+    def backward(ctx, g, _):
+        rt = ctx.rt
+        t, lab, wname, n_out, bias_name, logits = ctx.s
+        n, pitch = logits.shape
+        dlogits = torch.empty(n, pitch, device=t.device, dtype=BF16)
+        rt.call("mvptr_bce_bwd", logits, pitch, lab, n, n_out, g.reshape(1).to(F32).contiguous(), dlogits, pitch)
+        return decoder_backward(rt, t, dlogits, wname, n_out, bias_name), None, None, None, None, None, None
+
+
+class SmallHeadFn(Function):
+    """x W^T + b with a handful of outputs (ITM / retrieval classifier, modeling_vlbert.py:1247,
+    :1680, :1708) -> fp32 logits."""
+
+    @staticmethod
+    def forward(ctx, x, rt, wname, bname, anchor):
+        x = x.contiguous()
+        n, H = x.shape
+        a = rt.arena
+        C = a.w(wname).shape[0]
+        logits = torch.empty(n, C, device=x.device, dtype=F32)
+        rt.call("mvptr_small_head_fwd", x, H, a.w(wname), a.w(bname), logits, n, H, C)
+        ctx.rt, ctx.s = rt, (x, wname, bname, C)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dl):
+        rt = ctx.rt
+        x, wname, bname, C = ctx.s
+        n, H = x.shape
+        a = rt.arena
+        dx = torch.empty(n, H, device=x.device, dtype=BF16)
+        rt.call("mvptr_small_head_bwd", dl.to(F32).contiguous(), x, H, a.w(wname), dx, H, a.g(wname), a.g(bname), n, H, C)
+        return dx, None, None, None, None
+
+
+class SmallCEFn(Function):
+    """CrossEntropyLoss over [n, C] fp32 logits, C small (modeling_vlbert.py:1251, :1682)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, rt):
+        n, C = logits.shape
+        logits = logits.contiguous()
+        loss = torch.zeros(1, device=logits.device, dtype=F32)
+        rt.call("mvptr_small_ce", logits, labels, n, C, loss, None, None)
+        ctx.rt, ctx.s = rt, (logits, labels)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        rt = ctx.rt
+        logits, labels = ctx.s
+        n, C = logits.shape
+        dl = torch.empty_like(logits)
+        scratch = torch.zeros(1, device=logits.device, dtype=F32)
+        rt.call("mvptr_small_ce", logits, labels, n, C, scratch, dl, g.reshape(1).to(F32).contiguous())
+        return dl, None, None
+
+
+# ======================================================================================
+# Contrastive similarity, VSC loss, hard negatives
+# ======================================================================================
+def _split_bf16(x32):
+    hi = x32.to(BF16)
+    lo = (x32 - hi.float()).to(BF16)
+    return hi, lo
+
+
+def sim_matrix(rt, a32, b32):
+    """fp32-accurate a . b^T from bf16 tensor-core passes (hi*hi + hi*lo + lo*hi): keeps the
+    ranking / arg-max decisions taken on it (modeling_vlbert.py:527-534, run_retrieval.py:739)
+    stable against bf16 operand rounding."""
+    n, H = a32.shape
+    m = b32.shape[0]
+    pitch = _pad8(m)
+    out = torch.empty(n, pitch, device=a32.device, dtype=F32)
+    ah, al = _split_bf16(a32)
+    bh, bl = _split_bf16(b32)
+    rt.gemm(ah, bh, out, n, m, H, lda=H, ldb=H, ldd=pitch)
+    rt.gemm(ah, bl, out, n, m, H, lda=H, ldb=H, ldd=pitch, accumulate=True)
+    rt.gemm(al, bh, out, n, m, H, lda=H, ldb=H, ldd=pitch, accumulate=True)
+    return out
+
+
+class SimFn(Function):
+    @staticmethod
+    def forward(ctx, gt, gi, rt):
+        sim = sim_matrix(rt, gt, gi)
+        ctx.rt, ctx.s = rt, (gt, gi)
+        return sim[:, : gi.shape[0]]
+
+    @staticmethod
+    def backward(ctx, dsim):
+        rt = ctx.rt
+        gt, gi = ctx.s
+        n, H = gt.shape
+        m = gi.shape[0]
+        pn, pm = _pad8(n), _pad8(m)
+        d16 = torch.zeros(n, pm, device=gt.device, dtype=BF16)
+        d16[:, :m] = dsim
+        gt16, gi16 = gt.to(BF16), gi.to(BF16)
+        dgt = torch.empty(n, H, device=gt.device, dtype=F32)
+        dgi = torch.empty(m, H, device=gt.device, dtype=F32)
+        rt.gemm(d16, gi16, dgt, n, H, m, lda=pm, ldb=H, ldd=H, b_mn=True)
+        rt.gemm(d16, gt16, dgi, m, H, n, lda=pm, ldb=H, ldd=H, a_mn=True, b_mn=True)
+        return dgt, dgi, None
+
+
+class VSCFn(Function):
+    """(CE(s*sim, arange) + CE(s*sim^T, arange))/2 with s = exp(logit_scale)
+    (modeling_vlbert.py:1238-1241) + in-batch hardest negatives (:530-534)."""
+
+    @staticmethod
+    def forward(ctx, sim, rt, ls_name, anchor):
+        B = sim.shape[0]
+        simc = sim.contiguous()
+        dev = sim.device
+        lse = torch.empty(2, B, device=dev, dtype=F32)
+        loss = torch.zeros(1, device=dev, dtype=F32)
+        hard = torch.empty(2, B, device=dev, dtype=torch.int64)
+        ls = rt.arena.master_of(ls_name)
+        if ls.dtype != F32:
+            ls = ls.float()
+        rt.call("mvptr_vsc_fwd", simc, B, ls, lse[0], lse[1], loss, hard[0], hard[1])
+        ctx.rt, ctx.s = rt, (simc, ls, lse, ls_name)
+        ctx.mark_non_differentiable(hard)
+        return loss[0], hard
+
+    @staticmethod
+    def backward(ctx, g, _):
+        rt = ctx.rt
+        simc, ls, lse, ls_name = ctx.s
+        B = simc.shape[0]
+        dsim = torch.empty_like(simc)
+        rt.call("mvptr_vsc_bwd", simc, B, ls, lse[0], lse[1], g.reshape(1).to(F32).contiguous(), dsim,
+                rt.arena.g(ls_name).reshape(1))
+        return dsim, None, None, None
+
+
+def hard_negatives(rt, sim):
+    """arg-max only (no loss): hn_mod='hard' of modeling_vlbert.py:530-534."""
+    B = sim.shape[0]
+    dev = sim.device
+    lse = torch.empty(2, B, device=dev, dtype=F32)
+    loss = torch.zeros(1, device=dev, dtype=F32)
+    hard = torch.empty(2, B, device=dev, dtype=torch.int64)
+    zero = torch.zeros(1, device=dev, dtype=F32)
+    rt.call("mvptr_vsc_fwd", sim.contiguous(), B, zero, lse[0], lse[1], loss, hard[0], hard[1])
+    return hard[0], hard[1]
+
+
+# ======================================================================================
+# Gathers
+# ======================================================================================
+class ConcatRowsFn(Function):
+    """out[r] = cat(a[row_a[r]], b[row_b[r], col0:]): the torch.cat / index_select assembly of the
+    joint and hard-negative stage-2 inputs, modeling_vlbert.py:542-566 and :586."""
+
+    @staticmethod
+    def forward(ctx, a3, b3, col0, row_a, row_b, rt):
+        a3, b3 = a3.contiguous(), b3.contiguous()
+        Ba, La, H = a3.shape
+        Lb = b3.shape[1]
+        rows = row_a.shape[0] if row_a is not None else Ba
+        out = torch.empty(rows, La + Lb - col0, H, device=a3.device, dtype=BF16)
+        rt.call("mvptr_concat_rows", a3, La, b3, Lb, col0, row_a, row_b, out, rows, H)
+        ctx.rt, ctx.s = rt, (a3.shape, b3.shape, col0, row_a, row_b, rows)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        rt = ctx.rt
+        sa, sb, col0, row_a, row_b, rows = ctx.s
+        dev = dout.device
+        da = torch.zeros(sa, device=dev, dtype=F32)
+        db = torch.zeros(sb, device=dev, dtype=F32)
+        rt.call("mvptr_concat_rows_bwd", dout.contiguous(), sa[1], sb[1], col0, row_a, row_b, da, db, rows, sa[2])
+        da16 = torch.empty(sa, device=dev, dtype=BF16)
+        db16 = torch.empty(sb, device=dev, dtype=BF16)
+        rt.call("mvptr_add_cast", da, None, da16, da.numel())
+        rt.call("mvptr_add_cast", db, None, db16, db.numel())
+        return da16, db16, None, None, None, None
+
+
+class GatherRowsFn(Function):
+    """torch.masked_select(...).reshape(-1, H) of the masked-LM rows (modeling_vlbert.py:1232, :1246)."""
+
+    @staticmethod
+    def forward(ctx, x2d, idx, rt):
+        n, H = idx.shape[0], x2d.shape[1]
+        out = torch.empty(n, H, device=x2d.device, dtype=BF16)
+        rt.call("mvptr_gather_rows", x2d, idx, out, n, H)
+        ctx.s = (x2d.shape, idx)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        shape, idx = ctx.s
+        dx = torch.zeros(shape, device=dout.device, dtype=BF16)
+        dx.index_copy_(0, idx, dout)  # indexes are unique: plain row copies
+        return dx, None, None
+
+
+class WRAFn(Function):
+    """Batched weakly-supervised phrase grounding: mean top-3-sampled cosine similarity of every
+    phrase against the regions of its own image and of one sampled other image
+    (modeling_vlbert.py:1288-1300, helpers :1502-1508, :1543-1596)."""
+
+    @staticmethod
+    def forward(ctx, seq, phrase_index, img_index, neg_img, rand_pos, rand_neg, rt):
+        seq = seq.contiguous()
+        B, Lt, H = seq.shape
+        dev = seq.device
+        maxp = _lib.lib().mvptr_wra_max_phrases()
+        P = rand_pos.shape[1]
+        out = torch.empty(2, B, device=dev, dtype=F32)
+        sel = torch.full((2, B, maxp), -1, device=dev, dtype=torch.int32)
+        rt.call("mvptr_wra_fwd", seq, B, Lt, H, phrase_index, img_index, neg_img, rand_pos, rand_neg, P, out[0],
+                out[1], sel[0], sel[1])
+        ctx.rt, ctx.s = rt, (seq, phrase_index, neg_img, sel)
+        return out[0], out[1]
+
+    @staticmethod
+    def backward(ctx, dpos, dneg):
+        rt = ctx.rt
+        seq, phrase_index, neg_img, sel = ctx.s
+        B, Lt, H = seq.shape
+        dseq = torch.zeros(B, Lt, H, device=seq.device, dtype=F32)
+        rt.call("mvptr_wra_bwd", seq, B, Lt, H, phrase_index, neg_img, sel[0], sel[1], dpos.contiguous(),
+                dneg.contiguous(), dseq)
+        d16 = torch.empty(B, Lt, H, device=seq.device, dtype=BF16)
+        rt.call("mvptr_add_cast", dseq, None, d16, dseq.numel())
+        return d16, None, None, None, None, None, None
+
+
+def mask_additive(rt, mask_a, mask_b=None, col0=0, row_a=None, row_b=None):
+    """(1 - mask) * -10000 for [a | b[:, col0:]] rows (modeling_vlbert.py:430-460, 542-566, 587)."""
+    La = mask_a.shape[1]
+    Lb = mask_b.shape[1] if mask_b is not None else 0
+    rows = row_a.shape[0] if row_a is not None else mask_a.shape[0]
+    out = torch.empty(rows, La + Lb - col0, device=mask_a.device, dtype=F32)
+    rt.call("mvptr_mask_prepare", mask_a, La, mask_b, Lb, col0, row_a, row_b, out, rows)
+    return out

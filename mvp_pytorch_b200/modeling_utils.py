@@ -1,0 +1,233 @@
+"""Config / checkpoint plumbing with the reference's interface.
+
+Mirrors (does not import) ``PretrainedConfig`` / ``PreTrainedModel`` of
+transformers/pytorch_transformers/modeling_utils.py:70-216, :219-526 and ``BertConfig`` of
+modeling_bert.py:158-225: same constructor arguments, ``from_pretrained(dir, config=...)``,
+``save_pretrained(dir)`` producing ``config.json`` + ``pytorch_model.bin`` with the
+reference's state-dict keys, so checkpoints move both ways.
+"""
+import copy
+import json
+import logging
+import os
+
+import torch
+from torch import nn
+
+logger = logging.getLogger(__name__)
+
+CONFIG_NAME = "config.json"
+WEIGHTS_NAME = "pytorch_model.bin"
+
+
+class PretrainedConfig(object):
+    def __init__(self, **kwargs):
+        self.finetuning_task = kwargs.pop("finetuning_task", None)
+        self.num_labels = kwargs.pop("num_labels", 2)
+        self.output_attentions = kwargs.pop("output_attentions", False)
+        self.output_hidden_states = kwargs.pop("output_hidden_states", False)
+        self.torchscript = kwargs.pop("torchscript", False)
+        self.pruned_heads = kwargs.pop("pruned_heads", {})
+
+    def save_pretrained(self, save_directory):
+        assert os.path.isdir(save_directory), "Saving path should be a directory where the model and configuration can be saved"
+        self.to_json_file(os.path.join(save_directory, CONFIG_NAME))
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, **kwargs):
+        return_unused_kwargs = kwargs.pop("return_unused_kwargs", False)
+        kwargs.pop("cache_dir", None)
+        path = pretrained_model_name_or_path
+        if os.path.isdir(path):
+            path = os.path.join(path, CONFIG_NAME)
+        if not os.path.isfile(path):
+            raise EnvironmentError(f"config file not found at {path} (no network: only local paths are supported)")
+        config = cls.from_json_file(path)
+        to_remove = []
+        for key, value in kwargs.items():
+            if hasattr(config, key):
+                setattr(config, key, value)
+                to_remove.append(key)
+        for key in to_remove:
+            kwargs.pop(key, None)
+        return (config, kwargs) if return_unused_kwargs else config
+
+    @classmethod
+    def from_dict(cls, json_object):
+        config = cls(vocab_size_or_config_json_file=-1)
+        for key, value in json_object.items():
+            config.__dict__[key] = value
+        return config
+
+    @classmethod
+    def from_json_file(cls, json_file):
+        with open(json_file, "r", encoding="utf-8") as reader:
+            return cls.from_dict(json.loads(reader.read()))
+
+    def __eq__(self, other):
+        return self.__dict__ == other.__dict__
+
+    def __repr__(self):
+        return str(self.to_json_string())
+
+    def to_dict(self):
+        return copy.deepcopy(self.__dict__)
+
+    def to_json_string(self):
+        return json.dumps(self.to_dict(), indent=2, sort_keys=True) + "\n"
+
+    def to_json_file(self, json_file_path):
+        with open(json_file_path, "w", encoding="utf-8") as writer:
+            writer.write(self.to_json_string())
+
+
+class BertConfig(PretrainedConfig):
+    """Same arguments and defaults as the reference BertConfig (modeling_bert.py:189-225)."""
+
+    def __init__(self, vocab_size_or_config_json_file=30522, hidden_size=768, num_hidden_layers=12,
+                 num_attention_heads=12, intermediate_size=3072, hidden_act="gelu", hidden_dropout_prob=0.1,
+                 attention_probs_dropout_prob=0.1, max_position_embeddings=512, type_vocab_size=2,
+                 initializer_range=0.02, layer_norm_eps=1e-12, **kwargs):
+        super().__init__(**kwargs)
+        if isinstance(vocab_size_or_config_json_file, str):
+            with open(vocab_size_or_config_json_file, "r", encoding="utf-8") as reader:
+                for key, value in json.loads(reader.read()).items():
+                    self.__dict__[key] = value
+        elif isinstance(vocab_size_or_config_json_file, int):
+            self.vocab_size = vocab_size_or_config_json_file
+            self.hidden_size = hidden_size
+            self.num_hidden_layers = num_hidden_layers
+            self.num_attention_heads = num_attention_heads
+            self.hidden_act = hidden_act
+            self.intermediate_size = intermediate_size
+            self.hidden_dropout_prob = hidden_dropout_prob
+            self.attention_probs_dropout_prob = attention_probs_dropout_prob
+            self.max_position_embeddings = max_position_embeddings
+            self.type_vocab_size = type_vocab_size
+            self.initializer_range = initializer_range
+            self.layer_norm_eps = layer_norm_eps
+        else:
+            raise ValueError("First argument must be either a vocabulary size (int)"
+                             "or the path to a pretrained model config file (str)")
+
+
+class PreTrainedModel(nn.Module):
+    config_class = BertConfig
+    base_model_prefix = "bert"
+
+    def __init__(self, config, *inputs, **kwargs):
+        super().__init__()
+        if not isinstance(config, PretrainedConfig):
+            raise ValueError("Parameter config should be an instance of PretrainedConfig")
+        self.config = config
+        self._rt = None          # engine.Runtime, built lazily on the first forward
+        self._rt_prefix = ""     # name prefix of this module inside the runtime's root model
+
+    # ---- B200 runtime ----------------------------------------------------------------
+    def runtime(self):
+        """The engine runtime of the ROOT model (the module whose forward the user called)."""
+        from . import engine
+        if self._rt is None or not self._rt.arena.valid():
+            self._rt = engine.Runtime(self, self.config)
+            self._rt_prefix = ""
+        return self._rt
+
+    def rebuild_arena(self):
+        self._rt = None
+        for m in self.modules():
+            if isinstance(m, PreTrainedModel):
+                m._rt = None
+
+    def _adopt(self, child, prefix):
+        child._rt = self._rt
+        child._rt_prefix = self._rt_prefix + prefix
+
+    def zero_grad(self, set_to_none=False):
+        """Gradients live in the flat arena: zero it in place and keep the views bound."""
+        if self._rt is not None and self._rt.arena.grad is not None:
+            self._rt.arena.zero_grad()
+        else:
+            super().zero_grad(set_to_none=set_to_none)
+
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)
+        self.rebuild_arena()  # .to()/.cuda()/.bfloat16() re-home the parameters
+        return out
+
+    # ---- reference API ------------------------------------------------------------------
+    def init_weights(self, module):
+        """modeling_bert.py:579-590."""
+        from .modeling_bert import BertLayerNorm
+        if isinstance(module, (nn.Linear, nn.Embedding)):
+            module.weight.data.normal_(mean=0.0, std=self.config.initializer_range)
+        elif isinstance(module, BertLayerNorm):
+            module.bias.data.zero_()
+            module.weight.data.fill_(1.0)
+        if isinstance(module, nn.Linear) and module.bias is not None:
+            module.bias.data.zero_()
+
+    def tie_weights(self):
+        pass
+
+    def save_pretrained(self, save_directory):
+        """config.json + pytorch_model.bin, modeling_utils.py:326-341."""
+        assert os.path.isdir(save_directory), "Saving path should be a directory where the model and configuration can be saved"
+        model_to_save = self.module if hasattr(self, "module") else self
+        model_to_save.config.save_pretrained(save_directory)
+        sd = {k: v.detach().clone().cpu() for k, v in model_to_save.state_dict().items()}
+        torch.save(sd, os.path.join(save_directory, WEIGHTS_NAME))
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, *model_args, **kwargs):
+        """Local-directory subset of modeling_utils.py:343-526 / oscar modeling_utils.py:689-874:
+        tolerant key matching (optional ``bert.`` prefix either way), size-mismatched
+        ``cls.seq_relationship`` tolerated (oscar modeling_utils.py:858-860), LayerNorm
+        gamma/beta renamed, unexpected keys (e.g. the tied ``decoder.weight``) ignored."""
+        config = kwargs.pop("config", None)
+        state_dict = kwargs.pop("state_dict", None)
+        kwargs.pop("cache_dir", None)
+        from_tf = kwargs.pop("from_tf", False)
+        if from_tf:
+            raise NotImplementedError("TensorFlow checkpoints are out of scope")
+        if config is None:
+            config = cls.config_class.from_pretrained(pretrained_model_name_or_path, **kwargs)
+        model = cls(config, *model_args)
+        if state_dict is None:
+            path = pretrained_model_name_or_path
+            if os.path.isdir(path):
+                path = os.path.join(path, WEIGHTS_NAME)
+            if not os.path.isfile(path):
+                raise EnvironmentError(f"weights not found at {path} (no network: only local paths are supported)")
+            state_dict = torch.load(path, map_location="cpu")
+        renamed = {}
+        for k, v in state_dict.items():
+            nk = k.replace("gamma", "weight") if k.endswith("gamma") else k
+            nk = nk.replace("beta", "bias") if nk.endswith("beta") else nk
+            renamed[nk] = v
+        own = model.state_dict()
+        pfx = cls.base_model_prefix + "."
+        has_pfx_model = any(k.startswith(pfx) for k in own)
+        has_pfx_ckpt = any(k.startswith(pfx) for k in renamed)
+        load = {}
+        for k, v in renamed.items():
+            kk = k
+            if has_pfx_model and not has_pfx_ckpt:
+                kk = pfx + k if (pfx + k) in own else k
+            elif has_pfx_ckpt and not has_pfx_model and k.startswith(pfx):
+                kk = k[len(pfx):]
+            if kk in own:
+                if own[kk].shape != v.shape:
+                    logger.info("skip %s: checkpoint shape %s != model shape %s", kk, tuple(v.shape), tuple(own[kk].shape))
+                    continue
+                load[kk] = v
+        missing = [k for k in own if k not in load]
+        unexpected = [k for k in renamed if k not in load and (pfx + k) not in load]
+        if missing:
+            logger.info("Weights of %s not initialized from pretrained model: %s", cls.__name__, missing)
+        if unexpected:
+            logger.info("Weights from pretrained model not used in %s: %s", cls.__name__, unexpected)
+        model.load_state_dict(load, strict=False)
+        if hasattr(model, "tie_weights"):
+            model.tie_weights()
+        model.eval()
+        return model

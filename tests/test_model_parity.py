@@ -1,0 +1,167 @@
+"""GPU parity: the CUDA path (through the C-ABI library) against the committed golden outputs of
+the REAL reference (tests/golden, tiny config) and against the CPU oracle at the base shape
+(hidden 768, 12 heads, 2054-d regions).
+
+Tolerances (BASELINE.json north_star): bf16 compute -> rtol 1e-2 on logits/losses (activations:
+rtol 2e-2 + atol 2e-2 on unit-scale LayerNorm outputs, i.e. a few bf16 ulps after 18 layers);
+integer outputs (labels, indices) bit-exact.
+"""
+import os
+
+import pytest
+import torch
+
+from oracle import mvptr_oracle as O
+import mvptr_parity_utils as P
+
+pytestmark = pytest.mark.gpu
+
+
+def _golden(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def test_rep_tiny_matches_reference_golden(golden_dir):
+    g = _golden(golden_dir, "rep_tiny.pt")
+    cfg = O.Cfg(**g["cfg"])
+    sd = O.random_state_dict(cfg, "rep", seed=g["wseed"])
+    B, La, Lt, R = g["dims"]
+    b = O.synthetic_batch(cfg, B, La, Lt, R, seed=g["bseed"], ragged=True)
+    model = P.build("BiImageBertRep", cfg, sd)
+    with torch.no_grad():
+        seq, pooled, (txt, vis) = model(max_tag_length=Lt, **P.to_cuda(b))
+    torch.cuda.synchronize()
+    joint_mask = torch.cat([b["attention_mask_a"], b["attention_mask_b"][:, Lt:]], 1)
+    P.valid_rows_close(txt, g["txt"], b["attention_mask_a"], 2e-2, 2e-2, "txt")
+    P.valid_rows_close(vis, g["vis"], b["attention_mask_b"], 2e-2, 2e-2, "vis")
+    P.valid_rows_close(seq, g["seq"], joint_mask, 2e-2, 3e-2, "seq")
+    P.close(pooled, g["pooled"], 2e-2, 2e-2, "pooled")
+
+
+def test_retrieval_tiny_matches_reference_golden(golden_dir):
+    g = _golden(golden_dir, "retrieval_tiny.pt")
+    cfg = O.Cfg(**g["cfg"])
+    sd = O.random_state_dict(cfg, "retrieval", seed=g["wseed"])
+    B, La, Lt, R = g["dims"]
+    b = P.to_cuda(O.synthetic_batch(cfg, B, La, Lt, R, seed=g["bseed"], ragged=True))
+    model = P.build("BiImageBertForRetrieval", cfg, sd)
+    with torch.no_grad():
+        model.forward_mod = "coarse"
+        gt, gi = model(max_tag_length=Lt, **b)
+        model.forward_mod = "fine"
+        fine = model(max_tag_length=Lt, **b)
+    P.close(gt, g["global_txt"], 1e-2, 1e-2, "global_txt")
+    P.close(gi, g["global_img"], 1e-2, 1e-2, "global_img")
+    P.close(fine, g["fine_logits"], 1e-2, 1e-2, "fine logits")
+    # train mode with the recorded randperm draw
+    model.forward_mod = "train"
+    model.train()
+    orig = torch.randperm
+    try:
+        torch.randperm = lambda n, **kw: g["dice"].to(kw.get("device", "cpu"))
+        total, logits, vsc, itm, labels = model(max_tag_length=Lt, **b)
+    finally:
+        torch.randperm = orig
+    assert torch.equal(labels.cpu(), g["train_labels"])  # integer work: bit exact
+    P.close(vsc, g["train_vsc"], 1e-2, 1e-2, "vsc")
+    P.close(logits, g["train_logits"], 1e-2, 1e-2, "itm logits")
+    P.close(total, g["train_total"], 1e-2, 1e-2, "total")
+    with pytest.raises(NotImplementedError):
+        model.forward_mod = "bogus"
+        model(max_tag_length=Lt, **b)
+
+
+def _run_pretrain(cfg, sd, b, Lt):
+    model = P.build("BiBertImgForPreTraining", cfg, sd, train=True, max_text_seq_length=b["input_ids_a"].shape[1])
+    cb = P.to_cuda(b)
+    orig = torch.randperm
+    try:
+        torch.randperm = lambda n, **kw: b["dice_index"].to(kw.get("device", "cpu"))
+        losses = model(input_ids_a=cb["input_ids_a"], token_type_ids_a=cb["token_type_ids_a"],
+                       attention_mask_a=cb["attention_mask_a"], masked_lm_labels_a=cb["masked_lm_labels_a"],
+                       input_ids_b=cb["input_ids_b"], token_type_ids_b=cb["token_type_ids_b"],
+                       attention_mask_b=cb["attention_mask_b"], masked_lm_labels_b=cb["masked_lm_labels_b"],
+                       img_feats=cb["img_feats"], max_tag_length=Lt, img_index=cb["img_index"],
+                       phrase_index=cb["phrase_index"],
+                       wra_choices=(cb["neg_img"], _pad_choices(cb["rand_pos"]), _pad_choices(cb["rand_neg"])))
+    finally:
+        torch.randperm = orig
+    model.zero_grad()
+    losses[0].backward()
+    torch.cuda.synchronize()
+    return model, losses
+
+
+def _pad_choices(r):
+    out = torch.zeros(r.shape[0], 16, dtype=torch.int64, device=r.device)
+    out[:, : r.shape[1]] = r
+    return out
+
+
+def test_pretrain_tiny_losses_and_grads_match_reference_golden(golden_dir):
+    g = _golden(golden_dir, "pretrain_tiny.pt")
+    cfg = O.Cfg(**g["cfg"])
+    sd = O.random_state_dict(cfg, "pretrain", seed=g["wseed"])
+    B, La, Lt, R = g["dims"]
+    b = O.synthetic_batch(cfg, B, La, Lt, R, seed=g["bseed"], ragged=True, with_labels=True)
+    model, losses = _run_pretrain(cfg, sd, b, Lt)
+    assert len(losses) == 6
+    names = ["total", "vis_mlm", "vsc", "mlm", "itm", "wra"]
+    for n, a, r in zip(names, losses, g["losses"]):
+        P.close(a.detach(), r, 1.5e-2, 5e-3, n)
+    params = dict(model.named_parameters())
+    for k, gr in g["grads"].items():
+        rel = P.rel_l2(params[k].grad, gr)
+        assert rel < 5e-2, f"grad {k}: relative L2 error {rel:.4f}"
+    worst = 0.0
+    for k, n in g["grad_norms"].items():
+        got = float(params[k].grad.float().norm())
+        worst = max(worst, abs(got - n) / max(n, 1e-3))
+        assert abs(got - n) <= 0.06 * n + 2e-3, f"grad norm {k}: {got} vs {n}"
+    for k in g["no_grad"]:
+        assert float(params[k].grad.abs().max()) == 0.0
+
+
+def test_vqa_tiny_matches_reference_golden(golden_dir):
+    g = _golden(golden_dir, "vqa_tiny.pt")
+    cfg = O.Cfg(**g["cfg"])
+    sd = O.random_state_dict(cfg, "vqa", seed=g["wseed"])
+    B, La, Lt, R = g["dims"]
+    b = P.to_cuda(O.synthetic_batch(cfg, B, La, Lt, R, seed=g["bseed"], ragged=True))
+    model = P.build("BiImageBertForVQA", cfg, sd, train=True)
+    out = model(labels=g["labels"].cuda(), max_tag_length=Lt, **b)
+    loss, logits = out[0], out[1]
+    model.zero_grad()
+    loss.backward()
+    P.close(loss.detach(), g["loss"], 1e-2, 1e-2, "vqa loss")
+    P.close(logits.detach(), g["logits"], 2e-2, 2e-2, "vqa logits")
+    params = dict(model.named_parameters())
+    for k, gr in g["grads"].items():
+        rel = P.rel_l2(params[k].grad, gr)
+        assert rel < 5e-2, f"grad {k}: relative L2 error {rel:.4f}"
+
+
+def test_base_shape_forward_matches_oracle():
+    """config 1: base cross-modal encoder forward, batch 8 x (35 text+phrase, 20 tags, 50 regions x 2054)."""
+    cfg = O.Cfg()
+    sd = O.random_state_dict(cfg, "rep", seed=0)
+    B, La, Lt, R = 8, 35, 20, 50
+    b = O.synthetic_batch(cfg, B, La, Lt, R, seed=1, ragged=True)
+    torch.set_num_threads(os.cpu_count() or 8)
+    with torch.no_grad():
+        o_seq, o_pooled, (o_txt, o_vis) = O.rep_forward(sd, cfg, max_tag_length=Lt, **b)
+    model = P.build("BiImageBertRep", cfg, sd)
+    with torch.no_grad():
+        seq, pooled, (txt, vis) = model(max_tag_length=Lt, **P.to_cuda(b))
+    joint_mask = torch.cat([b["attention_mask_a"], b["attention_mask_b"][:, Lt:]], 1)
+    P.valid_rows_close(txt, o_txt, b["attention_mask_a"], 2e-2, 3e-2, "txt")
+    P.valid_rows_close(vis, o_vis, b["attention_mask_b"], 2e-2, 3e-2, "vis")
+    P.valid_rows_close(seq, o_seq, joint_mask, 2e-2, 4e-2, "seq")
+    P.close(pooled, o_pooled, 2e-2, 2e-2, "pooled")
+    # masking property: ids at masked positions must not change valid outputs / pooled
+    b2 = {k: v.clone() for k, v in b.items()}
+    b2["input_ids_a"][b["attention_mask_a"] == 0] = 1234
+    with torch.no_grad():
+        seq2, pooled2, _ = model(max_tag_length=Lt, **P.to_cuda(b2))
+    assert torch.equal(pooled2, pooled)
+    assert torch.equal(seq2[joint_mask.bool().cuda()], seq[joint_mask.bool().cuda()])
