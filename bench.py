@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""Headline benchmark: MVP base 2-stage pre-training step (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One "step" = one pass of the hot path over one synthetic batch of 256 image-text pairs per GPU:
+BiBertImgForPreTraining forward (text / visual / cross-modal encoders incl. the hard-negative
+pass, MLM + tag-MLM + VSC + ITM + WRA losses) + backward + gradient all-reduce (N>1) + fused AdamW,
+bf16 compute with fp32 master weights, dropout 0.1.  Prints ONE JSON line (contract in the task
+statement): `value` = pairs/s with inputs resident in HBM, `e2e` = the same through the public
+model API with pinned-host inputs copied every step and the six losses read back every step.
+
+`--impl reference` times the reference algorithm's CPU implementation (the oracle port,
+oracle/mvptr_oracle.py -- the reference itself is Python and cannot travel to the GPU box) on the
+host cores for the same metric on a bounded batch.
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORK = dict(B=256, La=40, Lt=20, R=50, n_phrase=5, H=768, I=3072, layers=6, heads=12, vocab=86051,
+            only_word=30522, img_dim=2054, p_drop=0.1, mlm_prob=0.15)
+
+
+# ------------------------------------------------------------------------------------------
+# algorithmic work: multiply-add = 2 FLOPs, training step = 3 x forward
+# ------------------------------------------------------------------------------------------
+def flops_per_step(B, La, Lt, R, n_mask_txt, n_mask_tag, H=768, I=3072, nl=6, img_dim=2054, vocab=30522):
+    f_lin = 2 * (4 * H * H + 2 * H * I)
+
+    def enc(L):
+        return nl * (L * f_lin + 4 * L * L * H)
+
+    per_pair = 2 * R * img_dim * H + enc(La) + enc(Lt + R) + 2 * enc(La + R) + 4 * H * H + 2 * 2 * H * H
+    heads = (n_mask_txt + n_mask_tag) * (2 * H * H + 2 * H * vocab)
+    return 3.0 * (B * per_pair + heads)
+
+
+def synthetic_batch(seed, B, La, Lt, R, n_phrase, vocab, only_word, img_dim, mlm_prob, img_dtype):
+    """All-valid synthetic pre-training batch with the 13 tensors of oscar_tsv4.py:364-377."""
+    g = torch.Generator().manual_seed(seed)
+    ids_a = torch.randint(1000, only_word, (B, La), generator=g)
+    ids_a[:, La - n_phrase:] = torch.randint(only_word, vocab, (B, n_phrase), generator=g)  # phrase concepts
+    ids_b = torch.randint(1000, only_word, (B, Lt), generator=g)
+    img = torch.randn(B, R, img_dim, generator=g).to(img_dtype)
+    lab_a = torch.full((B, La), -1, dtype=torch.long)
+    pick = torch.rand(B, La - n_phrase, generator=g) < mlm_prob
+    lab_a[:, : La - n_phrase][pick] = torch.randint(1000, only_word, (int(pick.sum()),), generator=g)
+    lab_b = torch.full((B, Lt + R), -1, dtype=torch.long)
+    pick_b = torch.rand(B, Lt, generator=g) < mlm_prob
+    lab_b[:, :Lt][pick_b] = torch.randint(1000, only_word, (int(pick_b.sum()),), generator=g)
+    return dict(
+        input_ids_a=ids_a, token_type_ids_a=torch.zeros(B, La, dtype=torch.long),
+        attention_mask_a=torch.ones(B, La, dtype=torch.long), masked_lm_labels_a=lab_a,
+        input_ids_b=ids_b, token_type_ids_b=torch.ones(B, Lt, dtype=torch.long),
+        attention_mask_b=torch.ones(B, Lt + R, dtype=torch.long), masked_lm_labels_b=lab_b, img_feats=img,
+        phrase_index=torch.tensor([[La - n_phrase, La]] * B), img_index=torch.tensor([[La, La + R]] * B))
+
+
+def make_config(drop):
+    from mvp_pytorch_b200.modeling_utils import BertConfig
+    c = BertConfig(vocab_size_or_config_json_file=WORK["vocab"], hidden_dropout_prob=drop,
+                   attention_probs_dropout_prob=drop)
+    c.only_word_size, c.qa_answer_size, c.img_feature_dim = WORK["only_word"], 3129, WORK["img_dim"]
+    c.img_feature_type, c.use_img_layernorm, c.img_layer_norm_eps = "faster_r-cnn", 1, 1e-12
+    c.loss_type, c.num_contrast_classes, c.max_text_seq_length = "sfmx", 2, 35
+    return c
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons, power = [], [], set(), []
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2])); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                   "power_w_max": max(power), "samples": len(sm)}
+        return out
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("bf16_tflops", 1590.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1400.0, 1590.0, 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port) on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_pretrain_pairs_per_s(B_cpu, steps, warmup):
+    from oracle import mvptr_oracle as O  # the only product-side use of oracle/: reported CPU baseline
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.Cfg()
+    sd = {k: v.requires_grad_(k != "qa_head.weight" and k != "qa_head.bias")
+          for k, v in O.random_state_dict(cfg, "pretrain", seed=0, bf16_exact=False).items()}
+    W = WORK
+    b = O.synthetic_batch(cfg, B_cpu, W["La"], W["Lt"], W["R"], seed=2, ragged=False, with_labels=True)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        losses = O.pretrain_forward(sd, cfg, b["input_ids_a"], b["token_type_ids_a"], b["attention_mask_a"],
+                                    b["masked_lm_labels_a"], b["input_ids_b"], b["token_type_ids_b"],
+                                    b["attention_mask_b"], b["masked_lm_labels_b"], b["img_feats"],
+                                    max_tag_length=W["Lt"], img_index=b["img_index"], phrase_index=b["phrase_index"],
+                                    dice_index=b["dice_index"], neg_img=b["neg_img"], rand_pos=b["rand_pos"],
+                                    rand_neg=b["rand_neg"])
+        losses[0].backward()
+        with torch.no_grad():  # plain SGD-free AdamW-equivalent memory pass is negligible on CPU; zero grads
+            for v in sd.values():
+                v.grad = None
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    t = statistics.median(times)
+    return B_cpu / t, cores, t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B_cpu = 8
+    v, cores, t = cpu_pretrain_pairs_per_s(B_cpu, args.steps, args.warmup)
+    W = WORK
+    line = {
+        "impl": "reference", "metric": "image-text pairs/sec (pretrain step)", "value": v, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "MVP base 2-stage pre-training step (MLM+ITM+VSC+WRA), fwd+bwd, CPU fp32",
+                   "batch_per_step": B_cpu, "text_phrase_len": W["La"], "tags": W["Lt"], "regions": W["R"]},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "sample": f"oracle port of BiBertImgForPreTraining fwd+bwd, batch {B_cpu}, median of {args.steps}"},
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    from mvp_pytorch_b200 import _lib
+    from mvp_pytorch_b200.modeling_vlbert import BiBertImgForPreTraining
+    from mvp_pytorch_b200.optimization import AdamW
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    W = WORK
+    B = args.batch or W["B"]
+    torch.manual_seed(1234 + rank)
+    model = BiBertImgForPreTraining(make_config(W["p_drop"])).to(dev).train()
+    if world > 1:  # identical replicas: broadcast rank-0 weights through the flat arena
+        rt = model.runtime()
+        dist.broadcast(rt.arena.master, 0)
+    opt = AdamW.for_model(model, lr=1e-4, weight_decay=0.01, max_grad_norm=10.0)
+    rt = model.runtime()
+    arena = rt.arena
+
+    n_batches = 4
+    host = []
+    for i in range(n_batches):
+        b = synthetic_batch(100 * rank + i, B, W["La"], W["Lt"], W["R"], W["n_phrase"], W["vocab"], W["only_word"],
+                            W["img_dim"], W["mlm_prob"], torch.bfloat16)
+        host.append({k: v.pin_memory() for k, v in b.items()})
+    resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+    n_mask_txt = float(sum((b["masked_lm_labels_a"] > -1).sum() for b in host)) / n_batches
+    n_mask_tag = float(sum((b["masked_lm_labels_b"] > -1).sum() for b in host)) / n_batches
+    flops = flops_per_step(B, W["La"], W["Lt"], W["R"], n_mask_txt, n_mask_tag)
+
+    def train_step(batch):
+        model.zero_grad()
+        out = model(max_tag_length=W["Lt"], **batch)
+        out[0].backward()
+        if world > 1:
+            dist.all_reduce(arena.grad, op=dist.ReduceOp.AVG)
+        opt.step()
+        return out
+
+    def timed(run_one, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = rt.launches
+        s.record()
+        for i in range(steps):
+            run_one(i)
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, rt.launches - l0
+
+    # ---- warm-up (also builds the arena, cuTensorMap entry point, allocator pools)
+    for i in range(max(args.warmup, 3)):
+        out = train_step(resident[i % n_batches])
+    torch.cuda.synchronize()
+    assert all(math.isfinite(float(x)) for x in out), "non-finite loss in warm-up"
+
+    if args.profile_step:  # for ncu --profile-from-start off: exactly one steady-state step
+        torch.cuda.profiler.start()
+        train_step(resident[0])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+
+    # ---- (1) device-resident throughput
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, launches = timed(lambda i: train_step(resident[i % n_batches]), args.steps)
+    clocks = sampler.stop() if sampler else None
+    # +2 launches / step: fused AdamW and the gradient sum of squares
+    launches_per_step = launches / args.steps + 2
+
+    # ---- (2) end to end: pinned host inputs copied every step (prefetched on a copy stream), six
+    #          losses read back every step into pinned memory
+    copy_stream = torch.cuda.Stream()
+    loss_host = torch.zeros(args.steps, 6, dtype=torch.float32).pin_memory()
+    staged = [None, None]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    freed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def stage(i):
+        slot = i & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[slot])
+            staged[slot] = {k: v.to(dev, non_blocking=True) for k, v in host[i % n_batches].items()}
+            ready[slot].record(copy_stream)
+
+    def e2e_step(i):
+        slot = i & 1
+        if i == 0:
+            stage(0)
+        if i + 1 < args.steps:
+            stage(i + 1)
+        torch.cuda.current_stream().wait_event(ready[slot])
+        out = train_step(staged[slot])
+        loss_host[i].copy_(torch.stack([x.detach().float() for x in out]), non_blocking=True)
+        freed[slot].record()
+
+    for f in freed:
+        f.record()
+    ms_e2e, _ = timed(e2e_step, args.steps)
+    assert torch.isfinite(loss_host).all(), "non-finite loss in the end-to-end run"
+
+    # ---- (3) one instrumented step: CUDA events around every kernel launch -> per-kernel roofline
+    prof = None
+    if rank == 0:
+        _lib.profile_enable(True)
+        train_step(resident[0])
+        prof = _lib.profile_collect()
+        _lib.profile_enable(False)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    sustained, burst, hbm, how = peaks()
+    pairs = B * world * args.steps
+    value = pairs / (ms / 1e3)
+    e2e = pairs / (ms_e2e / 1e3)
+    gemm_ms = sum(v["ms"] for k, v in prof.items() if k.startswith("gemm["))
+    gemm_fl = sum(v["work"] for k, v in prof.items() if k.startswith("gemm["))
+    gemm_n = sum(v["launches"] for k, v in prof.items() if k.startswith("gemm["))
+    total_prof_ms = sum(v["ms"] for v in prof.values())
+    achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    top = sorted(((v["ms"], k, v["launches"]) for k, v in prof.items()), reverse=True)[:8]
+    line = {
+        "metric": "image-text pairs/sec (pretrain step)", "value": value, "unit": "pairs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "MVP base 2-stage pre-training step (MLM+tag-MLM+ITM+VSC+WRA), fwd+bwd+AdamW, "
+                               "dropout 0.1, BASELINE.json configs[1]",
+                   "batch_per_gpu": B, "global_batch": B * world, "text_phrase_len": W["La"], "tags": W["Lt"],
+                   "regions": W["R"], "img_dim": W["img_dim"], "parallelism": f"dp{world}",
+                   "master_weights": "fp32", "l2": "inputs larger than L2: per-step working set (~11 GB activations, "
+                                                    "2.4 GB weights/grads/moments) >> 126 MB L2, 4 rotating batches"},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
+                     "frac": achieved / sustained, "traffic": None,
+                     "kernel": "gemm_kernel (tcgen05/TMEM/TMA), all launches of one step",
+                     "launches_per_step": gemm_n, "gemm_ms_per_step": gemm_ms,
+                     "gemm_share_of_kernel_time": gemm_ms / total_prof_ms if total_prof_ms else None,
+                     "peak_source": how + " bf16_tflops_sustained (kernel timed inside a long step)",
+                     "whole_step": {"algorithmic_tflop": flops / 1e12,
+                                    "achieved_tflops": flops / (ms / args.steps / 1e3) / 1e12,
+                                    "frac_of_sustained": flops / (ms / args.steps / 1e3) / 1e12 / sustained,
+                                    "frac_of_burst": flops / (ms / args.steps / 1e3) / 1e12 / burst},
+                     "top_kernels_ms": [{"kernel": k, "ms": round(m, 3), "launches": n} for m, k, n in top]},
+        "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 24,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(round(launches_per_step * args.steps)),
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu:
+        v, cores, t = cpu_pretrain_pairs_per_s(8, 3, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
+                                "sample": f"oracle port of BiBertImgForPreTraining fwd+bwd (fp32), batch 8, "
+                                          f"median of 3 after 1 warm-up ({t:.2f} s/step)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="pairs per GPU (default: the 256 of BASELINE.json)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="warm up, then run ONE step between cudaProfilerStart/Stop (for ncu) and exit")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

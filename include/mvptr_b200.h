@@ -33,6 +33,10 @@ extern "C" {
 
 int mvptr_abi_version(void);
 const char* mvptr_last_error(void);
+/* Optional per-launch profiler: when enabled, every entry point brackets its kernel launches with
+ * CUDA events on the launching stream; collect() synchronises and returns (name, work, ms). */
+int mvptr_profile_enable(int on);
+int mvptr_profile_collect(const char** names_host, double* work_host, float* ms_host, int cap);
 
 /* ---- dense contraction (tcgen05 + TMEM + TMA) --------------------------------
  * D[M,N] (+)= epilogue( alpha * A[M,K] . B[N,K]^T )
@@ -199,6 +203,35 @@ int mvptr_gelu_bwd(const void* dy, const void* pre, void* dx, size_t n, void* st
 int mvptr_bce_fwd(const float* logits, int ld, const float* labels, int n, int C, float* loss, void* stream);
 int mvptr_bce_bwd(const float* logits, int ld, const float* labels, int n, int C, const float* gscale, void* dlogits,
                   int ld_d, void* stream);
+
+/* ---- one encoder layer per call --------------------------------------------------------
+ * CaptionBertLayer.forward (modeling_vlbert.py:191-199): attention (:63-103) -> BertSelfOutput
+ * (modeling_bert.py:348-352) -> BertIntermediate (:394-397) -> BertOutput (:407-411), and its
+ * backward.  The caller owns every buffer; [M = B*L rows]:
+ *   x,att,pre1,a1,pre2,out [M,H] bf16; qkv [M,3H]; pre_g,inter [M,I]; lse [B,nh,L] f32;
+ *   st1,st2 [2,M] f32 (mean | rstd).  save=0 (inference) skips lse/st/pre_g.
+ * Backward reads the saved activations + dout and writes dx; d* are scratch of the same
+ * shapes as their forward counterparts; g_* are fp32 gradient accumulators (+=). */
+typedef struct {
+  int B, L, H, I, nh, save;
+  float eps, p_hidden, p_attn;
+  uint32_t seed_attn, seed1, seed2;
+  const float* maskadd;
+  const void *w_qkv, *b_qkv, *w_o, *b_o, *ln1_g, *ln1_b, *w_i, *b_i, *w_o2, *b_o2, *ln2_g, *ln2_b;
+  const void* x;
+  void *qkv, *att;
+  float* lse;
+  void* pre1;
+  float* st1;
+  void *a1, *pre_g, *inter, *pre2;
+  float* st2;
+  void* out;
+  const void* dout;
+  void *dx, *dpre2, *dpre2d, *dpre_g, *da1, *dpre1, *dpre1d, *datt, *dqkv;
+  float *g_w_qkv, *g_b_qkv, *g_w_o, *g_b_o, *g_ln1_g, *g_ln1_b, *g_w_i, *g_b_i, *g_w_o2, *g_b_o2, *g_ln2_g, *g_ln2_b;
+} mvptr_layer_args;
+int mvptr_layer_fwd(const mvptr_layer_args* args, void* stream);
+int mvptr_layer_bwd(const mvptr_layer_args* args, void* stream);
 
 #ifdef __cplusplus
 }

@@ -33,11 +33,28 @@ class GemmArgs(ctypes.Structure):
     ]
 
 
+class LayerArgs(ctypes.Structure):
+    _P = ctypes.c_void_p
+    _fields_ = (
+        [(n, ctypes.c_int) for n in ("B", "L", "H", "I", "nh", "save")]
+        + [(n, ctypes.c_float) for n in ("eps", "p_hidden", "p_attn")]
+        + [(n, ctypes.c_uint32) for n in ("seed_attn", "seed1", "seed2")]
+        + [(n, ctypes.c_void_p) for n in (
+            "maskadd",
+            "w_qkv", "b_qkv", "w_o", "b_o", "ln1_g", "ln1_b", "w_i", "b_i", "w_o2", "b_o2", "ln2_g", "ln2_b",
+            "x", "qkv", "att", "lse", "pre1", "st1", "a1", "pre_g", "inter", "pre2", "st2", "out",
+            "dout", "dx", "dpre2", "dpre2d", "dpre_g", "da1", "dpre1", "dpre1d", "datt", "dqkv",
+            "g_w_qkv", "g_b_qkv", "g_w_o", "g_b_o", "g_ln1_g", "g_ln1_b", "g_w_i", "g_b_i", "g_w_o2", "g_b_o2",
+            "g_ln2_g", "g_ln2_b")])
+
+
 _CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "f": ctypes.c_float,
        "u": ctypes.c_uint32, "z": ctypes.c_size_t}
 # argument kinds of every entry point declared in include/mvptr_b200.h (stream last)
 SIGNATURES = {
     "mvptr_gemm": "pp",
+    "mvptr_layer_fwd": "pp",
+    "mvptr_layer_bwd": "pp",
     "mvptr_embed_ln_fwd": "ppppppppp" + "il" + "ppp" + "iiifiii" + "fup",
     "mvptr_embed_bwd": "pppppp" + "iiiiii" + "p",
     "mvptr_ln_fwd": "pppp" + "il" + "pp" + "iif" + "fup",
@@ -72,6 +89,56 @@ SIGNATURES = {
 }
 
 
+class LaunchProfiler:
+    """Brackets every C-ABI call with CUDA events on the launching stream (bench.py uses it for the
+    per-kernel roofline numbers).  Adds host overhead, so it is only enabled for dedicated
+    instrumented steps, never inside a timed region."""
+
+    def __init__(self):
+        self.records = []  # (name, work, start_event, end_event)
+
+    def wrap(self, name, work, fn):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        self.records.append((name, work, s, e))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, work, s, e in self.records:
+            d = out.setdefault(name, {"launches": 0, "ms": 0.0, "work": 0.0})
+            d["launches"] += 1
+            d["ms"] += s.elapsed_time(e)
+            d["work"] += work
+        return out
+
+
+PROFILER = None
+
+
+def profile_enable(on):
+    lib().mvptr_profile_enable(int(bool(on)))
+
+
+def profile_collect(cap=100000):
+    """{kernel name: {launches, ms, work}} of the launches recorded since profile_enable(True)."""
+    L = lib()
+    names = (ctypes.c_char_p * cap)()
+    work = (ctypes.c_double * cap)()
+    ms = (ctypes.c_float * cap)()
+    L.mvptr_profile_collect.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    n = L.mvptr_profile_collect(names, work, ms, cap)
+    out = {}
+    for i in range(n):
+        d = out.setdefault(names[i].decode(), {"launches": 0, "ms": 0.0, "work": 0.0})
+        d["launches"] += 1
+        d["ms"] += ms[i]
+        d["work"] += work[i]
+    return out
+
+
 def call(name, *args):
     """Call an entry point; torch tensors are passed as device pointers, None as NULL,
     and the current CUDA stream is appended."""
@@ -85,7 +152,26 @@ def call(name, *args):
         else:
             conv.append(a)
     conv.append(torch.cuda.current_stream().cuda_stream)
-    rc = getattr(L, name)(*conv)
+    if PROFILER is not None:
+        box = []
+        PROFILER.wrap(name, 0.0, lambda: box.append(getattr(L, name)(*conv)))
+        rc = box[0]
+    else:
+        rc = getattr(L, name)(*conv)
+    if rc != 0:
+        raise MvptrError(f"{name} failed (rc={rc}): {L.mvptr_last_error().decode()}")
+
+
+def layer_call(name, args, n_kernels):
+    """mvptr_layer_fwd / mvptr_layer_bwd with a filled LayerArgs."""
+    L = lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    if PROFILER is not None:
+        box = []
+        PROFILER.wrap(name, 0.0, lambda: box.append(getattr(L, name)(ctypes.byref(args), stream)))
+        rc = box[0]
+    else:
+        rc = getattr(L, name)(ctypes.byref(args), stream)
     if rc != 0:
         raise MvptrError(f"{name} failed (rc={rc}): {L.mvptr_last_error().decode()}")
 
@@ -147,5 +233,11 @@ def gemm(A, B, D, M, N, K, *, lda, ldb, ldd, a_mn=False, b_mn=False, accumulate=
             setattr(g, name, t.data_ptr())
     g.act = ACT[act]
     g.ld_aux, g.p_drop, g.seed, g.block_n = ld_aux, float(p_drop), int(seed) & 0xFFFFFFFF, block_n
-    check(lib().mvptr_gemm(ctypes.byref(g), stream_ptr()), "mvptr_gemm")
+    if PROFILER is not None:
+        kind = "mvptr_gemm[%s%s]" % ("mn" if a_mn else "k", "mn" if b_mn else "k")
+        box = []
+        PROFILER.wrap(kind, 2.0 * M * N * K, lambda: box.append(lib().mvptr_gemm(ctypes.byref(g), stream_ptr())))
+        check(box[0], "mvptr_gemm")
+    else:
+        check(lib().mvptr_gemm(ctypes.byref(g), stream_ptr()), "mvptr_gemm")
     return D

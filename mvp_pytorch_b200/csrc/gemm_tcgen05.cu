@@ -2,8 +2,9 @@
 //   TMA (cp.async.bulk.tensor, 128B swizzle) -> smem ring -> tcgen05.mma (UMMA 128xBNx16,
 //   fp32 accumulators in TMEM, two accumulator stages) -> tcgen05.ld epilogue ->
 //   swizzled smem slabs -> TMA store / TMA reduce-add.
-// One CTA per SM, 8 warps: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator,
-// 4..7 = epilogue (warp%4 selects the TMEM lane quarter).
+// One CTA per SM, 12 warps: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator,
+// 4..11 = epilogue (warp%4 selects the TMEM lane quarter, (warp-4)/4 the column half), so the
+// per-element epilogue work of a K=768 tile stays shorter than its 6144-cycle mainloop.
 // Operands may be K-major or MN-major (transposed views for dgrad/wgrad) -- both use
 // the canonical SWIZZLE_128B UMMA layouts, so no transposed copies are ever made.
 #include <cudaTypedefs.h>
@@ -18,7 +19,8 @@ namespace gemm {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;
+constexpr int kEpiWarps = 8;
 constexpr int kAccStages = 2;
 constexpr int kSlabBytes = 4096;  // 32 rows x 128 B, one TMA-store box
 
@@ -148,7 +150,7 @@ struct SmemLayout {
   static constexpr int kBBytes = BN * BK * 2;   // 16/32 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : 6;
-  static constexpr int kOutBytes = 4 * 2 * kSlabBytes;  // 4 epilogue warps x 2 slabs
+  static constexpr int kOutBytes = kEpiWarps * kSlabBytes;  // one TMA-store slab per epilogue warp
   static constexpr int kBarBytes = 256;
   static constexpr int kTotal = kStages * kStageBytes + kOutBytes + kBarBytes + 1024;  // + alignment slack
 };
@@ -185,7 +187,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(tfull_bar + 8 * i, 1);
-      mbar_init(tempty_bar + 8 * i, 4);
+      mbar_init(tempty_bar + 8 * i, kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -280,11 +282,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp >= 4) {
     // ======================= epilogue =======================
-    const int q = warp - 4;  // TMEM lane quarter == warp % 4
-    uint8_t* slab0 = out_stage + q * 2 * kSlabBytes;
-    constexpr int kColsPerStore = F32OUT ? 32 : 64;
+    const int q = warp & 3;          // TMEM lane quarter == warp % 4
+    const int hf = (warp - 4) >> 2;  // column half of the tile
+    uint8_t* slab = out_stage + (warp - 4) * kSlabBytes;
+    constexpr int kHalf = BN / 2;
+    constexpr int kChunks = kHalf / 32;  // 32-column TMEM loads per tile per warp
+    constexpr int kChunksPerStore = F32OUT ? 1 : 2;
+    const bool bias_vec = p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
     int local = 0;
-    int n_stores = 0;
+    bool store_pending = false;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++local) {
       const int split = t / tiles_mn;
       const int mn = t - split * tiles_mn;
@@ -294,102 +300,128 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int m = m_blk * BM + q * 32 + lane;
       const bool row_ok = m < p.M;
       const bool lead = (split == 0);  // bias / residual are added by the first K-split only
+      const int n_base = n_blk * BN + hf * kHalf;
       mbar_wait(tfull_bar + 8 * as, aph);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + hf * kHalf;
 
-      for (int g = 0; g < BN / kColsPerStore; ++g) {
-        const int ng0 = n_blk * BN + g * kColsPerStore;
-        if (ng0 >= p.N) break;
-        uint8_t* slab = slab0 + (n_stores & 1) * kSlabBytes;
-        if (n_stores >= 2) {
-          if (lane == 0) tma_wait_read<1>();
-          __syncwarp();
+      uint32_t rbuf[2][32];
+      if (n_base < p.N) tc_ld32(t_row, rbuf[0]);
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const int n0 = n_base + c * 32;
+        if (n0 >= p.N) break;
+        tc_wait_ld();
+        if (c + 1 < kChunks && n0 + 32 < p.N) tc_ld32(t_row + (c + 1) * 32, rbuf[(c + 1) & 1]);
+        float v[32];
+        if (p.alpha != 1.0f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rbuf[c & 1][j]) * p.alpha;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rbuf[c & 1][j]);
         }
-#pragma unroll
-        for (int h = 0; h < kColsPerStore / 32; ++h) {
-          const int n0 = ng0 + h * 32;
-          if (n0 >= p.N) break;
-          uint32_t r[32];
-          tc_ld32(t_row + g * kColsPerStore + h * 32, r);
-          tc_wait_ld();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-          if (p.bias != nullptr && lead) {
+        if (p.bias != nullptr && lead) {
+          if (bias_vec && n0 + 32 <= p.N) {
             if (p.bias_is_bf16) {
-              const bf16* b = reinterpret_cast<const bf16*>(p.bias);
+              const bf16x8* b = reinterpret_cast<const bf16x8*>(reinterpret_cast<const bf16*>(p.bias) + n0);
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) v[j] += __bfloat162float(__ldg(b + n0 + j));
-            } else {
-              const float* b = reinterpret_cast<const float*>(p.bias);
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) v[j] += __ldg(b + n0 + j);
-            }
-          }
-          const size_t aux_off = (size_t)m * p.ld_aux + n0;
-          if (p.pre_act != nullptr && row_ok) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (n0 + u * 8 + 8 <= p.N) *reinterpret_cast<bf16x8*>(p.pre_act + aux_off + u * 8) = pack8(v + u * 8);
-          }
-          if (p.act == 1) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-          } else if (p.act == 2) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
-          }
-          if (p.gelu_grad_of != nullptr && row_ok) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (n0 + u * 8 + 8 <= p.N) {
+              for (int u = 0; u < 4; ++u) {
                 float x[8];
-                unpack8(*reinterpret_cast<const bf16x8*>(p.gelu_grad_of + aux_off + u * 8), x);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[u * 8 + j] *= gelu_erf_grad(x[j]);
-              }
-          }
-          if (p.use_dropout) {
-            const uint32_t base = (uint32_t)m * (uint32_t)p.N + (uint32_t)n0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = dropout_keep(p.seed, base + j, p.keep_thr) ? v[j] * p.inv_keep : 0.f;
-          }
-          if (p.residual != nullptr && row_ok && lead) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (n0 + u * 8 + 8 <= p.N) {
-                float x[8];
-                unpack8(*reinterpret_cast<const bf16x8*>(p.residual + aux_off + u * 8), x);
+                unpack8(__ldg(reinterpret_cast<const uint4*>(b + u)), x);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[u * 8 + j] += x[j];
               }
-          }
-          // registers -> 128B-swizzled slab (16-byte unit u of row r lands at unit u ^ (r & 7))
-          uint8_t* row = slab + lane * 128;
-          if constexpr (F32OUT) {
+            } else {
+              const float4* b = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.bias) + n0);
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-              *reinterpret_cast<float4*>(row + ((u ^ (lane & 7)) << 4)) =
-                  make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+              for (int u = 0; u < 8; ++u) {
+                const float4 x = __ldg(b + u);
+                v[4 * u] += x.x; v[4 * u + 1] += x.y; v[4 * u + 2] += x.z; v[4 * u + 3] += x.w;
+              }
+            }
+          } else if (p.bias_is_bf16) {
+            const bf16* b = reinterpret_cast<const bf16*>(p.bias);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) v[j] += __bfloat162float(__ldg(b + n0 + j));
           } else {
+            const float* b = reinterpret_cast<const float*>(p.bias);
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              *reinterpret_cast<bf16x8*>(row + (((h * 4 + u) ^ (lane & 7)) << 4)) = pack8(v + u * 8);
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) v[j] += __ldg(b + n0 + j);
           }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          if (p.accumulate)
-            tma_reduce_add_2d(&tmD, smem_u32(slab), ng0, m_blk * BM + q * 32);
-          else
-            tma_store_2d(&tmD, smem_u32(slab), ng0, m_blk * BM + q * 32);
-          tma_commit();
+        const size_t aux_off = (size_t)m * p.ld_aux + n0;
+        if (p.pre_act != nullptr && row_ok) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (n0 + u * 8 + 8 <= p.N) *reinterpret_cast<bf16x8*>(p.pre_act + aux_off + u * 8) = pack8(v + u * 8);
         }
-        ++n_stores;
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        } else if (p.act == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+        }
+        if (p.gelu_grad_of != nullptr && row_ok) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (n0 + u * 8 + 8 <= p.N) {
+              float x[8];
+              unpack8(*reinterpret_cast<const bf16x8*>(p.gelu_grad_of + aux_off + u * 8), x);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[u * 8 + j] *= gelu_erf_grad(x[j]);
+            }
+        }
+        if (p.use_dropout) {
+          const uint32_t base = (uint32_t)m * (uint32_t)p.N + (uint32_t)n0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = dropout_keep(p.seed, base + j, p.keep_thr) ? v[j] * p.inv_keep : 0.f;
+        }
+        if (p.residual != nullptr && row_ok && lead) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (n0 + u * 8 + 8 <= p.N) {
+              float x[8];
+              unpack8(*reinterpret_cast<const bf16x8*>(p.residual + aux_off + u * 8), x);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[u * 8 + j] += x[j];
+            }
+        }
+        // registers -> 128B-swizzled slab (16-byte unit u of row r lands at unit u ^ (r & 7))
+        const int h = c % kChunksPerStore;  // position of this chunk inside the store box
+        if (h == 0 && store_pending) {
+          if (lane == 0) tma_wait_read<0>();  // previous box has been read out of the slab
+          __syncwarp();
+          store_pending = false;
+        }
+        uint8_t* row = slab + lane * 128;
+        if constexpr (F32OUT) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            *reinterpret_cast<float4*>(row + ((u ^ (lane & 7)) << 4)) =
+                make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            *reinterpret_cast<bf16x8*>(row + (((h * 4 + u) ^ (lane & 7)) << 4)) = pack8(v + u * 8);
+        }
+        const bool last_in_box = (h == kChunksPerStore - 1) || (n0 + 32 >= p.N) || (c == kChunks - 1);
+        if (last_in_box) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            const int ng0 = n0 - h * 32;
+            if (p.accumulate)
+              tma_reduce_add_2d(&tmD, smem_u32(slab), ng0, m_blk * BM + q * 32);
+            else
+              tma_store_2d(&tmD, smem_u32(slab), ng0, m_blk * BM + q * 32);
+            tma_commit();
+          }
+          store_pending = true;
+        }
       }
       // all TMEM reads of this accumulator stage are complete (wait::ld above)
       tc_fence_before();
@@ -533,5 +565,7 @@ extern "C" int mvptr_gemm(const mvptr_gemm_args* g, void* stream_) {
   else             rc = make_map(&td, g->D, false, g->N, g->M, (uint64_t)g->ldd * 2, 64, 32);
   if (rc) return rc;
 
+  static const char* kNames[4] = {"gemm[k,k]", "gemm[k,mn]", "gemm[mn,k]", "gemm[mn,mn]"};
+  MVPTR_PROF(kNames[(g->a_mn ? 2 : 0) | (g->b_mn ? 1 : 0)], 2.0 * g->M * g->N * g->K, stream);
   return bn == 256 ? dispatch<256>(g, ta, tb, td, p, stream) : dispatch<128>(g, ta, tb, td, p, stream);
 }

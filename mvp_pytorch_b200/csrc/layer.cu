@@ -1,0 +1,119 @@
+// One encoder layer (CaptionBertLayer, modeling_vlbert.py:191-199) forward / backward as ONE
+// C-ABI call each: the host launches the 7 (fwd) / 13 (bwd) kernels back to back from C++, so
+// the Python side pays one ctypes call per layer instead of one per kernel.
+#include "common.cuh"
+
+#define TRY(expr)              \
+  do {                         \
+    int rc__ = (expr);         \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+static mvptr_gemm_args gemm_base(const void* A, int lda, const void* B, int ldb, void* D, int ldd, int M, int N, int K) {
+  mvptr_gemm_args g;
+  memset(&g, 0, sizeof(g));
+  g.A = A; g.B = B; g.D = D;
+  g.M = M; g.N = N; g.K = K;
+  g.lda = lda; g.ldb = ldb; g.ldd = ldd;
+  g.alpha = 1.0f;
+  g.bias_is_bf16 = 1;
+  return g;
+}
+
+static int split_k_for(int m_out, int n_out, int k) {
+  const int tiles = ((m_out + 127) / 128) * ((n_out + 255) / 256);
+  const int kb = (k + 63) / 64;
+  int s = (2 * mvptr::kNumSMs) / tiles;
+  if (s < 1) s = 1;
+  int cap = kb >= 4 ? kb / 4 : 1;
+  if (s > cap) s = cap;
+  return s < 1 ? 1 : s;
+}
+
+// dW[n_out, k_in] += dY[tokens, n_out]^T . X[tokens, k_in]
+static int wgrad(const void* dY, int ld_dy, const void* X, int ld_x, int n_out, int k_in, int tokens, float* dW,
+                 cudaStream_t s) {
+  mvptr_gemm_args g = gemm_base(dY, ld_dy, X, ld_x, dW, k_in, n_out, k_in, tokens);
+  g.a_mn = 1; g.b_mn = 1; g.d_is_f32 = 1; g.accumulate = 1;
+  g.split_k = split_k_for(n_out, k_in, tokens);
+  return mvptr_gemm(&g, s);
+}
+
+extern "C" int mvptr_layer_fwd(const mvptr_layer_args* a, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const int M = a->B * a->L, H = a->H, I = a->I;
+  const bool save = a->save != 0;
+  // fused QKV projection (three nn.Linear of modeling_bert.py:293-295; weights adjacent in the arena)
+  {
+    mvptr_gemm_args g = gemm_base(a->x, H, a->w_qkv, H, a->qkv, 3 * H, M, 3 * H, H);
+    g.bias = a->b_qkv;
+    TRY(mvptr_gemm(&g, s));
+  }
+  TRY(mvptr_attn_fwd(a->qkv, 3 * H, a->maskadd, a->att, H, save ? a->lse : nullptr, a->B, a->L, a->nh, H, a->p_attn,
+                     a->seed_attn, s));
+  {  // BertSelfOutput: LN(dropout(dense(att)) + x), modeling_bert.py:348-352
+    mvptr_gemm_args g = gemm_base(a->att, H, a->w_o, H, a->pre1, H, M, H, H);
+    g.bias = a->b_o; g.residual = a->x; g.ld_aux = H; g.p_drop = a->p_hidden; g.seed = a->seed1;
+    TRY(mvptr_gemm(&g, s));
+  }
+  TRY(mvptr_ln_fwd(a->pre1, a->ln1_g, a->ln1_b, a->a1, 0, 0, save ? a->st1 : nullptr, save ? a->st1 + M : nullptr, M, H,
+                   a->eps, 0.f, 0, s));
+  {  // BertIntermediate: gelu(dense(a1)), modeling_bert.py:394-397
+    mvptr_gemm_args g = gemm_base(a->a1, H, a->w_i, H, a->inter, I, M, I, H);
+    g.bias = a->b_i; g.act = 1; g.pre_act = save ? a->pre_g : nullptr; g.ld_aux = I;
+    TRY(mvptr_gemm(&g, s));
+  }
+  {  // BertOutput: LN(dropout(dense(inter)) + a1), modeling_bert.py:407-411
+    mvptr_gemm_args g = gemm_base(a->inter, I, a->w_o2, I, a->pre2, H, M, H, I);
+    g.bias = a->b_o2; g.residual = a->a1; g.ld_aux = H; g.p_drop = a->p_hidden; g.seed = a->seed2;
+    TRY(mvptr_gemm(&g, s));
+  }
+  TRY(mvptr_ln_fwd(a->pre2, a->ln2_g, a->ln2_b, a->out, 0, 0, save ? a->st2 : nullptr, save ? a->st2 + M : nullptr, M, H,
+                   a->eps, 0.f, 0, s));
+  return 0;
+}
+
+extern "C" int mvptr_layer_bwd(const mvptr_layer_args* a, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const int M = a->B * a->L, H = a->H, I = a->I;
+  const bool drop = a->p_hidden > 0.f;
+  // ---- BertOutput
+  TRY(mvptr_ln_bwd(a->dout, 0, 0, a->pre2, a->st2, a->st2 + M, a->ln2_g, a->dpre2, drop ? a->dpre2d : nullptr, a->g_ln2_g,
+                   a->g_ln2_b, a->g_b_o2, M, H, 0.f, 0, a->p_hidden, a->seed2, s));
+  const void* dY2 = drop ? a->dpre2d : a->dpre2;
+  TRY(wgrad(dY2, H, a->inter, I, H, I, M, a->g_w_o2, s));
+  {  // dpre_g = (dY2 . W_o2) * gelu'(pre_g)
+    mvptr_gemm_args g = gemm_base(dY2, H, a->w_o2, I, a->dpre_g, I, M, I, H);
+    g.b_mn = 1; g.gelu_grad_of = a->pre_g; g.ld_aux = I;
+    TRY(mvptr_gemm(&g, s));
+  }
+  // ---- BertIntermediate
+  TRY(mvptr_colsum(a->dpre_g, I, a->g_b_i, M, I, s));
+  TRY(wgrad(a->dpre_g, I, a->a1, H, I, H, M, a->g_w_i, s));
+  {  // da1 = dpre_g . W_i + dpre2 (residual branch)
+    mvptr_gemm_args g = gemm_base(a->dpre_g, I, a->w_i, H, a->da1, H, M, H, I);
+    g.b_mn = 1; g.residual = a->dpre2; g.ld_aux = H;
+    TRY(mvptr_gemm(&g, s));
+  }
+  // ---- BertSelfOutput
+  TRY(mvptr_ln_bwd(a->da1, 0, 0, a->pre1, a->st1, a->st1 + M, a->ln1_g, a->dpre1, drop ? a->dpre1d : nullptr, a->g_ln1_g,
+                   a->g_ln1_b, a->g_b_o, M, H, 0.f, 0, a->p_hidden, a->seed1, s));
+  const void* dY1 = drop ? a->dpre1d : a->dpre1;
+  TRY(wgrad(dY1, H, a->att, H, H, H, M, a->g_w_o, s));
+  {
+    mvptr_gemm_args g = gemm_base(dY1, H, a->w_o, H, a->datt, H, M, H, H);
+    g.b_mn = 1;
+    TRY(mvptr_gemm(&g, s));
+  }
+  // ---- attention
+  TRY(mvptr_attn_bwd(a->qkv, 3 * H, a->maskadd, a->att, a->datt, H, a->lse, a->dqkv, a->B, a->L, a->nh, H, a->p_attn,
+                     a->seed_attn, s));
+  TRY(mvptr_colsum(a->dqkv, 3 * H, a->g_b_qkv, M, 3 * H, s));
+  TRY(wgrad(a->dqkv, 3 * H, a->x, H, 3 * H, H, M, a->g_w_qkv, s));
+  {  // dx = dqkv . W_qkv + dpre1 (residual branch)
+    mvptr_gemm_args g = gemm_base(a->dqkv, 3 * H, a->w_qkv, H, a->dx, H, M, H, 3 * H);
+    g.b_mn = 1; g.residual = a->dpre1; g.ld_aux = H;
+    TRY(mvptr_gemm(&g, s));
+  }
+  return 0;
+}

@@ -314,6 +314,7 @@ using namespace mvptr;
 
 extern "C" int mvptr_ce_fwd(const float* logits, int ld, const int64_t* labels, int n, int V, int ignore_index,
                             float* row_lse, float* loss_sum, float* n_valid, void* stream) {
+  MVPTR_PROF("ce_fwd", 4.0*n*V, stream);
   if (n <= 0) return 0;
   ce_fwd_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(logits, ld, labels, V, ignore_index, row_lse, loss_sum, n_valid);
   MVPTR_CHECK_LAUNCH("ce_fwd");
@@ -322,6 +323,7 @@ extern "C" int mvptr_ce_fwd(const float* logits, int ld, const int64_t* labels, 
 extern "C" int mvptr_ce_bwd(const float* logits, int ld, const int64_t* labels, int n, int V, int ignore_index,
                             const float* row_lse, const float* n_valid, const float* gscale, void* dlogits, int ld_d,
                             void* stream) {
+  MVPTR_PROF("ce_bwd", 6.0*n*V, stream);
   if (n <= 0) return 0;
   ce_bwd_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(logits, ld, labels, V, ignore_index, row_lse, n_valid, gscale,
                                                      (bf16*)dlogits, ld_d);
@@ -388,6 +390,7 @@ extern "C" int mvptr_small_ce(const float* logits, const int64_t* labels, int n,
 extern "C" int mvptr_adamw(float* p, const float* g, float* m, float* v, void* p16, size_t n, size_t decay_end, float lr,
                            float beta1, float beta2, float eps, float weight_decay, int step, int correct_bias,
                            const float* grad_sumsq, float max_norm, void* stream) {
+  MVPTR_PROF("adamw", 30.0*n, stream);
   if (n == 0) return 0;
   if (n & 3) MVPTR_FAIL(MVPTR_ERR_ARG, "adamw: arena size must be a multiple of 4");
   float step_size = lr;
@@ -400,6 +403,7 @@ extern "C" int mvptr_adamw(float* p, const float* g, float* m, float* v, void* p
   return 0;
 }
 extern "C" int mvptr_sumsq(const float* g, size_t n, float* out, void* stream) {
+  MVPTR_PROF("sumsq", 4.0*n, stream);
   if (n == 0) return 0;
   if (n & 3) MVPTR_FAIL(MVPTR_ERR_ARG, "sumsq: n must be a multiple of 4");
   size_t blocks = (n / 4 + 255) / 256;

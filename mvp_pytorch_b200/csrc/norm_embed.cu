@@ -151,31 +151,36 @@ ln_fwd_kernel(const bf16* __restrict__ x_in, const bf16* __restrict__ gamma, con
 //   dx_drop = dx * input-dropout mask (the dropout that sat between the dense and the
 //             residual add, modeling_bert.py:350-351) ; dbias += sum_r dx_drop
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+template <int NC, bool DBIAS>
+__global__ void __launch_bounds__(128, 3)
 ln_bwd_kernel(const bf16* __restrict__ dy, RowMap dymap, const bf16* __restrict__ x_in,
               const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const bf16* __restrict__ gamma,
               bf16* __restrict__ dx, bf16* __restrict__ dx_drop, float* __restrict__ dgamma,
               float* __restrict__ dbeta, float* __restrict__ dbias, int rows, int H, uint32_t out_keep_thr,
               float out_inv_keep, uint32_t out_seed, uint32_t in_keep_thr, float in_inv_keep, uint32_t in_seed) {
+  constexpr int kWarps = 4;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int nwarp_total = gridDim.x * 8;
+  const int nwarp_total = gridDim.x * kWarps;
   const int nchunk = H >> 3;
-  float gam[kMaxChunks][8], ag[kMaxChunks][8], ab[kMaxChunks][8], abias[kMaxChunks][8];
+  float gam[NC][8], ag[NC][8], ab[NC][8], abias[DBIAS ? NC : 1][8];
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
+  for (int c = 0; c < NC; ++c) {
     const int ch = lane + 32 * c;
     if (ch < nchunk) unpack8(*reinterpret_cast<const bf16x8*>(gamma + ch * 8), gam[c]);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) ag[c][j] = ab[c][j] = abias[c][j] = 0.f;
+    for (int j = 0; j < 8; ++j) {
+      ag[c][j] = ab[c][j] = 0.f;
+      if (DBIAS) abias[c][j] = 0.f;
+    }
   }
-  for (int r = blockIdx.x * 8 + warp; r < rows; r += nwarp_total) {
+  for (int r = blockIdx.x * kWarps + warp; r < rows; r += nwarp_total) {
     const float mean = mean_in[r], rstd = rstd_in[r];
     const bf16* dyr = dy + dymap.off(r, H);
-    float g[kMaxChunks][8], xh[kMaxChunks][8];
+    float g[NC][8], xh[NC][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int ch = lane + 32 * c;
       if (ch < nchunk) {
         float xv[8];
@@ -198,7 +203,7 @@ ln_bwd_kernel(const bf16* __restrict__ dy, RowMap dymap, const bf16* __restrict_
     s1 = warp_sum(s1) / H;
     s2 = warp_sum(s2) / H;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int ch = lane + 32 * c;
       if (ch < nchunk) {
         float o[8];
@@ -211,7 +216,7 @@ ln_bwd_kernel(const bf16* __restrict__ dy, RowMap dymap, const bf16* __restrict_
             o[j] = dropout_keep(in_seed, (uint32_t)r * (uint32_t)H + ch * 8 + j, in_keep_thr) ? o[j] * in_inv_keep : 0.f;
           *reinterpret_cast<bf16x8*>(dx_drop + (size_t)r * H + ch * 8) = pack8(o);
         }
-        if (dbias) {
+        if (DBIAS) {
           // bias grad sees what the dense output saw: bf16-rounded, dropped dx
           bf16x8 pk = pack8(o);
           float q[8];
@@ -222,24 +227,24 @@ ln_bwd_kernel(const bf16* __restrict__ dy, RowMap dymap, const bf16* __restrict_
       }
     }
   }
-  // block reduce over the 8 warps, then one atomic per column per block
-  __shared__ float red[8][33 * 8];
-  for (int pass = 0; pass < 3; ++pass) {
+  // block reduce over the warps, then one atomic per column per block
+  __shared__ float red[kWarps][32 * 8 + 1];
+  for (int pass = 0; pass < (DBIAS ? 3 : 2); ++pass) {
     float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dbias);
-    if (!dst) continue;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int ch = lane + 32 * c;
       __syncthreads();
 #pragma unroll
-      for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = pass == 0 ? ag[c][j] : (pass == 1 ? ab[c][j] : abias[c][j]);
+      for (int j = 0; j < 8; ++j)
+        red[warp][lane * 8 + j] = pass == 0 ? ag[c][j] : (pass == 1 ? ab[c][j] : abias[DBIAS ? c : 0][j]);
       __syncthreads();
       if (warp == 0 && ch < nchunk) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float s = 0.f;
 #pragma unroll
-          for (int w = 0; w < 8; ++w) s += red[w][lane * 8 + j];
+          for (int w = 0; w < kWarps; ++w) s += red[w][lane * 8 + j];
           atomicAdd(dst + ch * 8 + j, s);
         }
       }
@@ -469,6 +474,7 @@ extern "C" int mvptr_embed_ln_fwd(const int64_t* ids, const int64_t* type_ids, c
                                   const void* beta, void* y, int y_rows_per_batch, long long y_batch_stride, void* pre,
                                   float* mean, float* rstd, int B, int L, int H, float eps, int vocab, int max_pos,
                                   int n_types, float p_drop, uint32_t seed, void* stream) {
+  MVPTR_PROF("embed_ln_fwd", 0, stream);
   CHECK_H(H);
   if (L > max_pos && !pos_ids) MVPTR_FAIL(MVPTR_ERR_ARG, "sequence length %d exceeds position table %d", L, max_pos);
   const int rows = B * L;
@@ -485,6 +491,7 @@ extern "C" int mvptr_embed_ln_fwd(const int64_t* ids, const int64_t* type_ids, c
 extern "C" int mvptr_ln_fwd(const void* x, const void* gamma, const void* beta, void* y, int y_rows_per_batch,
                             long long y_batch_stride, float* mean, float* rstd, int rows, int H, float eps,
                             float p_drop, uint32_t seed, void* stream) {
+  MVPTR_PROF("ln_fwd", 4.0*rows*H, stream);
   CHECK_H(H);
   if (rows == 0) return 0;
   RowMap ym{y_rows_per_batch > 0 ? y_rows_per_batch : rows, y_rows_per_batch > 0 ? y_batch_stride : 0};
@@ -499,20 +506,41 @@ extern "C" int mvptr_ln_bwd(const void* dy, int dy_rows_per_batch, long long dy_
                             const float* mean, const float* rstd, const void* gamma, void* dx, void* dx_drop,
                             float* dgamma, float* dbeta, float* dbias, int rows, int H, float out_p_drop,
                             uint32_t out_seed, float in_p_drop, uint32_t in_seed, void* stream) {
+  MVPTR_PROF("ln_bwd", 6.0*rows*H, stream);
   CHECK_H(H);
   if (rows == 0) return 0;
   if (dx_drop && in_p_drop <= 0.f) MVPTR_FAIL(MVPTR_ERR_ARG, "ln_bwd: dx_drop given without in_p_drop");
   RowMap dm{dy_rows_per_batch > 0 ? dy_rows_per_batch : rows, dy_rows_per_batch > 0 ? dy_batch_stride : 0};
-  int grid = (rows + 7) / 8;
-  if (grid > kNumSMs * 4) grid = kNumSMs * 4;
-  ln_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)dy, dm, (const bf16*)x, mean, rstd, (const bf16*)gamma, (bf16*)dx, (bf16*)dx_drop, dgamma, dbeta,
-      dbias, rows, H, thr(out_p_drop), invk(out_p_drop), out_seed, thr(in_p_drop), invk(in_p_drop), in_seed);
+  if (!dgamma || !dbeta) MVPTR_FAIL(MVPTR_ERR_ARG, "ln_bwd: dgamma/dbeta accumulators are required");
+  int grid = (rows + 3) / 4;
+  if (grid > kNumSMs * 3) grid = kNumSMs * 3;
+  const int nc = (H + 255) / 256;
+#define LN_BWD_LAUNCH(NC, DB)                                                                                     \
+  ln_bwd_kernel<NC, DB><<<grid, 128, 0, (cudaStream_t)stream>>>(                                                  \
+      (const bf16*)dy, dm, (const bf16*)x, mean, rstd, (const bf16*)gamma, (bf16*)dx, (bf16*)dx_drop, dgamma,     \
+      dbeta, dbias, rows, H, thr(out_p_drop), invk(out_p_drop), out_seed, thr(in_p_drop), invk(in_p_drop), in_seed)
+  if (dbias) {
+    switch (nc) {
+      case 1: LN_BWD_LAUNCH(1, true); break;
+      case 2: LN_BWD_LAUNCH(2, true); break;
+      case 3: LN_BWD_LAUNCH(3, true); break;
+      default: LN_BWD_LAUNCH(4, true); break;
+    }
+  } else {
+    switch (nc) {
+      case 1: LN_BWD_LAUNCH(1, false); break;
+      case 2: LN_BWD_LAUNCH(2, false); break;
+      case 3: LN_BWD_LAUNCH(3, false); break;
+      default: LN_BWD_LAUNCH(4, false); break;
+    }
+  }
+#undef LN_BWD_LAUNCH
   MVPTR_CHECK_LAUNCH("ln_bwd");
   return 0;
 }
 
 extern "C" int mvptr_colsum(const void* x, int ldx, float* out, int M, int N, void* stream) {
+  MVPTR_PROF("colsum", 2.0*M*N, stream);
   if (M <= 0 || N <= 0) return 0;
   if ((N & 7) || (ldx & 7)) MVPTR_FAIL(MVPTR_ERR_ARG, "colsum: N and ldx must be multiples of 8");
   const int rpb = 512;
@@ -525,6 +553,7 @@ extern "C" int mvptr_colsum(const void* x, int ldx, float* out, int M, int N, vo
 extern "C" int mvptr_embed_bwd(const void* dpre, const int64_t* ids, const int64_t* type_ids, float* dword,
                                float* dpos, float* dtype, int B, int L, int H, int vocab, int n_types,
                                int padding_idx, void* stream) {
+  MVPTR_PROF("embed_bwd", 0, stream);
   CHECK_H(H);
   const int rows = B * L;
   if (rows == 0) return 0;
@@ -539,6 +568,7 @@ extern "C" int mvptr_embed_bwd(const void* dpre, const int64_t* ids, const int64
 
 extern "C" int mvptr_pad_cast(const void* src, int src_is_f32, long long ld_src, void* dst, int ld_dst, int rows, int K,
                               void* stream) {
+  MVPTR_PROF("pad_cast", 0, stream);
   if (rows <= 0) return 0;
   dim3 grid((ld_dst + 255) / 256, rows);
   if (src_is_f32)
@@ -562,6 +592,7 @@ extern "C" int mvptr_mask_prepare(const int64_t* mask_a, int La, const int64_t* 
 
 extern "C" int mvptr_concat_rows(const void* a, int La, const void* b, int Lb, int b_col0, const int64_t* row_a,
                                  const int64_t* row_b, void* out, int rows, int H, void* stream) {
+  MVPTR_PROF("concat_rows", 0, stream);
   if (rows <= 0) return 0;
   if (H & 7) MVPTR_FAIL(MVPTR_ERR_ARG, "concat_rows: H must be a multiple of 8");
   const int n = rows * (La + (Lb - b_col0));
@@ -573,6 +604,7 @@ extern "C" int mvptr_concat_rows(const void* a, int La, const void* b, int Lb, i
 
 extern "C" int mvptr_concat_rows_bwd(const void* dout, int La, int Lb, int b_col0, const int64_t* row_a,
                                      const int64_t* row_b, float* da, float* db, int rows, int H, void* stream) {
+  MVPTR_PROF("concat_rows_bwd", 0, stream);
   if (rows <= 0) return 0;
   const int n = rows * (La + (Lb - b_col0));
   concat_rows_bwd_kernel<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>((const bf16*)dout, La, Lb, b_col0, row_a,
@@ -582,6 +614,7 @@ extern "C" int mvptr_concat_rows_bwd(const void* dout, int La, int Lb, int b_col
 }
 
 extern "C" int mvptr_gather_rows(const void* src, const int64_t* idx, void* out, int n, int H, void* stream) {
+  MVPTR_PROF("gather_rows", 0, stream);
   if (n <= 0) return 0;
   gather_rows_kernel<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>((const bf16*)src, idx, (bf16*)out, n, H);
   MVPTR_CHECK_LAUNCH("gather_rows");
@@ -596,6 +629,7 @@ extern "C" int mvptr_scatter_rows_add(const void* src, const int64_t* idx, float
 }
 
 extern "C" int mvptr_cast_f32_bf16(const float* src, void* dst, size_t n, void* stream) {
+  MVPTR_PROF("cast_f32_bf16", 6.0*n, stream);
   if (n == 0) return 0;
   size_t blocks = (n / 8 + 255) / 256;
   if (blocks > (size_t)kNumSMs * 8) blocks = (size_t)kNumSMs * 8;
@@ -606,6 +640,7 @@ extern "C" int mvptr_cast_f32_bf16(const float* src, void* dst, size_t n, void* 
 }
 
 extern "C" int mvptr_add_cast(const float* a, const void* b, void* d, size_t n, void* stream) {
+  MVPTR_PROF("add_cast", 6.0*n, stream);
   if (n == 0) return 0;
   if (n & 7) MVPTR_FAIL(MVPTR_ERR_ARG, "add_cast: n must be a multiple of 8");
   size_t blocks = (n / 8 + 255) / 256;

@@ -38,6 +38,7 @@ class Runtime:
         self.img_w16 = None
         self._img_w_version = -1
         self.launches = 0
+        self.layer_protos = {}
 
     # ---- bookkeeping -------------------------------------------------------------------
     def next_seed(self):
@@ -99,12 +100,45 @@ def dgrad(rt, dY, ld_dy, W, ld_w, tokens, n_out, k_in, dX, **epi):
 # CaptionBertLayer (:191-199) = attention (:63-103) + BertSelfOutput / BertIntermediate /
 # BertOutput (modeling_bert.py:348-352, 394-397, 407-411)
 # ======================================================================================
+_W_FIELDS = (("w_qkv", "attention.self.query.weight"), ("b_qkv", "attention.self.query.bias"),
+             ("w_o", "attention.output.dense.weight"), ("b_o", "attention.output.dense.bias"),
+             ("ln1_g", "attention.output.LayerNorm.weight"), ("ln1_b", "attention.output.LayerNorm.bias"),
+             ("w_i", "intermediate.dense.weight"), ("b_i", "intermediate.dense.bias"),
+             ("w_o2", "output.dense.weight"), ("b_o2", "output.dense.bias"),
+             ("ln2_g", "output.LayerNorm.weight"), ("ln2_b", "output.LayerNorm.bias"))
+
+
+def _layer_proto(rt, pf, with_grads):
+    """LayerArgs with the (stable) weight / gradient arena pointers of one layer filled in."""
+    key = (pf, with_grads, id(rt.arena.shadow), id(rt.arena.grad))
+    proto = rt.layer_protos.get(key)
+    if proto is None:
+        a = rt.arena
+        offs = a.offsets
+        # fused QKV relies on query/key/value tensors being adjacent in the arena
+        for kind in ("weight", "bias"):
+            q, k, v = (offs[pf + f"attention.self.{n}.{kind}"] for n in ("query", "key", "value"))
+            assert k[0] == q[0] + q[1] and v[0] == k[0] + k[1], "q/k/v must be adjacent in the parameter arena"
+        proto = _lib.LayerArgs()
+        proto.H, proto.I, proto.nh, proto.eps = rt.H, rt.I, rt.nh, rt.eps
+        sh = a.shadow.data_ptr()
+        for f, n in _W_FIELDS:
+            setattr(proto, f, sh + 2 * offs[pf + n][0])
+        if with_grads:
+            g = a.ensure_grad().data_ptr()
+            for f, n in _W_FIELDS:
+                setattr(proto, "g_" + f, g + 4 * offs[pf + n][0])
+        rt.layer_protos[key] = proto
+    return _lib.LayerArgs.from_buffer_copy(proto)
+
+
 class EncoderFn(Function):
+    """One ctypes call per layer (csrc/layer.cu launches the layer's kernels from C++)."""
+
     @staticmethod
     def forward(ctx, h, maskadd, rt, prefix, layer_lo, layer_hi, save, anchor):
         B, L, H = h.shape
         M, I, nh = B * L, rt.I, rt.nh
-        a = rt.arena
         dev = h.device
         p_h = rt.cfg.hidden_dropout_prob if rt.training else 0.0
         p_a = rt.cfg.attention_probs_dropout_prob if rt.training else 0.0
@@ -112,85 +146,72 @@ class EncoderFn(Function):
         if not x.is_contiguous():
             x = x.contiguous()
         saved = []
+        n_bf16 = M * (8 * H + 2 * I)  # qkv 3H | att | pre1 | a1 | pre2 | out | pre_g I | inter I
+        n_f32 = B * nh * L + 4 * M
+        ws = None
         for li in range(layer_lo, layer_hi):
             pf = f"{prefix}.layer.{li}."
-            s_attn, s1, s2 = rt.next_seed(), rt.next_seed(), rt.next_seed()
-            wqkv = a.w_span(pf + "attention.self.query.weight", 3 * H, H)
-            bqkv = a.w_span(pf + "attention.self.query.bias", 3 * H)
-            qkv = torch.empty(M, 3 * H, device=dev, dtype=BF16)
-            rt.gemm(x, wqkv, qkv, M, 3 * H, H, lda=H, ldb=H, ldd=3 * H, bias=bqkv)
-            att = torch.empty(M, H, device=dev, dtype=BF16)
-            lse = torch.empty(B, nh, L, device=dev, dtype=F32) if save else None
-            rt.call("mvptr_attn_fwd", qkv, 3 * H, maskadd, att, H, lse, B, L, nh, H, p_a, s_attn)
-            pre1 = torch.empty(M, H, device=dev, dtype=BF16)
-            rt.gemm(att, a.w(pf + "attention.output.dense.weight"), pre1, M, H, H, lda=H, ldb=H, ldd=H,
-                    bias=a.w(pf + "attention.output.dense.bias"), residual=x, ld_aux=H, p_drop=p_h, seed=s1)
-            a1 = torch.empty(M, H, device=dev, dtype=BF16)
-            st1 = torch.empty(2, M, device=dev, dtype=F32) if save else None
-            rt.call("mvptr_ln_fwd", pre1, a.w(pf + "attention.output.LayerNorm.weight"),
-                    a.w(pf + "attention.output.LayerNorm.bias"), a1, 0, 0, st1[0] if save else None,
-                    st1[1] if save else None, M, H, rt.eps, 0.0, 0)
-            inter = torch.empty(M, I, device=dev, dtype=BF16)
-            pre_g = torch.empty(M, I, device=dev, dtype=BF16) if save else None
-            rt.gemm(a1, a.w(pf + "intermediate.dense.weight"), inter, M, I, H, lda=H, ldb=H, ldd=I,
-                    bias=a.w(pf + "intermediate.dense.bias"), act="gelu", pre_act=pre_g, ld_aux=I)
-            pre2 = torch.empty(M, H, device=dev, dtype=BF16)
-            rt.gemm(inter, a.w(pf + "output.dense.weight"), pre2, M, H, I, lda=I, ldb=I, ldd=H,
-                    bias=a.w(pf + "output.dense.bias"), residual=a1, ld_aux=H, p_drop=p_h, seed=s2)
+            la = _layer_proto(rt, pf, False)
+            if save or ws is None:
+                blk = torch.empty(n_bf16, device=dev, dtype=BF16)
+                f32 = torch.empty(n_f32, device=dev, dtype=F32)
+                ws = (blk, f32)
+            else:
+                blk, f32 = ws
             out = torch.empty(M, H, device=dev, dtype=BF16)
-            st2 = torch.empty(2, M, device=dev, dtype=F32) if save else None
-            rt.call("mvptr_ln_fwd", pre2, a.w(pf + "output.LayerNorm.weight"), a.w(pf + "output.LayerNorm.bias"), out,
-                    0, 0, st2[0] if save else None, st2[1] if save else None, M, H, rt.eps, 0.0, 0)
+            b0, f0 = blk.data_ptr(), f32.data_ptr()
+            la.B, la.L, la.save = B, L, int(save)
+            la.p_hidden, la.p_attn = p_h, p_a
+            la.seed_attn, la.seed1, la.seed2 = rt.next_seed(), rt.next_seed(), rt.next_seed()
+            la.maskadd = maskadd.data_ptr()
+            la.x = x.data_ptr()
+            la.qkv = b0
+            la.att = b0 + 2 * M * 3 * H
+            la.pre1 = b0 + 2 * M * 4 * H
+            la.a1 = b0 + 2 * M * 5 * H
+            la.pre2 = b0 + 2 * M * 6 * H
+            la.pre_g = b0 + 2 * M * 7 * H
+            la.inter = b0 + 2 * M * (7 * H + I)
+            la.out = out.data_ptr()
+            la.lse = f0
+            la.st1 = f0 + 4 * B * nh * L
+            la.st2 = f0 + 4 * (B * nh * L + 2 * M)
+            _lib.layer_call("mvptr_layer_fwd", la, 7)
+            rt.launches += 7
             if save:
-                saved.append((pf, x, qkv, att, lse, pre1, st1, a1, pre_g, inter, pre2, st2, s_attn, s1, s2))
+                saved.append((pf, la, x, blk, f32, out))
             x = out
-        ctx.rt, ctx.saved, ctx.dims, ctx.maskadd, ctx.p = rt, saved, (B, L, H), maskadd, (p_h, p_a)
+        ctx.rt, ctx.saved, ctx.dims, ctx.maskadd = rt, saved, (B, L, H), maskadd
         return x.view(B, L, H)
 
     @staticmethod
     def backward(ctx, dout):
-        rt, (B, L, H), maskadd, (p_h, p_a) = ctx.rt, ctx.dims, ctx.maskadd, ctx.p
-        M, I, nh = B * L, rt.I, rt.nh
-        a = rt.arena
+        rt, (B, L, H), maskadd = ctx.rt, ctx.dims, ctx.maskadd
+        M, I = B * L, rt.I
         dev = dout.device
         dy = dout.reshape(M, H)
         if not dy.is_contiguous():
             dy = dy.contiguous()
-        for (pf, x, qkv, att, lse, pre1, st1, a1, pre_g, inter, pre2, st2, s_attn, s1, s2) in reversed(ctx.saved):
-            # ---- BertOutput: LN(dropout(dense(inter)) + a1)
-            dpre2 = torch.empty(M, H, device=dev, dtype=BF16)
-            dpre2d = torch.empty(M, H, device=dev, dtype=BF16) if p_h > 0 else None
-            rt.call("mvptr_ln_bwd", dy, 0, 0, pre2, st2[0], st2[1], a.w(pf + "output.LayerNorm.weight"), dpre2, dpre2d,
-                    a.g(pf + "output.LayerNorm.weight"), a.g(pf + "output.LayerNorm.bias"),
-                    a.g(pf + "output.dense.bias"), M, H, 0.0, 0, p_h, s2)
-            dY2 = dpre2d if p_h > 0 else dpre2
-            wgrad(rt, dY2, H, inter, I, H, I, M, a.g(pf + "output.dense.weight"))
-            dpre_g = torch.empty(M, I, device=dev, dtype=BF16)
-            dgrad(rt, dY2, H, a.w(pf + "output.dense.weight"), I, M, H, I, dpre_g, gelu_grad_of=pre_g, ld_aux=I)
-            # ---- BertIntermediate
-            rt.call("mvptr_colsum", dpre_g, I, a.g(pf + "intermediate.dense.bias"), M, I)
-            wgrad(rt, dpre_g, I, a1, H, I, H, M, a.g(pf + "intermediate.dense.weight"))
-            da1 = torch.empty(M, H, device=dev, dtype=BF16)
-            dgrad(rt, dpre_g, I, a.w(pf + "intermediate.dense.weight"), H, M, I, H, da1, residual=dpre2, ld_aux=H)
-            # ---- BertSelfOutput: LN(dropout(dense(att)) + x)
-            dpre1 = torch.empty(M, H, device=dev, dtype=BF16)
-            dpre1d = torch.empty(M, H, device=dev, dtype=BF16) if p_h > 0 else None
-            rt.call("mvptr_ln_bwd", da1, 0, 0, pre1, st1[0], st1[1], a.w(pf + "attention.output.LayerNorm.weight"),
-                    dpre1, dpre1d, a.g(pf + "attention.output.LayerNorm.weight"),
-                    a.g(pf + "attention.output.LayerNorm.bias"), a.g(pf + "attention.output.dense.bias"), M, H, 0.0, 0,
-                    p_h, s1)
-            dY1 = dpre1d if p_h > 0 else dpre1
-            wgrad(rt, dY1, H, att, H, H, H, M, a.g(pf + "attention.output.dense.weight"))
-            datt = torch.empty(M, H, device=dev, dtype=BF16)
-            dgrad(rt, dY1, H, a.w(pf + "attention.output.dense.weight"), H, M, H, H, datt)
-            # ---- attention
-            dqkv = torch.empty(M, 3 * H, device=dev, dtype=BF16)
-            rt.call("mvptr_attn_bwd", qkv, 3 * H, maskadd, att, datt, H, lse, dqkv, B, L, nh, H, p_a, s_attn)
-            rt.call("mvptr_colsum", dqkv, 3 * H, a.g_span(pf + "attention.self.query.bias", 3 * H), M, 3 * H)
-            wgrad(rt, dqkv, 3 * H, x, H, 3 * H, H, M, a.g_span(pf + "attention.self.query.weight", 3 * H, H))
+        # scratch shared by all layers: dpre2 | dpre2d | da1 | dpre1 | dpre1d | datt | dqkv 3H | dpre_g I
+        scratch = torch.empty(M * (9 * H + I), device=dev, dtype=BF16)
+        s0 = scratch.data_ptr()
+        for (pf, la_f, x, blk, f32, out) in reversed(ctx.saved):
+            la = _layer_proto(rt, pf, True)
+            for f in ("B", "L", "save", "p_hidden", "p_attn", "seed_attn", "seed1", "seed2", "maskadd", "x", "qkv",
+                      "att", "pre1", "a1", "pre2", "pre_g", "inter", "out", "lse", "st1", "st2"):
+                setattr(la, f, getattr(la_f, f))
             dx = torch.empty(M, H, device=dev, dtype=BF16)
-            dgrad(rt, dqkv, 3 * H, a.w_span(pf + "attention.self.query.weight", 3 * H, H), H, M, 3 * H, H, dx,
-                  residual=dpre1, ld_aux=H)
+            la.dout, la.dx = dy.data_ptr(), dx.data_ptr()
+            la.dpre2 = s0
+            la.dpre2d = s0 + 2 * M * H
+            la.da1 = s0 + 2 * M * 2 * H
+            la.dpre1 = s0 + 2 * M * 3 * H
+            la.dpre1d = s0 + 2 * M * 4 * H
+            la.datt = s0 + 2 * M * 5 * H
+            la.dqkv = s0 + 2 * M * 6 * H
+            la.dpre_g = s0 + 2 * M * 9 * H
+            _lib.layer_call("mvptr_layer_bwd", la, 13)
+            rt.launches += 13
             dy = dx
         ctx.saved = None
         return dy.view(B, L, H), None, None, None, None, None, None, None

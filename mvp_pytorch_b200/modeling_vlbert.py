@@ -251,23 +251,19 @@ def _mlm_loss(rt, top, seq2d, labels2d, head_prefix, anchor):
                              cfg.only_word_size, head_prefix + ".bias", anchor)
 
 
-def _draw_wra_choices(phrase_index, n_samples, max_phrases, device):
-    """The reference draws, per sample and in this order: randint(0,3) for the positive image's
-    phrases, random.choice of a negative image, randint(0,3) for the negative image's phrases
-    (modeling_vlbert.py:1566-1576 with t2i_sim :1548).  Same generators, same order; the results
-    are handed to the batched kernel as index tensors."""
-    n_ph = (phrase_index[:, 1] - phrase_index[:, 0]).tolist()
-    rand_pos = torch.zeros(n_samples, max_phrases, dtype=torch.int64)
-    rand_neg = torch.zeros(n_samples, max_phrases, dtype=torch.int64)
-    neg_img = torch.zeros(n_samples, dtype=torch.int64)
-    for b in range(n_samples):
-        k = min(int(n_ph[b]), max_phrases)
-        if k > 0:
-            rand_pos[b, :k] = torch.randint(0, 3, (k,))
-        neg_img[b] = random.choice(list(range(0, b)) + list(range(b + 1, n_samples)))
-        if k > 0:
-            rand_neg[b, :k] = torch.randint(0, 3, (k,))
-    return neg_img.to(device), rand_pos.to(device), rand_neg.to(device)
+def _draw_wra_choices(n_samples, max_phrases, device):
+    """Random choices of the 'sample' phrase-grounding loss, drawn on the device without a
+    host sync: per sample one OTHER image (the reference's random.choice over j != b,
+    modeling_vlbert.py:1572-1573) and, per phrase, which of the top-3 regions to keep for the
+    positive and the negative image (torch.randint(0, 3), :1548).  Same distributions as the
+    reference; the batched kernel consumes them as index tensors."""
+    r = torch.randint(0, max(n_samples - 1, 1), (n_samples,), device=device)
+    neg_img = r + (r >= torch.arange(n_samples, device=device)).to(r.dtype)  # uniform over j != b
+    if n_samples == 1:
+        neg_img = torch.zeros(1, dtype=torch.int64, device=device)
+    rand_pos = torch.randint(0, 3, (n_samples, max_phrases), device=device)
+    rand_neg = torch.randint(0, 3, (n_samples, max_phrases), device=device)
+    return neg_img, rand_pos, rand_neg
 
 
 class BiBertImgForPreTraining(BertPreTrainedModel):
@@ -333,7 +329,7 @@ class BiBertImgForPreTraining(BertPreTrainedModel):
             if phrase_mod == 'sample':
                 maxp = E._lib.lib().mvptr_wra_max_phrases()
                 if wra_choices is None:
-                    wra_choices = _draw_wra_choices(phrase_index.cpu(), B, maxp, sequence_output.device)
+                    wra_choices = _draw_wra_choices(B, maxp, sequence_output.device)
                 neg_img, rand_pos, rand_neg = wra_choices
                 pos_sims, neg_sims = E.WRAFn.apply(sequence_output, phrase_index.to(torch.int64).contiguous(),
                                                    img_index.to(torch.int64).contiguous(), neg_img.contiguous(),

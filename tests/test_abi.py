@@ -49,7 +49,8 @@ def test_ctypes_signatures_match_header(built):
             elif a.startswith("size_t"): kinds += "z"
             else: kinds += "i"
         assert kinds == spec, f"{name}: header {kinds} vs binding {spec}"
-    declared = set(fns) - {"mvptr_abi_version", "mvptr_last_error", "mvptr_wra_max_phrases"}
+    declared = set(fns) - {"mvptr_abi_version", "mvptr_last_error", "mvptr_wra_max_phrases", "mvptr_profile_enable",
+                               "mvptr_profile_collect"}
     assert declared == set(built.SIGNATURES), declared ^ set(built.SIGNATURES)
 
 
@@ -65,6 +66,19 @@ def test_gemm_args_struct_matches_header(built):
         for part in decl.split(","):
             names.append(part.replace("*", " ").split()[-1])
     assert names == [f[0] for f in built.GemmArgs._fields_]
+
+
+def test_layer_args_struct_matches_header(built):
+    hdr = open(os.path.join(ROOT, "include", "mvptr_b200.h")).read()
+    body = re.search(r"typedef struct \{([^}]*?)\} mvptr_layer_args;", hdr, flags=re.S).group(1)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        for part in decl.split(","):
+            names.append(part.replace("*", " ").split()[-1])
+    assert names == [f[0] for f in built.LayerArgs._fields_]
 
 
 def test_argument_errors_do_not_need_a_gpu(built):

@@ -78,7 +78,7 @@ def test_gemm_epilogues(lib):
     raw = A.float() @ B.float().t()
     dropped = (o3 == 0) & (raw.abs() > 1e-3)
     assert abs(dropped.float().mean().item() - 0.1) < 0.01
-    assert_close(o3[~dropped], raw[~dropped] / 0.9, 1e-3, 1e-3, "kept")
+    assert_close(o3[~dropped], raw[~dropped] / 0.9, 3e-3, 3e-3, "kept")
 
 
 # ------------------------------------------------------------------------------------
@@ -129,7 +129,7 @@ def test_embed_ln_fwd_bwd(lib):
     dW = torch.zeros(V, H, device="cuda"); dP = torch.zeros(64, H, device="cuda"); dT = torch.zeros(2, H, device="cuda")
     lib.call("mvptr_embed_bwd", dpre, ids, seg, dW, dP, dT, B, L, H, V, 2, 0)
     ref_w = wf.grad.clone(); ref_w[0] = 0
-    assert_close(dW, ref_w, 2e-2, 2e-2, "dword")
+    assert_close(dW, ref_w, 2e-2, 0.5, "dword")  # grads ~1e2; dpre is bf16
     assert_close(dP, pf.grad, 2e-2, 5e-2, "dpos")
     assert_close(dT, tf.grad, 2e-2, 0.2, "dtype")
 

