@@ -110,6 +110,14 @@ int mvptr_embed_bwd(const void* dpre, const int64_t* ids, const int64_t* type_id
 int mvptr_ln_fwd(const void* x, const void* gamma, const void* beta, void* y, int y_rows_per_batch,
                  long long y_batch_stride, float* mean, float* rstd, int rows, int H, float eps, float p_drop,
                  uint32_t seed, void* stream);
+/* out = LN(dropout(x) + residual): the tail of BertSelfOutput / BertOutput (modeling_bert.py:350-351,
+ * 409-410) as one coalesced pass; pre_out (nullable) saves the pre-LN sum for backward. */
+int mvptr_add_ln_fwd(const void* x, const void* residual, float in_p_drop, uint32_t in_seed, void* pre_out,
+                     const void* gamma, const void* beta, void* y, float* mean, float* rstd, int rows, int H,
+                     float eps, void* stream);
+/* erf-GELU of BertIntermediate (modeling_bert.py:396) and its backward fused with the dense bias gradient */
+int mvptr_gelu_fwd(const void* x, void* y, size_t n, void* stream);
+int mvptr_gelu_bwd_colsum(const void* dy, const void* pre, void* dx, float* dbias, int M, int N, void* stream);
 /* LayerNorm backward; also emits dx with the dense-output dropout mask re-applied (dx_drop)
  * and accumulates dgamma / dbeta / dbias (fp32, atomics). */
 int mvptr_ln_bwd(const void* dy, int dy_rows_per_batch, long long dy_batch_stride, const void* x, const float* mean,
@@ -209,7 +217,7 @@ int mvptr_bce_bwd(const float* logits, int ld, const float* labels, int n, int C
  * (modeling_bert.py:348-352) -> BertIntermediate (:394-397) -> BertOutput (:407-411), and its
  * backward.  The caller owns every buffer; [M = B*L rows]:
  *   x,att,pre1,a1,pre2,out [M,H] bf16; qkv [M,3H]; pre_g,inter [M,I]; lse [B,nh,L] f32;
- *   st1,st2 [2,M] f32 (mean | rstd).  save=0 (inference) skips lse/st/pre_g.
+ *   st1,st2 [2,M] f32 (mean | rstd).  save=0 (inference) skips lse/st/pre1/pre2.
  * Backward reads the saved activations + dout and writes dx; d* are scratch of the same
  * shapes as their forward counterparts; g_* are fp32 gradient accumulators (+=). */
 typedef struct {
@@ -226,6 +234,7 @@ typedef struct {
   void *a1, *pre_g, *inter, *pre2;
   float* st2;
   void* out;
+  void* tmp; /* [M,H] bf16 forward scratch (dense outputs before dropout+residual+LN) */
   const void* dout;
   void *dx, *dpre2, *dpre2d, *dpre_g, *da1, *dpre1, *dpre1d, *datt, *dqkv;
   float *g_w_qkv, *g_b_qkv, *g_w_o, *g_b_o, *g_ln1_g, *g_ln1_b, *g_w_i, *g_b_i, *g_w_o2, *g_b_o2, *g_ln2_g, *g_ln2_b;

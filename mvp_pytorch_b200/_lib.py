@@ -42,7 +42,7 @@ class LayerArgs(ctypes.Structure):
         + [(n, ctypes.c_void_p) for n in (
             "maskadd",
             "w_qkv", "b_qkv", "w_o", "b_o", "ln1_g", "ln1_b", "w_i", "b_i", "w_o2", "b_o2", "ln2_g", "ln2_b",
-            "x", "qkv", "att", "lse", "pre1", "st1", "a1", "pre_g", "inter", "pre2", "st2", "out",
+            "x", "qkv", "att", "lse", "pre1", "st1", "a1", "pre_g", "inter", "pre2", "st2", "out", "tmp",
             "dout", "dx", "dpre2", "dpre2d", "dpre_g", "da1", "dpre1", "dpre1d", "datt", "dqkv",
             "g_w_qkv", "g_b_qkv", "g_w_o", "g_b_o", "g_ln1_g", "g_ln1_b", "g_w_i", "g_b_i", "g_w_o2", "g_b_o2",
             "g_ln2_g", "g_ln2_b")])
@@ -58,6 +58,9 @@ SIGNATURES = {
     "mvptr_embed_ln_fwd": "ppppppppp" + "il" + "ppp" + "iiifiii" + "fup",
     "mvptr_embed_bwd": "pppppp" + "iiiiii" + "p",
     "mvptr_ln_fwd": "pppp" + "il" + "pp" + "iif" + "fup",
+    "mvptr_add_ln_fwd": "ppfu" + "pppp" + "pp" + "iifp",
+    "mvptr_gelu_fwd": "ppzp",
+    "mvptr_gelu_bwd_colsum": "ppppiip",
     "mvptr_ln_bwd": "p" + "il" + "pppp" + "pp" + "ppp" + "ii" + "fufu" + "p",
     "mvptr_colsum": "pipiip",
     "mvptr_pad_cast": "pilpiiip",

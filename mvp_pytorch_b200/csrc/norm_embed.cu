@@ -106,9 +106,11 @@ embed_ln_fwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__
 // y = dropout(LN(x))                    modeling_bert.py:242-246 (+ modeling_vlbert.py:499-503)
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-ln_fwd_kernel(const bf16* __restrict__ x_in, const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
-              bf16* __restrict__ y, RowMap ymap, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
-              int H, float eps, uint32_t keep_thr, float inv_keep, uint32_t seed) {
+ln_fwd_kernel(const bf16* __restrict__ x_in, const bf16* __restrict__ residual, bf16* __restrict__ pre_out,
+              const bf16* __restrict__ gamma, const bf16* __restrict__ beta, bf16* __restrict__ y, RowMap ymap,
+              float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int H, float eps,
+              uint32_t in_keep_thr, float in_inv_keep, uint32_t in_seed, uint32_t keep_thr, float inv_keep,
+              uint32_t seed) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -117,7 +119,26 @@ ln_fwd_kernel(const bf16* __restrict__ x_in, const bf16* __restrict__ gamma, con
 #pragma unroll
   for (int c = 0; c < kMaxChunks; ++c) {
     const int ch = lane + 32 * c;
-    if (ch < nchunk) unpack8(*reinterpret_cast<const bf16x8*>(x_in + (size_t)r * H + ch * 8), x[c]);
+    if (ch < nchunk) {
+      unpack8(*reinterpret_cast<const bf16x8*>(x_in + (size_t)r * H + ch * 8), x[c]);
+      if (in_keep_thr != 0xffffffffu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          x[c][j] = dropout_keep(in_seed, (uint32_t)r * (uint32_t)H + ch * 8 + j, in_keep_thr) ? x[c][j] * in_inv_keep : 0.f;
+      }
+      if (residual) {
+        float rr[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(residual + (size_t)r * H + ch * 8), rr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[c][j] += rr[j];
+      }
+      if (pre_out) {
+        // the saved pre-LN activation is what backward normalises, so LN runs on its bf16 rounding
+        const bf16x8 pk = pack8(x[c]);
+        *reinterpret_cast<bf16x8*>(pre_out + (size_t)r * H + ch * 8) = pk;
+        unpack8(pk, x[c]);
+      }
+    }
   }
   float mean, rstd;
   ln_row(x, nchunk, lane, H, eps, mean, rstd);
@@ -140,6 +161,60 @@ ln_fwd_kernel(const bf16* __restrict__ x_in, const bf16* __restrict__ gamma, con
           o[j] = dropout_keep(seed, (uint32_t)r * (uint32_t)H + ch * 8 + j, keep_thr) ? o[j] * inv_keep : 0.f;
       }
       *reinterpret_cast<bf16x8*>(yo + ch * 8) = pack8(o);
+    }
+  }
+}
+
+// y = gelu(x) elementwise (BertIntermediate activation, modeling_bert.py:396) -- run as its own
+// fully-occupied coalesced pass: cheaper than ~25 instructions/element in the 8-warp GEMM epilogue
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, size_t n) {
+  size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  const size_t stride = (size_t)gridDim.x * blockDim.x * 8;
+  for (; i + 8 <= n; i += stride) {
+    float a[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(x + i), a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = gelu_erf(a[j]);
+    *reinterpret_cast<bf16x8*>(y + i) = pack8(a);
+  }
+}
+
+// dx = dy * gelu'(pre) and dbias[n] += sum_m dx[m,n] in one pass (thread = 8 columns, loops rows)
+__global__ void __launch_bounds__(256)
+gelu_bwd_colsum_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ pre, bf16* __restrict__ dx,
+                       float* __restrict__ dbias, int M, int N, int rows_per_block) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + tx) * 8;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (col < N) {
+    for (int r = r0 + ty; r < r1; r += 8) {
+      float a[8], x[8];
+      const size_t off = (size_t)r * N + col;
+      unpack8(*reinterpret_cast<const bf16x8*>(dy + off), a);
+      unpack8(*reinterpret_cast<const bf16x8*>(pre + off), x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] *= gelu_erf_grad(x[j]);
+      const bf16x8 pk = pack8(a);
+      *reinterpret_cast<bf16x8*>(dx + off) = pk;
+      unpack8(pk, a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += a[j];
+    }
+  }
+  if (dbias == nullptr) return;
+  __shared__ float red[8][32 * 8 + 1];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[ty][tx * 8 + j] = acc[j];
+  __syncthreads();
+  if (ty == 0 && col < N) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w][tx * 8 + j];
+      atomicAdd(dbias + col + j, s);
     }
   }
 }
@@ -495,10 +570,48 @@ extern "C" int mvptr_ln_fwd(const void* x, const void* gamma, const void* beta, 
   CHECK_H(H);
   if (rows == 0) return 0;
   RowMap ym{y_rows_per_batch > 0 ? y_rows_per_batch : rows, y_rows_per_batch > 0 ? y_batch_stride : 0};
-  ln_fwd_kernel<<<(rows + 3) / 4, 128, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gamma,
-                                                                   (const bf16*)beta, (bf16*)y, ym, mean, rstd, rows,
-                                                                   H, eps, thr(p_drop), invk(p_drop), seed);
+  ln_fwd_kernel<<<(rows + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, nullptr, nullptr, (const bf16*)gamma, (const bf16*)beta, (bf16*)y, ym, mean, rstd, rows, H, eps,
+      0xffffffffu, 1.f, 0, thr(p_drop), invk(p_drop), seed);
   MVPTR_CHECK_LAUNCH("ln_fwd");
+  return 0;
+}
+
+extern "C" int mvptr_add_ln_fwd(const void* x, const void* residual, float in_p_drop, uint32_t in_seed, void* pre_out,
+                                const void* gamma, const void* beta, void* y, float* mean, float* rstd, int rows,
+                                int H, float eps, void* stream) {
+  MVPTR_PROF("add_ln_fwd", 8.0*rows*H, stream);
+  CHECK_H(H);
+  if (rows == 0) return 0;
+  RowMap ym{rows, 0};
+  ln_fwd_kernel<<<(rows + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (const bf16*)residual, (bf16*)pre_out, (const bf16*)gamma, (const bf16*)beta, (bf16*)y, ym, mean,
+      rstd, rows, H, eps, thr(in_p_drop), invk(in_p_drop), in_seed, 0xffffffffu, 1.f, 0);
+  MVPTR_CHECK_LAUNCH("add_ln_fwd");
+  return 0;
+}
+
+extern "C" int mvptr_gelu_fwd(const void* x, void* y, size_t n, void* stream) {
+  MVPTR_PROF("gelu_fwd", 4.0*n, stream);
+  if (n == 0) return 0;
+  if (n & 7) MVPTR_FAIL(MVPTR_ERR_ARG, "gelu_fwd: n must be a multiple of 8");
+  size_t blocks = (n / 8 + 255) / 256;
+  if (blocks > (size_t)kNumSMs * 16) blocks = (size_t)kNumSMs * 16;
+  gelu_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, n);
+  MVPTR_CHECK_LAUNCH("gelu_fwd");
+  return 0;
+}
+
+extern "C" int mvptr_gelu_bwd_colsum(const void* dy, const void* pre, void* dx, float* dbias, int M, int N,
+                                     void* stream) {
+  MVPTR_PROF("gelu_bwd_colsum", 6.0*M*N, stream);
+  if (M <= 0 || N <= 0) return 0;
+  if (N & 7) MVPTR_FAIL(MVPTR_ERR_ARG, "gelu_bwd_colsum: N must be a multiple of 8");
+  const int rpb = 256;
+  dim3 grid((N + 255) / 256, (M + rpb - 1) / rpb);
+  gelu_bwd_colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, (const bf16*)pre, (bf16*)dx, dbias, M,
+                                                                 N, rpb);
+  MVPTR_CHECK_LAUNCH("gelu_bwd_colsum");
   return 0;
 }
 

@@ -146,7 +146,7 @@ class EncoderFn(Function):
         if not x.is_contiguous():
             x = x.contiguous()
         saved = []
-        n_bf16 = M * (8 * H + 2 * I)  # qkv 3H | att | pre1 | a1 | pre2 | out | pre_g I | inter I
+        n_bf16 = M * (8 * H + 2 * I)  # qkv 3H | att | pre1 | a1 | pre2 | pre_g I | inter I | tmp
         n_f32 = B * nh * L + 4 * M
         ws = None
         for li in range(layer_lo, layer_hi):
@@ -172,12 +172,13 @@ class EncoderFn(Function):
             la.pre2 = b0 + 2 * M * 6 * H
             la.pre_g = b0 + 2 * M * 7 * H
             la.inter = b0 + 2 * M * (7 * H + I)
+            la.tmp = b0 + 2 * M * (7 * H + 2 * I)
             la.out = out.data_ptr()
             la.lse = f0
             la.st1 = f0 + 4 * B * nh * L
             la.st2 = f0 + 4 * (B * nh * L + 2 * M)
-            _lib.layer_call("mvptr_layer_fwd", la, 7)
-            rt.launches += 7
+            _lib.layer_call("mvptr_layer_fwd", la, 9)
+            rt.launches += 9
             if save:
                 saved.append((pf, la, x, blk, f32, out))
             x = out

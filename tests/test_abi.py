@@ -71,6 +71,7 @@ def test_gemm_args_struct_matches_header(built):
 def test_layer_args_struct_matches_header(built):
     hdr = open(os.path.join(ROOT, "include", "mvptr_b200.h")).read()
     body = re.search(r"typedef struct \{([^}]*?)\} mvptr_layer_args;", hdr, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     names = []
     for decl in body.split(";"):
         decl = decl.strip()
