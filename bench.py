@@ -88,7 +88,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "200", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
@@ -210,6 +210,9 @@ def run_b200(args):
     opt = AdamW.for_model(model, lr=1e-4, weight_decay=0.01, max_grad_norm=10.0)
     rt = model.runtime()
     arena = rt.arena
+    if world > 1:  # bucketed gradient all-reduce on a side stream, overlapped with backward
+        from mvp_pytorch_b200.parallel import allreduce_gradients, enable_overlapped_allreduce
+        enable_overlapped_allreduce(model)
 
     n_batches = 4
     host = []
@@ -228,7 +231,7 @@ def run_b200(args):
         out = model(max_tag_length=W["Lt"], **batch)
         out[0].backward()
         if world > 1:
-            dist.all_reduce(arena.grad, op=dist.ReduceOp.AVG)
+            allreduce_gradients(model)
         opt.step()
         return out
 
@@ -238,10 +241,12 @@ def run_b200(args):
         torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = rt.launches
+        t0 = time.perf_counter()
         s.record()
         for i in range(steps):
             run_one(i)
         e.record()
+        timed.host_ms = (time.perf_counter() - t0) * 1e3 / steps  # enqueue time per step (host side)
         torch.cuda.synchronize()
         ms = s.elapsed_time(e)
         if world > 1:
@@ -266,6 +271,7 @@ def run_b200(args):
     # ---- (1) device-resident throughput
     sampler = ClockSampler(local) if rank == 0 else None
     ms, launches = timed(lambda i: train_step(resident[i % n_batches]), args.steps)
+    host_ms = timed.host_ms
     clocks = sampler.stop() if sampler else None
     # +2 launches / step: fused AdamW and the gradient sum of squares
     launches_per_step = launches / args.steps + 2
@@ -349,6 +355,7 @@ def run_b200(args):
         "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 24,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(round(launches_per_step * args.steps)),
+        "host_enqueue_ms_per_step": host_ms,
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu:

@@ -242,6 +242,15 @@ typedef struct {
 int mvptr_layer_fwd(const mvptr_layer_args* args, void* stream);
 int mvptr_layer_bwd(const mvptr_layer_args* args, void* stream);
 
+/* ---- retrieval scoring (run_retrieval.py) ------------------------------------------------
+ * Per-row top-k of fp32 scores in the reference's ranking order: np.argsort(sim)[::-1][:k] of
+ * compute_ranks_coarse (run_retrieval.py:481-522) / compute_ranks (:429-478), made deterministic
+ * as descending score then descending index.  idx_out int64 [rows,k]; val_out (nullable) [rows,k]. */
+int mvptr_topk_rows(const float* x, long long ld, int rows, int n, int k, int64_t* idx_out, float* val_out,
+                    void* stream);
+/* softmax(logits)[:,1] of the 2-way ITM classifier (run_retrieval.py:776-777, 818-820) */
+int mvptr_match_prob(const float* logits, float* prob, int n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

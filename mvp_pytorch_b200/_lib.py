@@ -84,6 +84,8 @@ SIGNATURES = {
     "mvptr_small_ce": "ppiipppp",
     "mvptr_adamw": "ppppp" + "zz" + "fffff" + "ii" + "pf" + "p",
     "mvptr_sumsq": "pzpp",
+    "mvptr_topk_rows": "pliiippp",
+    "mvptr_match_prob": "ppip",
     "mvptr_wra_fwd": "piiippppp" + "ipppp" + "p",
     "mvptr_wra_bwd": "piiipppppp" + "p" + "p",
     "mvptr_gelu_bwd": "pppzp",

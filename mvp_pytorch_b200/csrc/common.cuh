@@ -79,7 +79,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // branchy ~25-instruction path -- the FFN epilogues run this per element next to the tensor pipe.
 __device__ __forceinline__ void erf_gauss(float x, float& erf_v, float& gauss) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));  // MUFU.RCP, ~1 ulp
   gauss = __expf(-z * z);  // exp(-x^2/2)
   float p = fmaf(t, 1.061405429f, -1.453152027f);
   p = fmaf(t, p, 1.421413741f);

@@ -170,6 +170,15 @@ ln_fwd_kernel(const bf16* __restrict__ x_in, const bf16* __restrict__ residual, 
 __global__ void __launch_bounds__(256) gelu_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, size_t n) {
   size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   const size_t stride = (size_t)gridDim.x * blockDim.x * 8;
+  for (; i + stride + 8 <= n; i += 2 * stride) {
+    const bf16x8 q0 = *reinterpret_cast<const bf16x8*>(x + i), q1 = *reinterpret_cast<const bf16x8*>(x + i + stride);
+    float a[8], b[8];
+    unpack8(q0, a); unpack8(q1, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a[j] = gelu_erf(a[j]); b[j] = gelu_erf(b[j]); }
+    *reinterpret_cast<bf16x8*>(y + i) = pack8(a);
+    *reinterpret_cast<bf16x8*>(y + i + stride) = pack8(b);
+  }
   for (; i + 8 <= n; i += stride) {
     float a[8];
     unpack8(*reinterpret_cast<const bf16x8*>(x + i), a);
@@ -189,7 +198,26 @@ gelu_bwd_colsum_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ pre
   const int r1 = min(M, r0 + rows_per_block);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (col < N) {
-    for (int r = r0 + ty; r < r1; r += 8) {
+    int r = r0 + ty;
+    for (; r + 8 < r1; r += 16) {  // two rows per iteration: 4 independent loads in flight
+      const size_t o0 = (size_t)r * N + col, o1 = (size_t)(r + 8) * N + col;
+      const bf16x8 d0 = *reinterpret_cast<const bf16x8*>(dy + o0), d1 = *reinterpret_cast<const bf16x8*>(dy + o1);
+      const bf16x8 p0 = *reinterpret_cast<const bf16x8*>(pre + o0), p1 = *reinterpret_cast<const bf16x8*>(pre + o1);
+      float a0[8], a1[8], x0[8], x1[8];
+      unpack8(d0, a0); unpack8(d1, a1); unpack8(p0, x0); unpack8(p1, x1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a0[j] *= gelu_erf_grad(x0[j]);
+        a1[j] *= gelu_erf_grad(x1[j]);
+      }
+      const bf16x8 k0 = pack8(a0), k1 = pack8(a1);
+      *reinterpret_cast<bf16x8*>(dx + o0) = k0;
+      *reinterpret_cast<bf16x8*>(dx + o1) = k1;
+      unpack8(k0, a0); unpack8(k1, a1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += a0[j] + a1[j];
+    }
+    for (; r < r1; r += 8) {
       float a[8], x[8];
       const size_t off = (size_t)r * N + col;
       unpack8(*reinterpret_cast<const bf16x8*>(dy + off), a);
@@ -226,102 +254,155 @@ gelu_bwd_colsum_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ pre
 //   dx_drop = dx * input-dropout mask (the dropout that sat between the dense and the
 //             residual add, modeling_bert.py:350-351) ; dbias += sum_r dx_drop
 // ---------------------------------------------------------------------------------
-template <int NC, bool DBIAS>
-__global__ void __launch_bounds__(128, 3)
-ln_bwd_kernel(const bf16* __restrict__ dy, RowMap dymap, const bf16* __restrict__ x_in,
-              const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const bf16* __restrict__ gamma,
-              bf16* __restrict__ dx, bf16* __restrict__ dx_drop, float* __restrict__ dgamma,
-              float* __restrict__ dbeta, float* __restrict__ dbias, int rows, int H, uint32_t out_keep_thr,
-              float out_inv_keep, uint32_t out_seed, uint32_t in_keep_thr, float in_inv_keep, uint32_t in_seed) {
-  constexpr int kWarps = 4;
+// LayerNorm backward in two fully-occupied passes (the kernel is HBM-latency bound, so occupancy
+// matters more than the one re-read):
+//   pass A (warp per row, inputs kept PACKED in registers, ~56 regs): dx and dx_drop;
+//   pass B (thread = 8 columns, loops rows, coalesced): dgamma, dbeta, dbias column sums.
+template <int NC>
+__global__ void __launch_bounds__(128, 8)
+ln_bwd_dx_kernel(const bf16* __restrict__ dy, RowMap dymap, const bf16* __restrict__ x_in,
+                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const bf16* __restrict__ gamma,
+                 bf16* __restrict__ dx, bf16* __restrict__ dx_drop, int rows, int H, uint32_t out_keep_thr,
+                 float out_inv_keep, uint32_t out_seed, uint32_t in_keep_thr, float in_inv_keep, uint32_t in_seed) {
+  extern __shared__ float s_gam[];
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int nwarp_total = gridDim.x * kWarps;
   const int nchunk = H >> 3;
-  float gam[NC][8], ag[NC][8], ab[NC][8], abias[DBIAS ? NC : 1][8];
+  for (int i = threadIdx.x; i < H; i += blockDim.x) s_gam[i] = __bfloat162float(gamma[i]);
+  __syncthreads();
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float mean = mean_in[r], rstd = rstd_in[r];
+  const bf16* dyr = dy + dymap.off(r, H);
+  bf16x8 pg[NC], px[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     const int ch = lane + 32 * c;
-    if (ch < nchunk) unpack8(*reinterpret_cast<const bf16x8*>(gamma + ch * 8), gam[c]);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      ag[c][j] = ab[c][j] = 0.f;
-      if (DBIAS) abias[c][j] = 0.f;
+    if (ch < nchunk) {
+      pg[c] = *reinterpret_cast<const bf16x8*>(dyr + ch * 8);
+      px[c] = *reinterpret_cast<const bf16x8*>(x_in + (size_t)r * H + ch * 8);
     }
   }
-  for (int r = blockIdx.x * kWarps + warp; r < rows; r += nwarp_total) {
-    const float mean = mean_in[r], rstd = rstd_in[r];
-    const bf16* dyr = dy + dymap.off(r, H);
-    float g[NC][8], xh[NC][8];
-    float s1 = 0.f, s2 = 0.f;
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const int ch = lane + 32 * c;
-      if (ch < nchunk) {
-        float xv[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(dyr + ch * 8), g[c]);
-        unpack8(*reinterpret_cast<const bf16x8*>(x_in + (size_t)r * H + ch * 8), xv);
+  for (int c = 0; c < NC; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nchunk) {
+      float g[8], xv[8];
+      unpack8(pg[c], g);
+      unpack8(px[c], xv);
+      if (out_keep_thr != 0xffffffffu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          g[j] = dropout_keep(out_seed, (uint32_t)r * (uint32_t)H + ch * 8 + j, out_keep_thr) ? g[j] * out_inv_keep : 0.f;
+        pg[c] = pack8(g);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float gg = g[j] * s_gam[ch * 8 + j];
+        s1 += gg;
+        s2 += gg * ((xv[j] - mean) * rstd);
+      }
+    }
+  }
+  s1 = warp_sum(s1) / H;
+  s2 = warp_sum(s2) / H;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nchunk) {
+      float g[8], xv[8], o[8];
+      unpack8(pg[c], g);
+      unpack8(px[c], xv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = rstd * (g[j] * s_gam[ch * 8 + j] - s1 - (xv[j] - mean) * rstd * s2);
+      if (dx) *reinterpret_cast<bf16x8*>(dx + (size_t)r * H + ch * 8) = pack8(o);
+      if (dx_drop) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o[j] = dropout_keep(in_seed, (uint32_t)r * (uint32_t)H + ch * 8 + j, in_keep_thr) ? o[j] * in_inv_keep : 0.f;
+        *reinterpret_cast<bf16x8*>(dx_drop + (size_t)r * H + ch * 8) = pack8(o);
+      }
+    }
+  }
+}
+
+// dgamma[n] += sum_r g*xhat ; dbeta[n] += sum_r g ; dbias[n] += sum_r dxb[r,n]
+// (g = dy with the output-dropout mask; dxb = the dx that reached the dense bias)
+__global__ void __launch_bounds__(256)
+ln_bwd_colsum_kernel(const bf16* __restrict__ dy, RowMap dymap, const bf16* __restrict__ x_in,
+                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                     const bf16* __restrict__ dxb, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                     float* __restrict__ dbias, int rows, int H, int rows_per_block, uint32_t out_keep_thr,
+                     float out_inv_keep, uint32_t out_seed) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + tx) * 8;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  float ag[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ab[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ad[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (col < H) {
+    for (int r = r0 + ty; r < r1; r += 16) {
+      const int ra = r, rb = r + 8;
+      const bool hb = rb < r1;
+      const bf16x8 ga = *reinterpret_cast<const bf16x8*>(dy + dymap.off(ra, H) + col);
+      const bf16x8 xa = *reinterpret_cast<const bf16x8*>(x_in + (size_t)ra * H + col);
+      bf16x8 gb = ga, xb = xa, da, db;
+      if (hb) {
+        gb = *reinterpret_cast<const bf16x8*>(dy + dymap.off(rb, H) + col);
+        xb = *reinterpret_cast<const bf16x8*>(x_in + (size_t)rb * H + col);
+      }
+      if (dbias) {
+        da = *reinterpret_cast<const bf16x8*>(dxb + (size_t)ra * H + col);
+        db = hb ? *reinterpret_cast<const bf16x8*>(dxb + (size_t)rb * H + col) : da;
+      }
+      const float ma = mean_in[ra], sa = rstd_in[ra];
+      const float mb = hb ? mean_in[rb] : 0.f, sb = hb ? rstd_in[rb] : 0.f;
+      float g[8], xv[8], q[8];
+      unpack8(ga, g);
+      unpack8(xa, xv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (out_keep_thr != 0xffffffffu)
+          g[j] = dropout_keep(out_seed, (uint32_t)ra * (uint32_t)H + col + j, out_keep_thr) ? g[j] * out_inv_keep : 0.f;
+        ag[j] += g[j] * ((xv[j] - ma) * sa);
+        ab[j] += g[j];
+      }
+      if (dbias) {
+        unpack8(da, q);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ad[j] += q[j];
+      }
+      if (hb) {
+        unpack8(gb, g);
+        unpack8(xb, xv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if (out_keep_thr != 0xffffffffu)
-            g[c][j] = dropout_keep(out_seed, (uint32_t)r * (uint32_t)H + ch * 8 + j, out_keep_thr)
-                          ? g[c][j] * out_inv_keep : 0.f;
-          xh[c][j] = (xv[j] - mean) * rstd;
-          ag[c][j] += g[c][j] * xh[c][j];
-          ab[c][j] += g[c][j];
-          const float gg = g[c][j] * gam[c][j];
-          s1 += gg;
-          s2 += gg * xh[c][j];
+            g[j] = dropout_keep(out_seed, (uint32_t)rb * (uint32_t)H + col + j, out_keep_thr) ? g[j] * out_inv_keep : 0.f;
+          ag[j] += g[j] * ((xv[j] - mb) * sb);
+          ab[j] += g[j];
         }
-      }
-    }
-    s1 = warp_sum(s1) / H;
-    s2 = warp_sum(s2) / H;
+        if (dbias) {
+          unpack8(db, q);
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const int ch = lane + 32 * c;
-      if (ch < nchunk) {
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rstd * (g[c][j] * gam[c][j] - s1 - xh[c][j] * s2);
-        if (dx) *reinterpret_cast<bf16x8*>(dx + (size_t)r * H + ch * 8) = pack8(o);
-        if (dx_drop) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            o[j] = dropout_keep(in_seed, (uint32_t)r * (uint32_t)H + ch * 8 + j, in_keep_thr) ? o[j] * in_inv_keep : 0.f;
-          *reinterpret_cast<bf16x8*>(dx_drop + (size_t)r * H + ch * 8) = pack8(o);
-        }
-        if (DBIAS) {
-          // bias grad sees what the dense output saw: bf16-rounded, dropped dx
-          bf16x8 pk = pack8(o);
-          float q[8];
-          unpack8(pk, q);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) abias[c][j] += q[j];
+          for (int j = 0; j < 8; ++j) ad[j] += q[j];
         }
       }
     }
   }
-  // block reduce over the warps, then one atomic per column per block
-  __shared__ float red[kWarps][32 * 8 + 1];
-  for (int pass = 0; pass < (DBIAS ? 3 : 2); ++pass) {
-    float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dbias);
+  __shared__ float red[8][32 * 8 + 1];
+  for (int pass = 0; pass < (dbias ? 3 : 2); ++pass) {
+    __syncthreads();
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const int ch = lane + 32 * c;
-      __syncthreads();
+    for (int j = 0; j < 8; ++j) red[ty][tx * 8 + j] = pass == 0 ? ag[j] : (pass == 1 ? ab[j] : ad[j]);
+    __syncthreads();
+    if (ty == 0 && col < H) {
+      float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dbias);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        red[warp][lane * 8 + j] = pass == 0 ? ag[c][j] : (pass == 1 ? ab[c][j] : abias[DBIAS ? c : 0][j]);
-      __syncthreads();
-      if (warp == 0 && ch < nchunk) {
+      for (int j = 0; j < 8; ++j) {
+        float s = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float s = 0.f;
-#pragma unroll
-          for (int w = 0; w < kWarps; ++w) s += red[w][lane * 8 + j];
-          atomicAdd(dst + ch * 8 + j, s);
-        }
+        for (int w = 0; w < 8; ++w) s += red[w][tx * 8 + j];
+        atomicAdd(dst + col + j, s);
       }
     }
   }
@@ -336,7 +417,20 @@ colsum_kernel(const bf16* __restrict__ x, int ldx, float* __restrict__ out, int 
   const int r1 = min(M, r0 + rows_per_block);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (col < N) {
-    for (int r = r0 + ty; r < r1; r += 8) {
+    int r = r0 + ty;
+    for (; r + 24 < r1; r += 32) {  // 4 independent 16-byte loads in flight per thread
+      bf16x8 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = *reinterpret_cast<const bf16x8*>(x + (size_t)(r + 8 * u) * ldx + col);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float v[8];
+        unpack8(q[u], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      }
+    }
+    for (; r < r1; r += 8) {
       float v[8];
       unpack8(*reinterpret_cast<const bf16x8*>(x + (size_t)r * ldx + col), v);
 #pragma unroll
@@ -625,29 +719,29 @@ extern "C" int mvptr_ln_bwd(const void* dy, int dy_rows_per_batch, long long dy_
   if (dx_drop && in_p_drop <= 0.f) MVPTR_FAIL(MVPTR_ERR_ARG, "ln_bwd: dx_drop given without in_p_drop");
   RowMap dm{dy_rows_per_batch > 0 ? dy_rows_per_batch : rows, dy_rows_per_batch > 0 ? dy_batch_stride : 0};
   if (!dgamma || !dbeta) MVPTR_FAIL(MVPTR_ERR_ARG, "ln_bwd: dgamma/dbeta accumulators are required");
-  int grid = (rows + 3) / 4;
-  if (grid > kNumSMs * 3) grid = kNumSMs * 3;
+  if (dbias && !dx && !dx_drop) MVPTR_FAIL(MVPTR_ERR_ARG, "ln_bwd: dbias needs dx or dx_drop to be written");
+  const int grid = (rows + 3) / 4;
   const int nc = (H + 255) / 256;
-#define LN_BWD_LAUNCH(NC, DB)                                                                                     \
-  ln_bwd_kernel<NC, DB><<<grid, 128, 0, (cudaStream_t)stream>>>(                                                  \
-      (const bf16*)dy, dm, (const bf16*)x, mean, rstd, (const bf16*)gamma, (bf16*)dx, (bf16*)dx_drop, dgamma,     \
-      dbeta, dbias, rows, H, thr(out_p_drop), invk(out_p_drop), out_seed, thr(in_p_drop), invk(in_p_drop), in_seed)
-  if (dbias) {
-    switch (nc) {
-      case 1: LN_BWD_LAUNCH(1, true); break;
-      case 2: LN_BWD_LAUNCH(2, true); break;
-      case 3: LN_BWD_LAUNCH(3, true); break;
-      default: LN_BWD_LAUNCH(4, true); break;
-    }
-  } else {
-    switch (nc) {
-      case 1: LN_BWD_LAUNCH(1, false); break;
-      case 2: LN_BWD_LAUNCH(2, false); break;
-      case 3: LN_BWD_LAUNCH(3, false); break;
-      default: LN_BWD_LAUNCH(4, false); break;
-    }
+  const int smem = H * (int)sizeof(float);
+#define LN_BWD_LAUNCH(NC)                                                                                          \
+  ln_bwd_dx_kernel<NC><<<grid, 128, smem, (cudaStream_t)stream>>>(                                                 \
+      (const bf16*)dy, dm, (const bf16*)x, mean, rstd, (const bf16*)gamma, (bf16*)dx, (bf16*)dx_drop, rows, H,      \
+      thr(out_p_drop), invk(out_p_drop), out_seed, thr(in_p_drop), invk(in_p_drop), in_seed)
+  switch (nc) {
+    case 1: LN_BWD_LAUNCH(1); break;
+    case 2: LN_BWD_LAUNCH(2); break;
+    case 3: LN_BWD_LAUNCH(3); break;
+    default: LN_BWD_LAUNCH(4); break;
   }
 #undef LN_BWD_LAUNCH
+  MVPTR_CHECK_LAUNCH("ln_bwd_dx");
+  {
+    const int rpb = 256;
+    dim3 g2((H + 255) / 256, (rows + rpb - 1) / rpb);
+    ln_bwd_colsum_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)dy, dm, (const bf16*)x, mean, rstd, (const bf16*)(dx_drop ? dx_drop : dx), dgamma, dbeta, dbias,
+        rows, H, rpb, thr(out_p_drop), invk(out_p_drop), out_seed);
+  }
   MVPTR_CHECK_LAUNCH("ln_bwd");
   return 0;
 }

@@ -213,6 +213,15 @@ class EncoderFn(Function):
             la.dpre_g = s0 + 2 * M * 9 * H
             _lib.layer_call("mvptr_layer_bwd", la, 13)
             rt.launches += 13
+            sync = getattr(rt, "grad_sync", None)
+            if sync is not None and sync.enabled:  # this layer's gradients are final: reduce them now
+                offs = rt.arena.offsets
+                w0 = offs[pf + "attention.self.query.weight"][0]
+                w1 = offs[pf + "output.dense.weight"]
+                sync.layer_done(w0, w1[0] + w1[1])
+                b0 = offs[pf + "attention.self.query.bias"][0]
+                b1 = offs[pf + "output.LayerNorm.bias"]
+                sync.layer_done(b0, b1[0] + b1[1])
             dy = dx
         ctx.saved = None
         return dy.view(B, L, H), None, None, None, None, None, None, None

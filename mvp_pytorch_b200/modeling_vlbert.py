@@ -202,6 +202,43 @@ class BiBertImgModel(BertPreTrainedModel):
         return (E.ClsProjNormFn.apply(txt, rt, pf + "txt_proj", anchor),
                 E.ClsProjNormFn.apply(vis, rt, pf + "vis_proj", anchor))
 
+    # ---- single-modality entry points used by the sharded retrieval scorer ---------------------
+    def encode_text(self, input_ids_a, token_type_ids_a=None, attention_mask_a=None, position_ids_a=None):
+        """Text stream only (embeddings + txt_encoder, :479, :509) -> (tokens [B,La,H], mask, normalised
+        global embedding [B,H] fp32).  Stage 1 is pair independent, so a caption is
+        encoded once however many images it is later paired with."""
+        rt, pf = self._ctx()
+        rt.begin_forward(self.training)
+        nl = self.config.num_hidden_layers // 2
+        anchor = self.txt_proj
+        save = torch.is_grad_enabled() and anchor.requires_grad
+        ids = input_ids_a.to(torch.int64).contiguous()
+        seg = token_type_ids_a.to(torch.int64).contiguous() if token_type_ids_a is not None else None
+        pos = position_ids_a.to(torch.int64).contiguous() if position_ids_a is not None else None
+        mask = _mask2d(attention_mask_a, ids)
+        emb = E.EmbedFn.apply(ids, seg, pos, rt, pf + "embeddings", save, anchor)
+        txt = E.encoder(rt, pf + "txt_encoder", emb, E.mask_additive(rt, mask), nl, anchor)
+        return txt, mask, E.ClsProjNormFn.apply(txt, rt, pf + "txt_proj", anchor)
+
+    def encode_image(self, input_ids_b, token_type_ids_b=None, attention_mask_b=None, img_feats=None,
+                     position_ids_b=None):
+        """Visual stream only (tag embeddings + region projection + vis_encoder, :481-512)."""
+        rt, pf = self._ctx()
+        rt.begin_forward(self.training)
+        nl = self.config.num_hidden_layers // 2
+        anchor = self.txt_proj
+        save = torch.is_grad_enabled() and anchor.requires_grad
+        ids = input_ids_b.to(torch.int64).contiguous()
+        seg = token_type_ids_b.to(torch.int64).contiguous() if token_type_ids_b is not None else None
+        pos = position_ids_b.to(torch.int64).contiguous() if position_ids_b is not None else None
+        if attention_mask_b is None:
+            attention_mask_b = torch.ones(ids.shape[0], ids.shape[1] + img_feats.shape[1], dtype=torch.int64,
+                                          device=ids.device)
+        mask = _mask2d(attention_mask_b, ids)
+        emb = E.VisInputFn.apply(ids, seg, pos, img_feats, rt, pf, save, anchor)
+        vis = E.encoder(rt, pf + "vis_encoder", emb, E.mask_additive(rt, mask), nl, anchor)
+        return vis, mask, E.ClsProjNormFn.apply(vis, rt, pf + "vis_proj", anchor)
+
     def forward_joint(self, *args, **kwargs):
         raise NotImplementedError("forward_joint (two-image input, :725-869) is a listed next step (SURVEY f-3)")
 
@@ -238,17 +275,25 @@ class BertVQAHeads(_ParamOnly):
         self.predictions = BertQAPredictionHead(config)
 
 
-def _mlm_loss(rt, top, seq2d, labels2d, head_prefix, anchor):
-    """masked_select rows with label > -1 -> LM head -> CE(ignore_index=-1) (:1231-1235, :1244-1249)."""
-    cfg = top.config
+def _mlm_rows(labels2d):
+    """Flat indexes and labels of the positions with a label > -1 (the masked_select of :1231-1235 /
+    :1244-1249).  The dynamic size costs one host sync, so callers do this on the INPUT labels before
+    any encoder work is queued: the host then runs ahead of the GPU for the rest of the step."""
     flat = labels2d.reshape(-1)
     idx = torch.nonzero(flat > -1).reshape(-1)
+    return idx, flat[idx].contiguous()
+
+
+def _mlm_loss(rt, top, seq2d, rows, head_prefix, anchor):
+    """selected rows -> LM head -> CE(ignore_index=-1) (:1231-1235, :1244-1249)."""
+    cfg = top.config
+    idx, labels = rows
     if idx.numel() == 0:
         return torch.full((), float("nan"), device=seq2d.device)  # CrossEntropy of an empty selection
-    rows = E.GatherRowsFn.apply(seq2d, idx, rt)
-    t = E.HeadTransformFn.apply(rows, rt, head_prefix + ".transform", anchor)
-    return E.VocabCEFn.apply(t, flat[idx].contiguous(), rt, "bert.embeddings.word_embeddings.weight",
-                             cfg.only_word_size, head_prefix + ".bias", anchor)
+    x = E.GatherRowsFn.apply(seq2d, idx, rt)
+    t = E.HeadTransformFn.apply(x, rt, head_prefix + ".transform", anchor)
+    return E.VocabCEFn.apply(t, labels, rt, "bert.embeddings.word_embeddings.weight", cfg.only_word_size,
+                             head_prefix + ".bias", anchor)
 
 
 def _draw_wra_choices(n_samples, max_phrases, device):
@@ -289,6 +334,14 @@ class BiBertImgForPreTraining(BertPreTrainedModel):
         rt = self.runtime()
         self._adopt(self.bert, "bert.")
         anchor = self.logit_scale
+        B, La = input_ids_a.shape
+        Ltot = La + (attention_mask_b.shape[1] - max_tag_length if attention_mask_b is not None
+                     else img_feats.shape[1])
+        # label-only bookkeeping first (its host sync must not sit behind the queued forward)
+        vis_rows = _mlm_rows(masked_lm_labels_b)
+        lab = torch.full((B, Ltot), -1, dtype=torch.int64, device=input_ids_a.device)
+        lab[:, :La] = masked_lm_labels_a
+        txt_rows = _mlm_rows(lab)
         outputs, single_stream_output, hard_indexes = self.bert(
             input_ids_a=input_ids_a, position_ids_a=position_ids_a, token_type_ids_a=token_type_ids_a,
             attention_mask_a=attention_mask_a, head_mask=head_mask, img_feats=img_feats, input_ids_b=input_ids_b,
@@ -296,18 +349,15 @@ class BiBertImgForPreTraining(BertPreTrainedModel):
             max_tag_length=max_tag_length, encode_hn=True)
         txt, vis, sim_mat = single_stream_output
         sequence_output, pooled_output, hard_sequence_output, hard_pooled_output = outputs
-        B, La = input_ids_a.shape
         H = self.config.hidden_size
+        assert sequence_output.shape[1] == Ltot
 
         # visual-tag MLM on the visual encoder output (:1231-1235)
-        vis_mlm_loss = _mlm_loss(rt, self, vis.reshape(-1, H), masked_lm_labels_b, "half_mlm", anchor)
+        vis_mlm_loss = _mlm_loss(rt, self, vis.reshape(-1, H), vis_rows, "half_mlm", anchor)
         # VSC (:1238-1241)
         retrieval_loss, _ = E.VSCFn.apply(sim_mat, rt, "logit_scale", anchor)
         # MLM on the text part of the joint sequence (:1244-1249)
-        Ltot = sequence_output.shape[1]
-        lab = torch.full((B, Ltot), -1, dtype=torch.int64, device=input_ids_a.device)
-        lab[:, :La] = masked_lm_labels_a
-        masked_lm_loss = _mlm_loss(rt, self, sequence_output.reshape(-1, H), lab, "cls.predictions", anchor)
+        masked_lm_loss = _mlm_loss(rt, self, sequence_output.reshape(-1, H), txt_rows, "cls.predictions", anchor)
         # ITM: 0 = matched, 1 = hard negative (:1247-1251)
         pooled_all = torch.cat([pooled_output, hard_pooled_output], dim=0)
         rel = E.SmallHeadFn.apply(pooled_all, rt, "cls.seq_relationship.weight", "cls.seq_relationship.bias", anchor)

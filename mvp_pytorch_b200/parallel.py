@@ -1,0 +1,122 @@
+"""One-process-per-GPU data parallelism for the hot path.
+
+The reference trains with DeepSpeed ZeRO-2 / DDP (run_pretrain_ml.py:226-227, 406-418) and evaluates
+with single-process nn.DataParallel (run_retrieval.py:577-578).  Here every rank owns one GPU and
+a full replica; the only data-path exchange of a training step is the all-reduce of the flat fp32
+gradient arena, issued bucket by bucket on a side stream while backward is still running; retrieval
+shards its independent units (captions, images, pairs) and all-gathers only embeddings / scores.
+
+Everything in this file is host logic over torch.distributed and runs on the gloo backend too
+(tests/test_parallel.py, world_size 2 on CPU).
+"""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(n, rank, world_size):
+    """Contiguous [lo, hi) slice of n independent units for this rank (sizes differ by at most one)."""
+    base, rem = divmod(n, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def all_gather_rows(t, group=None):
+    """Concatenate per-rank tensors that differ in dim 0 (NCCL / gloo all_gather needs equal shapes)."""
+    rank, ws = world()
+    if ws == 1:
+        return t
+    n = torch.tensor([t.shape[0]], device=t.device, dtype=torch.int64)
+    sizes = [torch.zeros_like(n) for _ in range(ws)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s) for s in sizes]
+    mx = max(sizes)
+    pad = t
+    if t.shape[0] < mx:
+        pad = torch.cat([t, t.new_zeros((mx - t.shape[0],) + tuple(t.shape[1:]))], 0)
+    out = [torch.empty_like(pad) for _ in range(ws)]
+    dist.all_gather(out, pad.contiguous(), group=group)
+    return torch.cat([o[:s] for o, s in zip(out, sizes)], 0)
+
+
+def merge_topk(scores, indexes, k):
+    """Merge per-shard top-k candidate lists [rows, shards*k] into the global top-k with the
+    reference ranking order (descending score, ties -> larger global index first)."""
+    order = torch.arange(scores.shape[1], device=scores.device).expand_as(scores)
+    # sort by (score desc, index desc): stable sort by index desc first, then by score desc
+    by_idx = torch.sort(indexes, dim=1, descending=True, stable=True)[1]
+    s1, i1 = torch.gather(scores, 1, by_idx), torch.gather(indexes, 1, by_idx)
+    by_score = torch.sort(s1, dim=1, descending=True, stable=True)[1]
+    del order
+    return torch.gather(s1, 1, by_score)[:, :k], torch.gather(i1, 1, by_score)[:, :k]
+
+
+class GradientSync:
+    """Bucketed all-reduce(avg) of the flat gradient arena, overlapped with backward.
+
+    ``layer_done(lo, hi)`` is called by the engine as soon as the gradients of arena range
+    [lo, hi) are final (after each encoder layer's backward); the range is all-reduced on a
+    communication stream.  ``finish()`` reduces whatever was not covered and joins the streams.
+    Every rank runs the same model, so the collective order is identical everywhere."""
+
+    def __init__(self, arena, group=None):
+        self.arena, self.group = arena, group
+        self.done = []
+        self.stream = torch.cuda.Stream() if arena.device.type == "cuda" else None
+        self.enabled = world()[1] > 1
+
+    def _reduce(self, lo, hi):
+        g = self.arena.grad[lo:hi]
+        if self.stream is None:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+            g.div_(world()[1])
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ev)
+            dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
+
+    def layer_done(self, lo, hi):
+        if not self.enabled or hi <= lo:
+            return
+        self._reduce(lo, hi)
+        self.done.append((lo, hi))
+
+    def finish(self):
+        if not self.enabled:
+            return
+        pos = 0
+        for lo, hi in sorted(self.done):
+            if lo > pos:
+                self._reduce(pos, lo)
+            pos = max(pos, hi)
+        if pos < self.arena.numel:
+            self._reduce(pos, self.arena.numel)
+        self.done = []
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+
+
+def allreduce_gradients(model, group=None):
+    """Average the gradients of all replicas (call after backward(), before optimizer.step()).
+    Uses the overlapped bucket schedule when ``enable_overlapped_allreduce(model)`` was called
+    before backward; otherwise reduces the whole arena in one collective."""
+    rt = model.runtime()
+    sync = getattr(rt, "grad_sync", None)
+    if sync is None:
+        sync = GradientSync(rt.arena, group)
+    sync.finish()
+
+
+def enable_overlapped_allreduce(model, group=None):
+    """Register the bucketed, backward-overlapped gradient all-reduce on a model."""
+    rt = model.runtime()
+    rt.arena.ensure_grad()
+    rt.grad_sync = GradientSync(rt.arena, group)
+    return rt.grad_sync

