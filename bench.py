@@ -199,7 +199,8 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     W = WORK
     B = args.batch or W["B"]
     torch.manual_seed(1234 + rank)
@@ -308,10 +309,13 @@ def run_b200(args):
     assert torch.isfinite(loss_host).all(), "non-finite loss in the end-to-end run"
 
     # ---- (3) one instrumented step: CUDA events around every kernel launch -> per-kernel roofline
+    #          (every rank runs the step -- it contains collectives -- only rank 0 records)
     prof = None
     if rank == 0:
         _lib.profile_enable(True)
-        train_step(resident[0])
+    train_step(resident[0])
+    torch.cuda.synchronize()
+    if rank == 0:
         prof = _lib.profile_collect()
         _lib.profile_enable(False)
 

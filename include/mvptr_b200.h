@@ -81,7 +81,8 @@ typedef struct {
   int ld_aux;
   float p_drop;
   uint32_t seed;
-  int block_n; /* 0 = auto, else 128 or 256 */
+  int block_n;  /* 0 = auto, else 128 or 256 */
+  int cta_pair; /* 0 = auto, 1 = single-CTA tiles (128 x block_n), 2 = CTA-pair tiles (256 x 256, cta_group::2) */
 } mvptr_gemm_args;
 
 int mvptr_gemm(const mvptr_gemm_args* args, void* stream);

@@ -29,7 +29,7 @@ class GemmArgs(ctypes.Structure):
         ("bias", ctypes.c_void_p), ("bias_is_bf16", ctypes.c_int),
         ("pre_act", ctypes.c_void_p), ("act", ctypes.c_int),
         ("gelu_grad_of", ctypes.c_void_p), ("residual", ctypes.c_void_p), ("ld_aux", ctypes.c_int),
-        ("p_drop", ctypes.c_float), ("seed", ctypes.c_uint32), ("block_n", ctypes.c_int),
+        ("p_drop", ctypes.c_float), ("seed", ctypes.c_uint32), ("block_n", ctypes.c_int), ("cta_pair", ctypes.c_int),
     ]
 
 
@@ -127,14 +127,17 @@ def profile_enable(on):
     lib().mvptr_profile_enable(int(bool(on)))
 
 
-def profile_collect(cap=100000):
-    """{kernel name: {launches, ms, work}} of the launches recorded since profile_enable(True)."""
+def profile_collect(cap=100000, raw=False):
+    """{kernel name: {launches, ms, work}} of the launches recorded since profile_enable(True)
+    (raw=True: the list of (name, work, ms) per launch)."""
     L = lib()
     names = (ctypes.c_char_p * cap)()
     work = (ctypes.c_double * cap)()
     ms = (ctypes.c_float * cap)()
     L.mvptr_profile_collect.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
     n = L.mvptr_profile_collect(names, work, ms, cap)
+    if raw:
+        return [(names[i].decode(), work[i], ms[i]) for i in range(n)]
     out = {}
     for i in range(n):
         d = out.setdefault(names[i].decode(), {"launches": 0, "ms": 0.0, "work": 0.0})
@@ -156,7 +159,7 @@ def call(name, *args):
             conv.append(a.data_ptr())
         else:
             conv.append(a)
-    conv.append(torch.cuda.current_stream().cuda_stream)
+    conv.append(_raw_stream())
     if PROFILER is not None:
         box = []
         PROFILER.wrap(name, 0.0, lambda: box.append(getattr(L, name)(*conv)))
@@ -170,7 +173,7 @@ def call(name, *args):
 def layer_call(name, args, n_kernels):
     """mvptr_layer_fwd / mvptr_layer_bwd with a filled LayerArgs."""
     L = lib()
-    stream = torch.cuda.current_stream().cuda_stream
+    stream = _raw_stream()
     if PROFILER is not None:
         box = []
         PROFILER.wrap(name, 0.0, lambda: box.append(getattr(L, name)(ctypes.byref(args), stream)))
@@ -205,8 +208,13 @@ def check(rc, what):
         raise MvptrError(f"{what} failed (rc={rc}): {lib().mvptr_last_error().decode()}")
 
 
+def _raw_stream():
+    """Current CUDA stream handle of the current device (the fast C accessor, ~0.3 us)."""
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
+
+
 def stream_ptr():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(_raw_stream())
 
 
 def ptr(t):
@@ -218,7 +226,7 @@ ACT = {None: 0, "none": 0, "gelu": 1, "tanh": 2}
 
 def gemm(A, B, D, M, N, K, *, lda, ldb, ldd, a_mn=False, b_mn=False, accumulate=False, split_k=1, alpha=1.0,
          bias=None, pre_act=None, act=None, gelu_grad_of=None, residual=None, ld_aux=0, p_drop=0.0, seed=0,
-         block_n=0):
+         block_n=0, cta_pair=0):
     """D[M,N] (+)= epilogue(alpha * A . B^T); see include/mvptr_b200.h."""
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
     assert D.dtype in (torch.bfloat16, torch.float32)
@@ -238,6 +246,7 @@ def gemm(A, B, D, M, N, K, *, lda, ldb, ldd, a_mn=False, b_mn=False, accumulate=
             setattr(g, name, t.data_ptr())
     g.act = ACT[act]
     g.ld_aux, g.p_drop, g.seed, g.block_n = ld_aux, float(p_drop), int(seed) & 0xFFFFFFFF, block_n
+    g.cta_pair = cta_pair
     if PROFILER is not None:
         kind = "mvptr_gemm[%s%s]" % ("mn" if a_mn else "k", "mn" if b_mn else "k")
         box = []

@@ -125,4 +125,6 @@ class ParamArena:
     def zero_grad(self):
         if self.grad is not None:
             self.grad.zero_()
-            self.bind_grads()
+            first = next(iter(self.params.values()))
+            if first.grad is None or first.grad.data_ptr() != self.grad.data_ptr() + 4 * self.offsets[next(iter(self.params))][0]:
+                self.bind_grads()  # only when something (e.g. zero_grad(set_to_none)) dropped the views

@@ -96,6 +96,52 @@ __device__ __forceinline__ void tma_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
+// ---------------- cluster / CTA-pair helpers ----------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(bar),
+      "r"(cta)
+      : "memory");
+}
+// CTA-pair TMA load: data lands in THIS CTA's smem, the transaction bytes are credited to the
+// LEADER CTA's mbarrier (peer bit of the barrier address cleared, as CUTLASS SM100_TMA_2SM_LOAD)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // ---------------- tcgen05 ----------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -144,22 +190,32 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool 
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <int BN>
+template <int BN, int CTAS = 1>
 struct SmemLayout {
-  static constexpr int kABytes = BM * BK * 2;   // 16 KB
-  static constexpr int kBBytes = BN * BK * 2;   // 16/32 KB
+  static constexpr int kABytes = BM * BK * 2;            // 16 KB (per CTA)
+  static constexpr int kBBytes = (BN / CTAS) * BK * 2;   // a CTA pair splits the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (kStageBytes == 48 * 1024) ? 4 : 6;
   static constexpr int kOutBytes = kEpiWarps * kSlabBytes;  // one TMA-store slab per epilogue warp
   static constexpr int kBarBytes = 256;
   static constexpr int kTotal = kStages * kStageBytes + kOutBytes + kBarBytes + 1024;  // + alignment slack
 };
 
-template <int BN, bool A_MN, bool B_MN, bool F32OUT>
+// CTAS == 2: a CTA pair (cluster 2x1) computes a 256 x BN tile with cta_group::2 MMAs issued by the
+// leader CTA; each CTA stages its own 128 A rows and HALF of the B tile, so the bytes per FLOP that
+// every SM pulls through L2 drop by a third and six 32 KB stages fit: the 4-stage single-CTA ring
+// could not cover the TMA latency at K=768 (tensor pipe 63 % active in ncu, profiles/).
+template <int BN, bool A_MN, bool B_MN, bool F32OUT, int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const Params p) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, CTAS>;
+  constexpr bool kPair = CTAS == 2;
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int cta_stride = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;  // tiles advance per cluster
+  const int cta_first = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  constexpr int kTileM = BM * CTAS;
   constexpr int kStages = L::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -187,18 +243,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(tfull_bar + 8 * i, 1);
-      mbar_init(tempty_bar + 8 * i, kEpiWarps);
+      mbar_init(tempty_bar + 8 * i, kEpiWarps * CTAS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)(kAccStages * BN))
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)(kAccStages * BN))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)(kAccStages * BN))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();  // peer barriers initialised before any remote arrive / TMA credit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -209,29 +273,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      constexpr int kBRows = BN / CTAS;  // B rows (K-major) / columns (MN-major) staged by this CTA
+      for (int t = cta_first; t < p.num_tiles; t += cta_stride) {
         const int split = t / tiles_mn;
         const int mn = t - split * tiles_mn;
         const int m_blk = mn / p.n_tiles, n_blk = mn - m_blk * p.n_tiles;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int m0 = m_blk * kTileM + (int)cta_rank * BM;
+        const int n0 = n_blk * BN + (int)cta_rank * kBRows;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
           const uint32_t sb = sa + L::kABytes;
           const uint32_t fb = full_bar + 8 * stage;
-          mbar_expect_tx(fb, L::kStageBytes);
+          if (leader) mbar_expect_tx(fb, L::kStageBytes * CTAS);  // bytes of both CTAs land on the leader's barrier
+          auto load = [&](uint32_t dst, const CUtensorMap* map, int c0, int c1) {
+            if constexpr (kPair) tma_load_2d_pair(dst, map, fb, c0, c1);
+            else tma_load_2d(dst, map, fb, c0, c1);
+          };
           if constexpr (!A_MN) {
-            tma_load_2d(sa, &tmA, fb, kb * BK, m_blk * BM);
+            load(sa, &tmA, kb * BK, m0);
           } else {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * (BK * 128), &tmA, fb, m_blk * BM + c * 64, kb * BK);
+            for (int c = 0; c < BM / 64; ++c) load(sa + c * (BK * 128), &tmA, m0 + c * 64, kb * BK);
           }
           if constexpr (!B_MN) {
-            tma_load_2d(sb, &tmB, fb, kb * BK, n_blk * BN);
+            load(sb, &tmB, kb * BK, n0);
           } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * (BK * 128), &tmB, fb, n_blk * BN + c * 64, kb * BK);
+            for (int c = 0; c < kBRows / 64; ++c) load(sb + c * (BK * 128), &tmB, n0 + c * 64, kb * BK);
           }
           if (++stage == kStages) {
             stage = 0;
@@ -241,9 +312,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer =======================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN, A_MN, B_MN);
+    // ======================= MMA issuer (leader CTA of a pair only) =======================
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc(kTileM, BN, A_MN, B_MN);
       // K-major: 8-row groups 1024 B apart (SBO); MN-major: 8 k-rows per 1024 B (SBO),
       // 64-wide MN chunks BK*128 B apart (LBO).
       constexpr uint32_t a_lbo = A_MN ? BK * 128 : 16, a_sbo = 1024, a_kstep = A_MN ? UMMA_K * 128 : UMMA_K * 2;
@@ -251,7 +322,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++local) {
+      for (int t = cta_first; t < p.num_tiles; t += cta_stride, ++local) {
         const int split = t / tiles_mn;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -269,15 +340,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t da = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo);
             const uint64_t db = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo);
-            tc_mma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (kPair) tc_mma_bf16_pair(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else tc_mma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(empty_bar + 8 * stage);  // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if constexpr (kPair) tc_commit_pair(empty_bar + 8 * stage);
+          else tc_commit(empty_bar + 8 * stage);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        tc_commit(tfull_bar + 8 * as);  // accumulator ready for the epilogue
+        // accumulator ready for the epilogue warps (of both CTAs)
+        if constexpr (kPair) tc_commit_pair(tfull_bar + 8 * as);
+        else tc_commit(tfull_bar + 8 * as);
       }
     }
   } else if (warp >= 4) {
@@ -291,13 +367,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const bool bias_vec = p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
     int local = 0;
     bool store_pending = false;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++local) {
+    for (int t = cta_first; t < p.num_tiles; t += cta_stride, ++local) {
       const int split = t / tiles_mn;
       const int mn = t - split * tiles_mn;
       const int m_blk = mn / p.n_tiles, n_blk = mn - m_blk * p.n_tiles;
       const int as = local & 1;
       const uint32_t aph = (local >> 1) & 1;
-      const int m = m_blk * BM + q * 32 + lane;
+      const int m_base = m_blk * kTileM + (int)cta_rank * BM;
+      const int m = m_base + q * 32 + lane;
       const bool row_ok = m < p.M;
       const bool lead = (split == 0);  // bias / residual are added by the first K-split only
       const int n_base = n_blk * BN + hf * kHalf;
@@ -415,9 +492,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (lane == 0) {
             const int ng0 = n0 - h * 32;
             if (p.accumulate)
-              tma_reduce_add_2d(&tmD, smem_u32(slab), ng0, m_blk * BM + q * 32);
+              tma_reduce_add_2d(&tmD, smem_u32(slab), ng0, m_base + q * 32);
             else
-              tma_store_2d(&tmD, smem_u32(slab), ng0, m_blk * BM + q * 32);
+              tma_store_2d(&tmD, smem_u32(slab), ng0, m_base + q * 32);
             tma_commit();
           }
           store_pending = true;
@@ -426,18 +503,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // all TMEM reads of this accumulator stage are complete (wait::ld above)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar + 8 * as);
+      if (lane == 0) {
+        if (kPair && !leader) mbar_arrive_remote(tempty_bar + 8 * as, 0);  // the leader's MMA warp owns the pair's TMEM
+        else mbar_arrive(tempty_bar + 8 * as);
+      }
     }
     if (lane == 0) tma_wait_read<0>();
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();  // the peer's smem / TMEM stay alive until both CTAs are done
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)(kAccStages * BN))
-                 : "memory");
+    if constexpr (kPair)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"((uint32_t)(kAccStages * BN))
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"((uint32_t)(kAccStages * BN))
+                   : "memory");
   }
 }
 
@@ -473,36 +559,52 @@ static int make_map(CUtensorMap* map, const void* base, bool f32, uint64_t inner
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool F32OUT>
+template <int BN, bool A_MN, bool B_MN, bool F32OUT, int CTAS>
 static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, const Params& p,
                   cudaStream_t stream) {
-  auto kern = gemm_kernel<BN, A_MN, B_MN, F32OUT>;
-  constexpr int smem = SmemLayout<BN>::kTotal;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, F32OUT, CTAS>;
+  constexpr int smem = SmemLayout<BN, CTAS>::kTotal;
   static bool configured = false;  // per template instantiation
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) MVPTR_FAIL(MVPTR_ERR_CUDA, "gemm smem attr: %s", cudaGetErrorString(e));
     configured = true;
   }
-  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-  kern<<<grid, kThreads, smem, stream>>>(a, b, d, p);
-  MVPTR_CHECK_LAUNCH("gemm_kernel");
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  if (CTAS == 2) {
+    const int clusters = p.num_tiles < kNumSMs / 2 ? p.num_tiles : kNumSMs / 2;
+    cfg.gridDim = dim3(2 * clusters);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3(p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs);
+  }
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, b, d, p);
+  if (e != cudaSuccess) MVPTR_FAIL(MVPTR_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
   return 0;
 }
 
-template <int BN>
+template <int BN, int CTAS>
 static int dispatch(const mvptr_gemm_args* g, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d,
                     const Params& p, cudaStream_t s) {
   const int key = (g->a_mn ? 4 : 0) | (g->b_mn ? 2 : 0) | (g->d_is_f32 ? 1 : 0);
   switch (key) {
-    case 0: return launch<BN, false, false, false>(a, b, d, p, s);
-    case 1: return launch<BN, false, false, true>(a, b, d, p, s);
-    case 2: return launch<BN, false, true, false>(a, b, d, p, s);
-    case 3: return launch<BN, false, true, true>(a, b, d, p, s);
-    case 4: return launch<BN, true, false, false>(a, b, d, p, s);
-    case 5: return launch<BN, true, false, true>(a, b, d, p, s);
-    case 6: return launch<BN, true, true, false>(a, b, d, p, s);
-    default: return launch<BN, true, true, true>(a, b, d, p, s);
+    case 0: return launch<BN, false, false, false, CTAS>(a, b, d, p, s);
+    case 1: return launch<BN, false, false, true, CTAS>(a, b, d, p, s);
+    case 2: return launch<BN, false, true, false, CTAS>(a, b, d, p, s);
+    case 3: return launch<BN, false, true, true, CTAS>(a, b, d, p, s);
+    case 4: return launch<BN, true, false, false, CTAS>(a, b, d, p, s);
+    case 5: return launch<BN, true, false, true, CTAS>(a, b, d, p, s);
+    case 6: return launch<BN, true, true, false, CTAS>(a, b, d, p, s);
+    default: return launch<BN, true, true, true, CTAS>(a, b, d, p, s);
   }
 }
 
@@ -530,9 +632,18 @@ extern "C" int mvptr_gemm(const mvptr_gemm_args* g, void* stream_) {
   if (bn == 0) bn = (g->N <= 128) ? 128 : 256;
   if (bn != 128 && bn != 256) MVPTR_FAIL(MVPTR_ERR_ARG, "gemm: block_n must be 128 or 256");
 
+  // cta_pair: 0 auto, 1 off, 2 on.  Auto (measured, profiles/bench_gemm_pair_r1.txt): CTA pairs win
+  // 8-13 % when the mainloop is long (K >= 1536) or an operand is MN-major (dgrad / wgrad); the short
+  // K-major K=768 forward GEMMs are a wash or slightly slower, so they keep single-CTA tiles.
+  int ctas = g->cta_pair == 1 ? 1
+           : g->cta_pair == 2 ? 2
+           : (bn == 256 && g->M > BM && (g->K >= 1536 || g->a_mn || g->b_mn)) ? 2 : 1;
+  if (ctas == 2 && bn != 256) MVPTR_FAIL(MVPTR_ERR_ARG, "gemm: CTA pairs need block_n 256");
+  const int tile_m = BM * ctas;
+
   Params p;
   p.M = g->M; p.N = g->N; p.K = g->K;
-  p.m_tiles = (g->M + BM - 1) / BM;
+  p.m_tiles = (g->M + tile_m - 1) / tile_m;
   p.n_tiles = (g->N + bn - 1) / bn;
   p.kb_total = (g->K + BK - 1) / BK;
   if (split > p.kb_total) split = p.kb_total;
@@ -558,7 +669,7 @@ extern "C" int mvptr_gemm(const mvptr_gemm_args* g, void* stream_) {
   if (!g->a_mn) rc = make_map(&ta, g->A, false, g->K, g->M, (uint64_t)g->lda * 2, BK, BM);
   else          rc = make_map(&ta, g->A, false, g->M, g->K, (uint64_t)g->lda * 2, 64, BK);
   if (rc) return rc;
-  if (!g->b_mn) rc = make_map(&tb, g->B, false, g->K, g->N, (uint64_t)g->ldb * 2, BK, bn);
+  if (!g->b_mn) rc = make_map(&tb, g->B, false, g->K, g->N, (uint64_t)g->ldb * 2, BK, bn / ctas);
   else          rc = make_map(&tb, g->B, false, g->N, g->K, (uint64_t)g->ldb * 2, 64, BK);
   if (rc) return rc;
   if (g->d_is_f32) rc = make_map(&td, g->D, true, g->N, g->M, (uint64_t)g->ldd * 4, 32, 32);
@@ -567,5 +678,6 @@ extern "C" int mvptr_gemm(const mvptr_gemm_args* g, void* stream_) {
 
   static const char* kNames[4] = {"gemm[k,k]", "gemm[k,mn]", "gemm[mn,k]", "gemm[mn,mn]"};
   MVPTR_PROF(kNames[(g->a_mn ? 2 : 0) | (g->b_mn ? 1 : 0)], 2.0 * g->M * g->N * g->K, stream);
-  return bn == 256 ? dispatch<256>(g, ta, tb, td, p, stream) : dispatch<128>(g, ta, tb, td, p, stream);
+  if (ctas == 2) return dispatch<256, 2>(g, ta, tb, td, p, stream);
+  return bn == 256 ? dispatch<256, 1>(g, ta, tb, td, p, stream) : dispatch<128, 1>(g, ta, tb, td, p, stream);
 }

@@ -701,7 +701,7 @@ extern "C" int mvptr_gelu_bwd_colsum(const void* dy, const void* pre, void* dx, 
   MVPTR_PROF("gelu_bwd_colsum", 6.0*M*N, stream);
   if (M <= 0 || N <= 0) return 0;
   if (N & 7) MVPTR_FAIL(MVPTR_ERR_ARG, "gelu_bwd_colsum: N must be a multiple of 8");
-  const int rpb = 256;
+  const int rpb = 128;
   dim3 grid((N + 255) / 256, (M + rpb - 1) / rpb);
   gelu_bwd_colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, (const bf16*)pre, (bf16*)dx, dbias, M,
                                                                  N, rpb);
@@ -736,7 +736,7 @@ extern "C" int mvptr_ln_bwd(const void* dy, int dy_rows_per_batch, long long dy_
 #undef LN_BWD_LAUNCH
   MVPTR_CHECK_LAUNCH("ln_bwd_dx");
   {
-    const int rpb = 256;
+    const int rpb = 64;  // many small blocks: the pass is latency bound, it wants loads of many rows in flight
     dim3 g2((H + 255) / 256, (rows + rpb - 1) / rpb);
     ln_bwd_colsum_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(
         (const bf16*)dy, dm, (const bf16*)x, mean, rstd, (const bf16*)(dx_drop ? dx_drop : dx), dgamma, dbeta, dbias,

@@ -22,6 +22,7 @@ def run(name, M, N, K, reps=5, a_mn=False, b_mn=False, f32=False, **epi):
     if epi.get("drop"): kw["p_drop"] = 0.1; kw["seed"] = 5
     if epi.get("split"): kw["split_k"] = epi["split"]; kw["accumulate"] = True
     if epi.get("bn"): kw["block_n"] = epi["bn"]
+    kw["cta_pair"] = epi.get("pair", 0)
     ts = []
     for i in range(reps + 2):
         flush.zero_()
@@ -36,6 +37,15 @@ def run(name, M, N, K, reps=5, a_mn=False, b_mn=False, f32=False, **epi):
 
 
 M = 46080
+print("== single-CTA vs CTA-pair tiles ==")
+for nm, (m, n, k), kw in (("ffn1 bias", (M, 3072, 768), dict(bias=True)), ("ffn2 bias", (M, 768, 3072), dict(bias=True)),
+                          ("o-proj bias", (M, 768, 768), dict(bias=True)), ("qkv bias", (M, 2304, 768), dict(bias=True)),
+                          ("txt ffn1 bias", (10240, 3072, 768), dict(bias=True)), ("txt o-proj", (10240, 768, 768), dict(bias=True)),
+                          ("dgrad N3072 K768", (M, 3072, 768), dict(b_mn=True)), ("dgrad N768 K3072 +res", (M, 768, 3072), dict(b_mn=True, res=True)),
+                          ("wgrad 768x3072", (768, 3072, M), dict(a_mn=True, b_mn=True, f32=True, split=4)),
+                          ("wgrad 2304x768", (2304, 768, M), dict(a_mn=True, b_mn=True, f32=True, split=5))):
+    run(nm + " [1cta]", m, n, k, pair=1, **kw)
+    run(nm + " [pair]", m, n, k, pair=2, **kw)
 print("== epilogue ablation, K=768, N=768 ==")
 run("plain store", M, 768, 768)
 run("plain store bn128", M, 768, 768, bn=128)

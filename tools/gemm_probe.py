@@ -74,7 +74,8 @@ def run_case(name):
         ref = ref + 1.0
     p_drop = c.get("p_drop", 0.0)
     _lib.gemm(A_st, B_st, D, M, N, K, lda=lda, ldb=ldb, ldd=npitch, a_mn=a_mn, b_mn=b_mn,
-              accumulate=c.get("acc", False), split_k=c.get("split", 1), block_n=c["bn"], p_drop=p_drop, seed=1234, **kw)
+              accumulate=c.get("acc", False), split_k=c.get("split", 1), block_n=c["bn"], p_drop=p_drop, seed=1234,
+              cta_pair=int(os.environ.get("MVPTR_CTA_PAIR", "0")), **kw)
     torch.cuda.synchronize()
     out = D[:, :N].float()
     info = {"case": name}
