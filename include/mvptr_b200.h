@@ -156,9 +156,10 @@ int mvptr_add_cast(const float* a, const void* b, void* d, size_t n, void* strea
  * transpose_for_scores modeling_bert.py:299-303.  lse [B,nh,L] (nullable) is saved for backward. */
 int mvptr_attn_fwd(const void* qkv, int ld_qkv, const float* maskadd, void* ctx, int ld_ctx, float* lse, int B, int L,
                    int nh, int H, float p_drop, uint32_t seed, void* stream);
+/* dbias (nullable, fp32 [3H], +=): column sums of dqkv, i.e. the gradient of the fused QKV bias */
 int mvptr_attn_bwd(const void* qkv, int ld_qkv, const float* maskadd, const void* ctx, const void* dctx, int ld_ctx,
-                   const float* lse, void* dqkv, int B, int L, int nh, int H, float p_drop, uint32_t seed,
-                   void* stream);
+                   const float* lse, void* dqkv, float* dbias, int B, int L, int nh, int H, float p_drop,
+                   uint32_t seed, void* stream);
 
 /* ---- losses -------------------------------------------------------------------------
  * CrossEntropyLoss(ignore_index=-1) over fp32 logits [n,V]: modeling_vlbert.py:1229,1235,1249.

@@ -72,7 +72,7 @@ SIGNATURES = {
     "mvptr_cast_f32_bf16": "ppzp",
     "mvptr_add_cast": "pppzp",
     "mvptr_attn_fwd": "pippip" + "iiii" + "fup",
-    "mvptr_attn_bwd": "pipppipp" + "iiii" + "fup",
+    "mvptr_attn_bwd": "pipppippp" + "iiii" + "fup",
     "mvptr_ce_fwd": "pipiiipppp",
     "mvptr_ce_bwd": "pipiii" + "ppp" + "pip",
     "mvptr_l2norm_fwd": "ppppiip",

@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const FwdParams p) {
       if (q1 < L) l[q1] = (mx1 + log2f(sum1)) / kLog2e;
     }
     const bool drop = p.keep_thr != 0xffffffffu;
-    const uint32_t rbase0 = (((uint32_t)b * p.nh + h) * L + q0) * L, rbase1 = (((uint32_t)b * p.nh + h) * L + q1) * L;
+    const uint32_t Lp = (uint32_t)(L + 1) & ~1u;  // even row pitch of the dropout index: (k, k+1) share one hash
+    const uint32_t rbase0 = (((uint32_t)b * p.nh + h) * L + q0) * Lp, rbase1 = (((uint32_t)b * p.nh + h) * L + q1) * Lp;
     float o[8][4];
 #pragma unroll
     for (int d = 0; d < 8; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
@@ -192,10 +193,13 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const FwdParams p) {
         pv[4 * u + 3] = s[j][3] * inv1;
         if (drop) {
           const uint32_t k = j * 8 + 2 * t;
-          pv[4 * u + 0] = dropout_keep(p.seed, rbase0 + k, p.keep_thr) ? pv[4 * u + 0] * p.inv_keep : 0.f;
-          pv[4 * u + 1] = dropout_keep(p.seed, rbase0 + k + 1, p.keep_thr) ? pv[4 * u + 1] * p.inv_keep : 0.f;
-          pv[4 * u + 2] = dropout_keep(p.seed, rbase1 + k, p.keep_thr) ? pv[4 * u + 2] * p.inv_keep : 0.f;
-          pv[4 * u + 3] = dropout_keep(p.seed, rbase1 + k + 1, p.keep_thr) ? pv[4 * u + 3] * p.inv_keep : 0.f;
+          bool k0, k1, k2, k3;
+          dropout_pair(p.seed, rbase0 + k, p.keep_thr, k0, k1);
+          dropout_pair(p.seed, rbase1 + k, p.keep_thr, k2, k3);
+          pv[4 * u + 0] = k0 ? pv[4 * u + 0] * p.inv_keep : 0.f;
+          pv[4 * u + 1] = k1 ? pv[4 * u + 1] * p.inv_keep : 0.f;
+          pv[4 * u + 2] = k2 ? pv[4 * u + 2] * p.inv_keep : 0.f;
+          pv[4 * u + 3] = k3 ? pv[4 * u + 3] * p.inv_keep : 0.f;
         }
       }
       const uint32_t pa[4] = {pack2(pv[0], pv[1]), pack2(pv[2], pv[3]), pack2(pv[4], pv[5]), pack2(pv[6], pv[7])};
@@ -230,6 +234,7 @@ struct BwdParams {
   int ld_ctx;
   const float* lse;  // [B, nh, L]
   bf16* dqkv;        // [B*L, ld_qkv]
+  float* dbias;      // [3H] fp32 (+=): column sums of dqkv = gradient of the fused QKV bias (nullable)
   int B, L, nh, H;
   float scale;
   uint32_t keep_thr;
@@ -249,6 +254,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const BwdParams p) {
   float* Ms = reinterpret_cast<float*>(Stg + 8 * 16 * LDS);  // additive mask, log2 domain
   float* Ls = Ms + LP;                                       // lse, log2 domain (+inf for padded queries)
   float* Ds = Ls + LP;                                       // rowsum(dO * O)
+  float* Cs = Ds + LP;                                       // [3][64] column sums of dQ | dK | dV
   const int b = blockIdx.y, h = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int L = p.L;
@@ -263,6 +269,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const BwdParams p) {
     Ms[i] = i < L ? p.maskadd[row0 + i] * kLog2e : -INFINITY;
     Ls[i] = i < L ? lse[i] * kLog2e : INFINITY;
   }
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) Cs[i] = 0.f;
   cp_async_wait_all();
   __syncthreads();
   // D[q] = sum_d dO[q,d] * O[q,d]
@@ -288,7 +295,25 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const BwdParams p) {
   const float sc = p.scale * kLog2e;
   const bool drop = p.keep_thr != 0xffffffffu;
   const uint32_t hb = ((uint32_t)b * p.nh + h) * L;
+  const uint32_t Lp = (uint32_t)(L + 1) & ~1u;  // same even pitch as the forward's dropout index
   bf16* stg = Stg + warp * 16 * LDS;
+
+  // column sums of a 16 x 64 accumulator tile (rows beyond L are exactly zero) -> Cs[which][0..64)
+  auto colsum_tile = [&](const float (&acc)[8][4], float f, int which) {
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      float s0 = (acc[d][0] + acc[d][2]) * f, s1 = (acc[d][1] + acc[d][3]) * f;
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      }
+      if (g == 0) {
+        atomicAdd(Cs + which * D + d * 8 + 2 * t, s0);
+        atomicAdd(Cs + which * D + d * 8 + 2 * t + 1, s1);
+      }
+    }
+  };
 
   // ---------------- pass 1: dQ (warp owns 16 queries, loops over key pairs) ----------------
   for (int qt = warp; qt < n_tiles; qt += nwarps) {
@@ -314,10 +339,13 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const BwdParams p) {
                        exp2f(s[u][3] * sc + m1 - l1)};
         float dpp[4] = {dp[u][0], dp[u][1], dp[u][2], dp[u][3]};
         if (drop) {
-          dpp[0] = dropout_keep(p.seed, (hb + q0) * L + k, p.keep_thr) ? dpp[0] * p.inv_keep : 0.f;
-          dpp[1] = dropout_keep(p.seed, (hb + q0) * L + k + 1, p.keep_thr) ? dpp[1] * p.inv_keep : 0.f;
-          dpp[2] = dropout_keep(p.seed, (hb + q1) * L + k, p.keep_thr) ? dpp[2] * p.inv_keep : 0.f;
-          dpp[3] = dropout_keep(p.seed, (hb + q1) * L + k + 1, p.keep_thr) ? dpp[3] * p.inv_keep : 0.f;
+          bool k0, k1, k2, k3;
+          dropout_pair(p.seed, (hb + q0) * Lp + k, p.keep_thr, k0, k1);
+          dropout_pair(p.seed, (hb + q1) * Lp + k, p.keep_thr, k2, k3);
+          dpp[0] = k0 ? dpp[0] * p.inv_keep : 0.f;
+          dpp[1] = k1 ? dpp[1] * p.inv_keep : 0.f;
+          dpp[2] = k2 ? dpp[2] * p.inv_keep : 0.f;
+          dpp[3] = k3 ? dpp[3] * p.inv_keep : 0.f;
         }
         ds[4 * u + 0] = pr[0] * (dpp[0] - d0);
         ds[4 * u + 1] = pr[1] * (dpp[1] - d0);
@@ -327,6 +355,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const BwdParams p) {
       const uint32_t pa[4] = {pack2(ds[0], ds[1]), pack2(ds[2], ds[3]), pack2(ds[4], ds[5]), pack2(ds[6], ds[7])};
       mma_p_rows(dq, pa, Ks, kp * 16, lane);
     }
+    if (p.dbias) colsum_tile(dq, p.scale, 0);
     __syncwarp();
 #pragma unroll
     for (int d = 0; d < 8; ++d) {
@@ -372,10 +401,10 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const BwdParams p) {
         float dpp[4] = {dp[u][0], dp[u][1], dp[u][2], dp[u][3]};
         float pd[4] = {pr[0], pr[1], pr[2], pr[3]};
         if (drop) {
-          const bool kp0 = dropout_keep(p.seed, (hb + q) * L + k0, p.keep_thr);
-          const bool kp1 = dropout_keep(p.seed, (hb + q + 1) * L + k0, p.keep_thr);
-          const bool kp2 = dropout_keep(p.seed, (hb + q) * L + k1, p.keep_thr);
-          const bool kp3 = dropout_keep(p.seed, (hb + q + 1) * L + k1, p.keep_thr);
+          const bool kp0 = dropout_keep(p.seed, (hb + q) * Lp + k0, p.keep_thr);
+          const bool kp1 = dropout_keep(p.seed, (hb + q + 1) * Lp + k0, p.keep_thr);
+          const bool kp2 = dropout_keep(p.seed, (hb + q) * Lp + k1, p.keep_thr);
+          const bool kp3 = dropout_keep(p.seed, (hb + q + 1) * Lp + k1, p.keep_thr);
           dpp[0] = kp0 ? dpp[0] * p.inv_keep : 0.f; pd[0] = kp0 ? pd[0] * p.inv_keep : 0.f;
           dpp[1] = kp1 ? dpp[1] * p.inv_keep : 0.f; pd[1] = kp1 ? pd[1] * p.inv_keep : 0.f;
           dpp[2] = kp2 ? dpp[2] * p.inv_keep : 0.f; pd[2] = kp2 ? pd[2] * p.inv_keep : 0.f;
@@ -391,6 +420,10 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const BwdParams p) {
       const uint32_t sa[4] = {pack2(ds[0], ds[1]), pack2(ds[2], ds[3]), pack2(ds[4], ds[5]), pack2(ds[6], ds[7])};
       mma_p_rows(dv, pa, dOs, qp * 16, lane);
       mma_p_rows(dk, sa, Qs, qp * 16, lane);
+    }
+    if (p.dbias) {
+      colsum_tile(dk, p.scale, 1);
+      colsum_tile(dv, 1.f, 2);
     }
     // dK then dV through the per-warp staging tile
 #pragma unroll
@@ -414,6 +447,11 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const BwdParams p) {
       }
     }
   }
+  if (p.dbias) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * D; i += blockDim.x)
+      atomicAdd(p.dbias + (i / D) * p.H + h * D + (i % D), Cs[i]);
+  }
 }
 
 template <int NT>
@@ -436,7 +474,7 @@ static int launch_fwd(const FwdParams& p, cudaStream_t s) {
 template <int NT>
 static int launch_bwd(const BwdParams& p, cudaStream_t s) {
   constexpr int LP = NT * 8;
-  constexpr int smem = 4 * LP * LDS * 2 + 8 * 16 * LDS * 2 + 3 * LP * 4;
+  constexpr int smem = 4 * LP * LDS * 2 + 8 * 16 * LDS * 2 + 3 * LP * 4 + 3 * D * 4;
   auto kern = attn_bwd_kernel<NT>;
   static bool configured = false;
   if (!configured) {
@@ -479,12 +517,12 @@ extern "C" int mvptr_attn_fwd(const void* qkv, int ld_qkv, const float* maskadd,
 }
 
 extern "C" int mvptr_attn_bwd(const void* qkv, int ld_qkv, const float* maskadd, const void* ctx, const void* dctx,
-                              int ld_ctx, const float* lse, void* dqkv, int B, int L, int nh, int H, float p_drop,
-                              uint32_t seed, void* stream) {
+                              int ld_ctx, const float* lse, void* dqkv, float* dbias, int B, int L, int nh, int H,
+                              float p_drop, uint32_t seed, void* stream) {
   MVPTR_PROF("attn_bwd", 10.0*B*nh*L*L*64, stream);
   if (int rc = attn_check(B, L, nh, H, ld_qkv, ld_ctx)) return rc;
   attn::BwdParams p{(const bf16*)qkv, ld_qkv, maskadd, (const bf16*)ctx, (const bf16*)dctx, ld_ctx, lse, (bf16*)dqkv,
-                    B, L, nh, H, 0.125f, keep_threshold(p_drop), p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f, seed};
+                    dbias, B, L, nh, H, 0.125f, keep_threshold(p_drop), p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f, seed};
   cudaStream_t s = (cudaStream_t)stream;
   if (L <= 64) return attn::launch_bwd<8>(p, s);
   if (L <= 96) return attn::launch_bwd<12>(p, s);

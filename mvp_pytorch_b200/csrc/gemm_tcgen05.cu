@@ -453,9 +453,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
         }
         if (p.use_dropout) {
-          const uint32_t base = (uint32_t)m * (uint32_t)p.N + (uint32_t)n0;
+          const uint32_t base = (uint32_t)m * (uint32_t)p.N + (uint32_t)n0;  // multiple of 8 when N % 8 == 0
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = dropout_keep(p.seed, base + j, p.keep_thr) ? v[j] * p.inv_keep : 0.f;
+          for (int u = 0; u < 4; ++u) dropout8(v + u * 8, p.seed, base + u * 8, p.keep_thr, p.inv_keep);
         }
         if (p.residual != nullptr && row_ok && lead) {
 #pragma unroll

@@ -110,9 +110,9 @@ extern "C" int mvptr_layer_bwd(const mvptr_layer_args* a, void* stream) {
     TRY(mvptr_gemm(&g, s));
   }
   // ---- attention
-  TRY(mvptr_attn_bwd(a->qkv, 3 * H, a->maskadd, a->att, a->datt, H, a->lse, a->dqkv, a->B, a->L, a->nh, H, a->p_attn,
-                     a->seed_attn, s));
-  TRY(mvptr_colsum(a->dqkv, 3 * H, a->g_b_qkv, M, 3 * H, s));
+  // also accumulates the fused QKV bias gradient (column sums of dqkv) -- no separate pass over dqkv
+  TRY(mvptr_attn_bwd(a->qkv, 3 * H, a->maskadd, a->att, a->datt, H, a->lse, a->dqkv, a->g_b_qkv, a->B, a->L, a->nh, H,
+                     a->p_attn, a->seed_attn, s));
   TRY(wgrad(a->dqkv, 3 * H, a->x, H, 3 * H, H, M, a->g_w_qkv, s));
   {  // dx = dqkv . W_qkv + dpre1 (residual branch)
     mvptr_gemm_args g = gemm_base(a->dqkv, 3 * H, a->w_qkv, H, a->dx, H, M, H, 3 * H);

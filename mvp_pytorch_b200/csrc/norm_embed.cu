@@ -92,11 +92,8 @@ embed_ln_fwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__
       unpack8(*reinterpret_cast<const bf16x8*>(gamma + ch * 8), g);
       unpack8(*reinterpret_cast<const bf16x8*>(beta + ch * 8), b2);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        o[j] = g[j] * ((x[c][j] - mean) * rstd) + b2[j];
-        if (keep_thr != 0xffffffffu)
-          o[j] = dropout_keep(seed, (uint32_t)r * (uint32_t)H + ch * 8 + j, keep_thr) ? o[j] * inv_keep : 0.f;
-      }
+      for (int j = 0; j < 8; ++j) o[j] = g[j] * ((x[c][j] - mean) * rstd) + b2[j];
+      if (keep_thr != 0xffffffffu) dropout8(o, seed, (uint32_t)r * (uint32_t)H + ch * 8, keep_thr, inv_keep);
       *reinterpret_cast<bf16x8*>(yo + ch * 8) = pack8(o);
     }
   }
@@ -121,11 +118,7 @@ ln_fwd_kernel(const bf16* __restrict__ x_in, const bf16* __restrict__ residual, 
     const int ch = lane + 32 * c;
     if (ch < nchunk) {
       unpack8(*reinterpret_cast<const bf16x8*>(x_in + (size_t)r * H + ch * 8), x[c]);
-      if (in_keep_thr != 0xffffffffu) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          x[c][j] = dropout_keep(in_seed, (uint32_t)r * (uint32_t)H + ch * 8 + j, in_keep_thr) ? x[c][j] * in_inv_keep : 0.f;
-      }
+      if (in_keep_thr != 0xffffffffu) dropout8(x[c], in_seed, (uint32_t)r * (uint32_t)H + ch * 8, in_keep_thr, in_inv_keep);
       if (residual) {
         float rr[8];
         unpack8(*reinterpret_cast<const bf16x8*>(residual + (size_t)r * H + ch * 8), rr);
@@ -155,11 +148,8 @@ ln_fwd_kernel(const bf16* __restrict__ x_in, const bf16* __restrict__ residual, 
       unpack8(*reinterpret_cast<const bf16x8*>(gamma + ch * 8), g);
       unpack8(*reinterpret_cast<const bf16x8*>(beta + ch * 8), b2);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        o[j] = g[j] * ((x[c][j] - mean) * rstd) + b2[j];
-        if (keep_thr != 0xffffffffu)
-          o[j] = dropout_keep(seed, (uint32_t)r * (uint32_t)H + ch * 8 + j, keep_thr) ? o[j] * inv_keep : 0.f;
-      }
+      for (int j = 0; j < 8; ++j) o[j] = g[j] * ((x[c][j] - mean) * rstd) + b2[j];
+      if (keep_thr != 0xffffffffu) dropout8(o, seed, (uint32_t)r * (uint32_t)H + ch * 8, keep_thr, inv_keep);
       *reinterpret_cast<bf16x8*>(yo + ch * 8) = pack8(o);
     }
   }
@@ -264,13 +254,14 @@ ln_bwd_dx_kernel(const bf16* __restrict__ dy, RowMap dymap, const bf16* __restri
                  const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const bf16* __restrict__ gamma,
                  bf16* __restrict__ dx, bf16* __restrict__ dx_drop, int rows, int H, uint32_t out_keep_thr,
                  float out_inv_keep, uint32_t out_seed, uint32_t in_keep_thr, float in_inv_keep, uint32_t in_seed) {
-  extern __shared__ float s_gam[];
   const int lane = threadIdx.x & 31;
   const int nchunk = H >> 3;
-  for (int i = threadIdx.x; i < H; i += blockDim.x) s_gam[i] = __bfloat162float(gamma[i]);
-  __syncthreads();
   const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (r >= rows) return;
+  bf16x8 pgam[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+    if (lane + 32 * c < nchunk) pgam[c] = *reinterpret_cast<const bf16x8*>(gamma + (lane + 32 * c) * 8);
   const float mean = mean_in[r], rstd = rstd_in[r];
   const bf16* dyr = dy + dymap.off(r, H);
   bf16x8 pg[NC], px[NC];
@@ -287,18 +278,17 @@ ln_bwd_dx_kernel(const bf16* __restrict__ dy, RowMap dymap, const bf16* __restri
   for (int c = 0; c < NC; ++c) {
     const int ch = lane + 32 * c;
     if (ch < nchunk) {
-      float g[8], xv[8];
+      float g[8], xv[8], gm[8];
       unpack8(pg[c], g);
       unpack8(px[c], xv);
+      unpack8(pgam[c], gm);
       if (out_keep_thr != 0xffffffffu) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          g[j] = dropout_keep(out_seed, (uint32_t)r * (uint32_t)H + ch * 8 + j, out_keep_thr) ? g[j] * out_inv_keep : 0.f;
+        dropout8(g, out_seed, (uint32_t)r * (uint32_t)H + ch * 8, out_keep_thr, out_inv_keep);
         pg[c] = pack8(g);
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float gg = g[j] * s_gam[ch * 8 + j];
+        const float gg = g[j] * gm[j];
         s1 += gg;
         s2 += gg * ((xv[j] - mean) * rstd);
       }
@@ -310,16 +300,15 @@ ln_bwd_dx_kernel(const bf16* __restrict__ dy, RowMap dymap, const bf16* __restri
   for (int c = 0; c < NC; ++c) {
     const int ch = lane + 32 * c;
     if (ch < nchunk) {
-      float g[8], xv[8], o[8];
+      float g[8], xv[8], o[8], gm[8];
       unpack8(pg[c], g);
       unpack8(px[c], xv);
+      unpack8(pgam[c], gm);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = rstd * (g[j] * s_gam[ch * 8 + j] - s1 - (xv[j] - mean) * rstd * s2);
+      for (int j = 0; j < 8; ++j) o[j] = rstd * (g[j] * gm[j] - s1 - (xv[j] - mean) * rstd * s2);
       if (dx) *reinterpret_cast<bf16x8*>(dx + (size_t)r * H + ch * 8) = pack8(o);
       if (dx_drop) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          o[j] = dropout_keep(in_seed, (uint32_t)r * (uint32_t)H + ch * 8 + j, in_keep_thr) ? o[j] * in_inv_keep : 0.f;
+        dropout8(o, in_seed, (uint32_t)r * (uint32_t)H + ch * 8, in_keep_thr, in_inv_keep);
         *reinterpret_cast<bf16x8*>(dx_drop + (size_t)r * H + ch * 8) = pack8(o);
       }
     }
@@ -722,7 +711,7 @@ extern "C" int mvptr_ln_bwd(const void* dy, int dy_rows_per_batch, long long dy_
   if (dbias && !dx && !dx_drop) MVPTR_FAIL(MVPTR_ERR_ARG, "ln_bwd: dbias needs dx or dx_drop to be written");
   const int grid = (rows + 3) / 4;
   const int nc = (H + 255) / 256;
-  const int smem = H * (int)sizeof(float);
+  const int smem = 0;
 #define LN_BWD_LAUNCH(NC)                                                                                          \
   ln_bwd_dx_kernel<NC><<<grid, 128, smem, (cudaStream_t)stream>>>(                                                 \
       (const bf16*)dy, dm, (const bf16*)x, mean, rstd, (const bf16*)gamma, (bf16*)dx, (bf16*)dx_drop, rows, H,      \

@@ -211,8 +211,8 @@ class EncoderFn(Function):
             la.datt = s0 + 2 * M * 5 * H
             la.dqkv = s0 + 2 * M * 6 * H
             la.dpre_g = s0 + 2 * M * 9 * H
-            _lib.layer_call("mvptr_layer_bwd", la, 13)
-            rt.launches += 13
+            _lib.layer_call("mvptr_layer_bwd", la, 14)
+            rt.launches += 14
             sync = getattr(rt, "grad_sync", None)
             if sync is not None and sync.enabled:  # this layer's gradients are final: reduce them now
                 offs = rt.arena.offsets
@@ -462,7 +462,9 @@ def decoder_logits(rt, t, wname, n_out, bias_name):
     n, H = t.shape
     a = rt.arena
     pitch = _pad8(n_out)
-    logits = torch.empty(n, pitch, device=t.device, dtype=F32)
+    # row count rounded up so that the data-dependent number of masked positions maps onto a few
+    # recurring allocation sizes (a fresh cudaMalloc inside a step costs tens of ms)
+    logits = torch.empty((n + 255) // 256 * 256, pitch, device=t.device, dtype=F32)[:n]
     rt.gemm(t, a.w(wname), logits, n, n_out, H, lda=H, ldb=H, ldd=pitch, bias=a.w_span(bias_name, n_out))
     return logits
 
@@ -500,7 +502,7 @@ class VocabCEFn(Function):
         t, labels, wname, n_out, bias_name, logits, lse, acc = ctx.s
         n = t.shape[0]
         pitch = logits.shape[1]
-        dlogits = torch.empty(n, pitch, device=t.device, dtype=BF16)
+        dlogits = torch.empty((n + 255) // 256 * 256, pitch, device=t.device, dtype=BF16)[:n]
         gs = g.reshape(1).to(F32).contiguous()
         rt.call("mvptr_ce_bwd", logits, pitch, labels, n, n_out, -1, lse, acc[1:2], gs, dlogits, pitch)
         dt = decoder_backward(rt, t, dlogits, wname, n_out, bias_name)

@@ -159,7 +159,9 @@ def test_attention_fwd_bwd(lib, L):
     dctx = rnd(B * L, H, seed=5)
     ref.backward(dctx.float())
     dqkv = torch.empty_like(qkv)
-    lib.call("mvptr_attn_bwd", qkv, 3 * H, maskadd, ctx, dctx, H, lse, dqkv, B, L, nh, H, 0.0, 0)
+    dbias = torch.zeros(3 * H, device="cuda")
+    lib.call("mvptr_attn_bwd", qkv, 3 * H, maskadd, ctx, dctx, H, lse, dqkv, dbias, B, L, nh, H, 0.0, 0)
+    assert_close(dbias, x.grad.sum(0), 2e-2, 0.3, "fused qkv bias grad")
     rel = ((dqkv.float() - x.grad).norm() / x.grad.norm()).item()
     assert rel < 2e-2, f"attn bwd rel l2 {rel}"
     assert_close(dqkv, x.grad, 3e-2, 3e-2, "attn bwd")
@@ -178,7 +180,7 @@ def test_attention_dropout_consistency(lib):
     p = torch.softmax(q @ k.transpose(-1, -2) / 8.0, -1)
     dctx = rnd(B * L, H, seed=2)
     dqkv = torch.empty_like(qkv)
-    lib.call("mvptr_attn_bwd", qkv, 3 * H, maskadd, ctx, dctx, H, lse, dqkv, B, L, nh, H, 0.3, 99)
+    lib.call("mvptr_attn_bwd", qkv, 3 * H, maskadd, ctx, dctx, H, lse, dqkv, None, B, L, nh, H, 0.3, 99)
     # dV = P_drop^T dO ; ctx = P_drop V  ->  <dV, V> == <dO, ctx> for every head (adjoint identity)
     dv = dqkv.float().view(B, L, 3, nh, 64)[:, :, 2]
     vv = qkv.float().view(B, L, 3, nh, 64)[:, :, 2]
