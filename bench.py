@@ -26,6 +26,11 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# grow allocator segments by virtual-memory mapping instead of cudaMalloc/cudaFree (which synchronise):
+# the number of masked-LM rows is data dependent, so buffer sizes vary a little from step to step
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+if not os.environ.get("MVPTR_KEEP_NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (the image default prints the NCCL version)
 
 import torch  # noqa: E402
 

@@ -298,20 +298,15 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const BwdParams p) {
   const uint32_t Lp = (uint32_t)(L + 1) & ~1u;  // same even pitch as the forward's dropout index
   bf16* stg = Stg + warp * 16 * LDS;
 
-  // column sums of a 16 x 64 accumulator tile (rows beyond L are exactly zero) -> Cs[which][0..64)
-  auto colsum_tile = [&](const float (&acc)[8][4], float f, int which) {
+  // column sums of the 16 x 64 bf16 tile a warp has just staged in `stg` (rows beyond L are exactly
+  // zero): lane l owns columns 2l, 2l+1 -- 16 conflict-free 4-byte smem reads, no shuffles
+  float cs[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+  auto colsum_staged = [&](int which) {
 #pragma unroll
-    for (int d = 0; d < 8; ++d) {
-      float s0 = (acc[d][0] + acc[d][2]) * f, s1 = (acc[d][1] + acc[d][3]) * f;
-#pragma unroll
-      for (int o = 4; o < 32; o <<= 1) {
-        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-      }
-      if (g == 0) {
-        atomicAdd(Cs + which * D + d * 8 + 2 * t, s0);
-        atomicAdd(Cs + which * D + d * 8 + 2 * t + 1, s1);
-      }
+    for (int r = 0; r < 16; ++r) {
+      const float2 v = __bfloat1622float2(*reinterpret_cast<const bf162*>(stg + r * LDS + 2 * lane));
+      cs[which][0] += v.x;
+      cs[which][1] += v.y;
     }
   };
 
@@ -355,7 +350,6 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const BwdParams p) {
       const uint32_t pa[4] = {pack2(ds[0], ds[1]), pack2(ds[2], ds[3]), pack2(ds[4], ds[5]), pack2(ds[6], ds[7])};
       mma_p_rows(dq, pa, Ks, kp * 16, lane);
     }
-    if (p.dbias) colsum_tile(dq, p.scale, 0);
     __syncwarp();
 #pragma unroll
     for (int d = 0; d < 8; ++d) {
@@ -363,6 +357,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const BwdParams p) {
       *reinterpret_cast<uint32_t*>(stg + (g + 8) * LDS + d * 8 + 2 * t) = pack2(dq[d][2] * p.scale, dq[d][3] * p.scale);
     }
     __syncwarp();
+    if (p.dbias) colsum_staged(0);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int id = lane + 32 * i, r = id >> 3, c = id & 7;
@@ -421,10 +416,6 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const BwdParams p) {
       mma_p_rows(dv, pa, dOs, qp * 16, lane);
       mma_p_rows(dk, sa, Qs, qp * 16, lane);
     }
-    if (p.dbias) {
-      colsum_tile(dk, p.scale, 1);
-      colsum_tile(dv, 1.f, 2);
-    }
     // dK then dV through the per-warp staging tile
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
@@ -437,6 +428,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const BwdParams p) {
         *reinterpret_cast<uint32_t*>(stg + (g + 8) * LDS + d * 8 + 2 * t) = pack2(src[2] * f, src[3] * f);
       }
       __syncwarp();
+      if (p.dbias) colsum_staged(which + 1);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int id = lane + 32 * i, r = id >> 3, c = id & 7;
@@ -448,6 +440,11 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const BwdParams p) {
     }
   }
   if (p.dbias) {
+#pragma unroll
+    for (int w = 0; w < 3; ++w) {
+      atomicAdd(Cs + w * D + 2 * lane, cs[w][0]);
+      atomicAdd(Cs + w * D + 2 * lane + 1, cs[w][1]);
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < 3 * D; i += blockDim.x)
       atomicAdd(p.dbias + (i / D) * p.H + h * D + (i % D), Cs[i]);
