@@ -291,7 +291,7 @@ def run_b200(args):
     n_mask_tag = float(sum((b["masked_lm_labels_b"] > -1).sum() for b in host)) / n_batches
     flops = flops_per_step(B, W["La"], W["Lt"], W["R"], n_mask_txt, n_mask_tag)
 
-    def train_step(batch):
+    def eager_step(batch):
         model.zero_grad()
         out = model(max_tag_length=W["Lt"], **batch)
         out[0].backward()
@@ -299,6 +299,25 @@ def run_b200(args):
             allreduce_gradients(model)
         opt.step()
         return out
+
+    # The public fast path: the whole step captured as one CUDA graph (mvp_pytorch_b200/graphs.py).
+    # --no-graph (or a failed capture, reported on stderr) falls back to the eager step.
+    graphed = None
+    if not args.no_graph and not args.profile_step:
+        try:
+            from mvp_pytorch_b200.graphs import GraphedTrainStep
+            for i in range(3):
+                eager_step(resident[i % n_batches])
+            graphed = GraphedTrainStep(model, opt, resident[0], forward_kwargs=dict(max_tag_length=W["Lt"]),
+                                       allreduce=world > 1)
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] CUDA-graph capture failed, using the eager step: {exc!r}", file=sys.stderr)
+            graphed = None
+
+    def train_step(batch):
+        if graphed is not None:
+            return graphed(batch)
+        return eager_step(batch)
 
     def timed(run_one, steps):
         if world > 1:
@@ -326,6 +345,7 @@ def run_b200(args):
         out = train_step(resident[i % n_batches])
     torch.cuda.synchronize()
     assert all(math.isfinite(float(x)) for x in out), "non-finite loss in warm-up"
+    n_kernels_per_step = None
 
     if args.profile_step:  # for ncu --profile-from-start off: exactly one steady-state step
         torch.cuda.profiler.start()
@@ -340,7 +360,13 @@ def run_b200(args):
     ms, launches = timed(lambda i: train_step(resident[i % n_batches]), args.steps)
     host_ms = timed.host_ms
     clocks = sampler.stop() if sampler else None
-    # +2 launches / step: fused AdamW and the gradient sum of squares
+    # +2 launches / step: fused AdamW and the gradient sum of squares.  Under a CUDA graph the host does
+    # not launch kernels one by one: count the kernels of one (eager) step instead -- the graph replays them.
+    if graphed is not None:
+        l0 = rt.launches
+        eager_step(resident[0])
+        launches = (rt.launches - l0) * args.steps
+        graphed.check_overflow()
     launches_per_step = launches / args.steps + 2
 
     # ---- (2) end to end: pinned host inputs copied every step (prefetched on a copy stream), six
@@ -366,7 +392,8 @@ def run_b200(args):
             stage(i + 1)
         torch.cuda.current_stream().wait_event(ready[slot])
         out = train_step(staged[slot])
-        loss_host[i].copy_(torch.stack([x.detach().float() for x in out]), non_blocking=True)
+        loss_host[i].copy_(out if torch.is_tensor(out) else torch.stack([x.detach().float() for x in out]),
+                           non_blocking=True)
         freed[slot].record()
 
     for f in freed:
@@ -379,7 +406,7 @@ def run_b200(args):
     prof = None
     if rank == 0:
         _lib.profile_enable(True)
-    train_step(resident[0])
+    eager_step(resident[0])
     torch.cuda.synchronize()
     if rank == 0:
         prof = _lib.profile_collect()
@@ -412,7 +439,7 @@ def run_b200(args):
                                "dropout 0.1, BASELINE.json configs[1]",
                    "batch_per_gpu": B, "global_batch": B * world, "text_phrase_len": W["La"], "tags": W["Lt"],
                    "regions": W["R"], "img_dim": W["img_dim"], "parallelism": f"dp{world}",
-                   "master_weights": "fp32", "l2": "inputs larger than L2: per-step working set (~11 GB activations, "
+                   "master_weights": "fp32", "cuda_graph": graphed is not None, "l2": "inputs larger than L2: per-step working set (~11 GB activations, "
                                                     "2.4 GB weights/grads/moments) >> 126 MB L2, 4 rotating batches"},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
                      "frac": achieved / sustained, "traffic": None,
@@ -451,6 +478,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="pairs per GPU (default: the 256 of BASELINE.json)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="run the eager step instead of the CUDA-graph step")
     ap.add_argument("--profile-step", action="store_true",
                     help="warm up, then run ONE step between cudaProfilerStart/Stop (for ncu) and exit")
     args = ap.parse_args()

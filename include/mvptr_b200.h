@@ -188,9 +188,14 @@ int mvptr_small_ce(const float* logits, const int64_t* labels, int n, int C, flo
 /* ---- optimizer ------------------------------------------------------------------------
  * AdamW.step of transformers/pytorch_transformers/optimization.py:130-189 over one flat fp32
  * arena (decay-first layout), also refreshing the bf16 compute copy; grad clipping folded in. */
+/* dyn_lr_step (nullable, device float[2] = {lr, step}): read at execution time instead of the by-value
+ * lr / step, so a captured CUDA graph follows the LR schedule and the bias correction. */
 int mvptr_adamw(float* p, const float* g, float* m, float* v, void* p16, size_t n, size_t decay_end, float lr,
                 float beta1, float beta2, float eps, float weight_decay, int step, int correct_bias,
-                const float* grad_sumsq, float max_norm, void* stream);
+                const float* grad_sumsq, float max_norm, const float* dyn_lr_step, void* stream);
+/* Copies *src (device or pinned-host word, read when the copy executes) into the dropout epoch mixed
+ * into every dropout hash: lets CUDA-graph replays draw fresh masks with baked-in seeds. */
+int mvptr_set_dropout_epoch(const uint32_t* src, void* stream);
 int mvptr_sumsq(const float* g, size_t n, float* out, void* stream);
 
 /* ---- weakly-supervised phrase grounding (WRA), batched ----------------------------------

@@ -82,7 +82,8 @@ SIGNATURES = {
     "mvptr_small_head_fwd": "pipppiiip",
     "mvptr_small_head_bwd": "ppippippiiip",
     "mvptr_small_ce": "ppiipppp",
-    "mvptr_adamw": "ppppp" + "zz" + "fffff" + "ii" + "pf" + "p",
+    "mvptr_adamw": "ppppp" + "zz" + "fffff" + "ii" + "pf" + "pp",
+    "mvptr_set_dropout_epoch": "pp",
     "mvptr_sumsq": "pzpp",
     "mvptr_topk_rows": "pliiippp",
     "mvptr_match_prob": "ppip",

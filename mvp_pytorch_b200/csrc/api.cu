@@ -66,3 +66,13 @@ extern "C" int mvptr_profile_collect(const char** names, double* work, float* ms
 
 extern "C" int mvptr_abi_version(void) { return MVPTR_ABI_VERSION; }
 extern "C" const char* mvptr_last_error(void) { return mvptr::g_err; }
+
+extern "C" int mvptr_set_epoch_gemm(const uint32_t*, void*);
+extern "C" int mvptr_set_epoch_rows(const uint32_t*, void*);
+extern "C" int mvptr_set_epoch_attn(const uint32_t*, void*);
+// src: device or PINNED host pointer (read when the copy executes, i.e. at graph replay time)
+extern "C" int mvptr_set_dropout_epoch(const uint32_t* src, void* stream) {
+  if (int rc = mvptr_set_epoch_gemm(src, stream)) return rc;
+  if (int rc = mvptr_set_epoch_rows(src, stream)) return rc;
+  return mvptr_set_epoch_attn(src, stream);
+}

@@ -40,6 +40,11 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ float fast_exp2(float x) {  // one MUFU.EX2 (exp2f adds range fix-ups we do not need)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
   const int sz = valid ? 16 : 0;  // src-size 0 -> zero fill
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
@@ -157,10 +162,10 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const FwdParams p) {
     float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
-      s[j][0] = exp2f(s[j][0] - mx0);
-      s[j][1] = exp2f(s[j][1] - mx0);
-      s[j][2] = exp2f(s[j][2] - mx1);
-      s[j][3] = exp2f(s[j][3] - mx1);
+      s[j][0] = fast_exp2(s[j][0] - mx0);
+      s[j][1] = fast_exp2(s[j][1] - mx0);
+      s[j][2] = fast_exp2(s[j][2] - mx1);
+      s[j][3] = fast_exp2(s[j][3] - mx1);
       sum0 += s[j][0] + s[j][1];
       sum1 += s[j][2] + s[j][3];
     }
@@ -168,7 +173,9 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const FwdParams p) {
     sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
     sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
     sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-    const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+    // normalisation (1/sum) and the dropout rescale (1/keep) are applied once to the 16x64 output tile,
+    // not to every probability: P only needs a keep/zero select before the PV product
+    const float inv0 = p.inv_keep / sum0, inv1 = p.inv_keep / sum1;
     const int q0 = qt * 16 + g, q1 = q0 + 8;
     if (p.lse && t == 0) {
       float* l = p.lse + ((size_t)b * p.nh + h) * L;
@@ -187,23 +194,27 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const FwdParams p) {
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int j = 2 * kk + u;
-        pv[4 * u + 0] = s[j][0] * inv0;
-        pv[4 * u + 1] = s[j][1] * inv0;
-        pv[4 * u + 2] = s[j][2] * inv1;
-        pv[4 * u + 3] = s[j][3] * inv1;
+        pv[4 * u + 0] = s[j][0];
+        pv[4 * u + 1] = s[j][1];
+        pv[4 * u + 2] = s[j][2];
+        pv[4 * u + 3] = s[j][3];
         if (drop) {
           const uint32_t k = j * 8 + 2 * t;
           bool k0, k1, k2, k3;
           dropout_pair(p.seed, rbase0 + k, p.keep_thr, k0, k1);
           dropout_pair(p.seed, rbase1 + k, p.keep_thr, k2, k3);
-          pv[4 * u + 0] = k0 ? pv[4 * u + 0] * p.inv_keep : 0.f;
-          pv[4 * u + 1] = k1 ? pv[4 * u + 1] * p.inv_keep : 0.f;
-          pv[4 * u + 2] = k2 ? pv[4 * u + 2] * p.inv_keep : 0.f;
-          pv[4 * u + 3] = k3 ? pv[4 * u + 3] * p.inv_keep : 0.f;
+          pv[4 * u + 0] = k0 ? pv[4 * u + 0] : 0.f;
+          pv[4 * u + 1] = k1 ? pv[4 * u + 1] : 0.f;
+          pv[4 * u + 2] = k2 ? pv[4 * u + 2] : 0.f;
+          pv[4 * u + 3] = k3 ? pv[4 * u + 3] : 0.f;
         }
       }
       const uint32_t pa[4] = {pack2(pv[0], pv[1]), pack2(pv[2], pv[3]), pack2(pv[4], pv[5]), pack2(pv[6], pv[7])};
       mma_p_rows(o, pa, Vs, kk * 16, lane);
+    }
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      o[d][0] *= inv0; o[d][1] *= inv0; o[d][2] *= inv1; o[d][3] *= inv1;
     }
     // stage the 16x64 output tile in this warp's own (already consumed) Q rows, then store 16-byte rows
     __syncwarp();
@@ -330,8 +341,8 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const BwdParams p) {
       for (int u = 0; u < 2; ++u) {
         const int k = kp * 16 + u * 8 + 2 * t;
         const float m0 = Ms[k], m1 = Ms[k + 1];
-        float pr[4] = {exp2f(s[u][0] * sc + m0 - l0), exp2f(s[u][1] * sc + m1 - l0), exp2f(s[u][2] * sc + m0 - l1),
-                       exp2f(s[u][3] * sc + m1 - l1)};
+        float pr[4] = {fast_exp2(s[u][0] * sc + m0 - l0), fast_exp2(s[u][1] * sc + m1 - l0), fast_exp2(s[u][2] * sc + m0 - l1),
+                       fast_exp2(s[u][3] * sc + m1 - l1)};
         float dpp[4] = {dp[u][0], dp[u][1], dp[u][2], dp[u][3]};
         if (drop) {
           bool k0, k1, k2, k3;
@@ -391,8 +402,8 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const BwdParams p) {
       for (int u = 0; u < 2; ++u) {
         const int q = qp * 16 + u * 8 + 2 * t;
         const float la = Ls[q], lb = Ls[q + 1], da_ = Ds[q], db_ = Ds[q + 1];
-        float pr[4] = {exp2f(s[u][0] * sc + m0 - la), exp2f(s[u][1] * sc + m0 - lb), exp2f(s[u][2] * sc + m1 - la),
-                       exp2f(s[u][3] * sc + m1 - lb)};
+        float pr[4] = {fast_exp2(s[u][0] * sc + m0 - la), fast_exp2(s[u][1] * sc + m0 - lb), fast_exp2(s[u][2] * sc + m1 - la),
+                       fast_exp2(s[u][3] * sc + m1 - lb)};
         float dpp[4] = {dp[u][0], dp[u][1], dp[u][2], dp[u][3]};
         float pd[4] = {pr[0], pr[1], pr[2], pr[3]};
         if (drop) {
@@ -527,3 +538,5 @@ extern "C" int mvptr_attn_bwd(const void* qkv, int ld_qkv, const float* maskadd,
   if (L <= 192) return attn::launch_bwd<24>(p, s);
   return attn::launch_bwd<32>(p, s);
 }
+
+MVPTR_DEFINE_EPOCH_SETTER(mvptr_set_epoch_attn)

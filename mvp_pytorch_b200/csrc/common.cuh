@@ -109,10 +109,23 @@ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
   x ^= x >> 16;
   return x;
 }
+// Dropout epoch: a per-translation-unit device word mixed into every dropout hash.  A CUDA-graph
+// replay cannot change kernel arguments (the per-site seeds are baked in at capture), so the graph
+// starts with a copy of a pinned host counter into this word (mvptr_set_dropout_epoch) and every
+// replay draws fresh masks.  Outside graphs it stays 0 and the host varies the seeds instead.
+static __device__ uint32_t g_dropout_epoch = 0;
+#define MVPTR_DEFINE_EPOCH_SETTER(fn)                                                                  \
+  extern "C" int fn(const uint32_t* src, void* stream) {                                               \
+    cudaError_t e = cudaMemcpyToSymbolAsync(::mvptr::g_dropout_epoch, src, sizeof(uint32_t), 0, cudaMemcpyDefault, \
+                                            (cudaStream_t)stream);                                     \
+    if (e != cudaSuccess) MVPTR_FAIL(MVPTR_ERR_CUDA, #fn ": %s", cudaGetErrorString(e));                \
+    return 0;                                                                                          \
+  }
+
 // One 32-bit hash serves TWO neighbouring elements (idx, idx^1): 16 random bits each, compared
 // against keep_thr >> 16 (p_keep resolution 1.5e-5).  Halves the integer work of the dropout sites.
 __device__ __forceinline__ uint32_t dropout_bits(uint32_t seed, uint32_t idx) {
-  return hash32((idx >> 1) * 0x9E3779B9u + seed);
+  return hash32((idx >> 1) * 0x9E3779B9u + seed + g_dropout_epoch * 0x85EBCA6Bu);
 }
 __device__ __forceinline__ bool dropout_keep(uint32_t seed, uint32_t idx, uint32_t keep_thr) {
   // keep_thr = floor(keep_prob * 2^32)

@@ -9,6 +9,8 @@
 // the canonical SWIZZLE_128B UMMA layouts, so no transposed copies are ever made.
 #include <cudaTypedefs.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -41,6 +43,7 @@ struct Params {
   uint32_t keep_thr;
   uint32_t seed;
   int use_dropout;
+  int debug;  // MVPTR_GEMM_DEBUG bit 0: skip the slab-reuse wait (timing experiment only, results may be wrong)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -470,7 +473,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // registers -> 128B-swizzled slab (16-byte unit u of row r lands at unit u ^ (r & 7))
         const int h = c % kChunksPerStore;  // position of this chunk inside the store box
         if (h == 0 && store_pending) {
-          if (lane == 0) tma_wait_read<0>();  // previous box has been read out of the slab
+          if (lane == 0 && !(p.debug & 1)) tma_wait_read<0>();  // previous box has been read out of the slab
           __syncwarp();
           store_pending = false;
         }
@@ -663,6 +666,8 @@ extern "C" int mvptr_gemm(const mvptr_gemm_args* g, void* stream_) {
   p.inv_keep = p.use_dropout ? 1.0f / (1.0f - g->p_drop) : 1.0f;
   p.keep_thr = keep_threshold(g->p_drop);
   p.seed = g->seed;
+  static const int debug_flags = getenv("MVPTR_GEMM_DEBUG") ? atoi(getenv("MVPTR_GEMM_DEBUG")) : 0;
+  p.debug = debug_flags;
 
   CUtensorMap ta, tb, td;
   int rc;
@@ -681,3 +686,5 @@ extern "C" int mvptr_gemm(const mvptr_gemm_args* g, void* stream_) {
   if (ctas == 2) return dispatch<256, 2>(g, ta, tb, td, p, stream);
   return bn == 256 ? dispatch<256, 1>(g, ta, tb, td, p, stream) : dispatch<128, 1>(g, ta, tb, td, p, stream);
 }
+
+MVPTR_DEFINE_EPOCH_SETTER(mvptr_set_epoch_gemm)

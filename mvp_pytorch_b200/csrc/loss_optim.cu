@@ -261,7 +261,13 @@ __global__ void small_ce_kernel(const float* __restrict__ logits, const int64_t*
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              bf16* __restrict__ p16, size_t n, size_t decay_end, float lr, float step_size, float beta1, float beta2,
-             float eps, float weight_decay, const float* __restrict__ grad_norm, float max_norm) {
+             float eps, float weight_decay, const float* __restrict__ grad_norm, float max_norm,
+             const float* __restrict__ dyn, int correct_bias) {
+  if (dyn) {  // {lr, step} read at execution time (CUDA-graph replays)
+    lr = dyn[0];
+    const float st = dyn[1];
+    step_size = correct_bias ? lr * sqrtf(1.f - powf(beta2, st)) / (1.f - powf(beta1, st)) : lr;
+  }
   float gs = 1.f;
   if (grad_norm && max_norm > 0.f) {
     const float nrm = sqrtf(*grad_norm);
@@ -389,7 +395,7 @@ extern "C" int mvptr_small_ce(const float* logits, const int64_t* labels, int n,
 }
 extern "C" int mvptr_adamw(float* p, const float* g, float* m, float* v, void* p16, size_t n, size_t decay_end, float lr,
                            float beta1, float beta2, float eps, float weight_decay, int step, int correct_bias,
-                           const float* grad_sumsq, float max_norm, void* stream) {
+                           const float* grad_sumsq, float max_norm, const float* dyn_lr_step, void* stream) {
   MVPTR_PROF("adamw", 30.0*n, stream);
   if (n == 0) return 0;
   if (n & 3) MVPTR_FAIL(MVPTR_ERR_ARG, "adamw: arena size must be a multiple of 4");
@@ -398,7 +404,8 @@ extern "C" int mvptr_adamw(float* p, const float* g, float* m, float* v, void* p
   size_t blocks = (n / 4 + 255) / 256;
   if (blocks > (size_t)kNumSMs * 8) blocks = (size_t)kNumSMs * 8;
   adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)p16, n, decay_end, lr, step_size,
-                                                                   beta1, beta2, eps, weight_decay, grad_sumsq, max_norm);
+                                                                   beta1, beta2, eps, weight_decay, grad_sumsq, max_norm,
+                                                                   dyn_lr_step, correct_bias);
   MVPTR_CHECK_LAUNCH("adamw");
   return 0;
 }

@@ -845,3 +845,5 @@ extern "C" int mvptr_add_cast(const float* a, const void* b, void* d, size_t n, 
   MVPTR_CHECK_LAUNCH("add_cast");
   return 0;
 }
+
+MVPTR_DEFINE_EPOCH_SETTER(mvptr_set_epoch_rows)

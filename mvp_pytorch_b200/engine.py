@@ -53,6 +53,15 @@ class Runtime:
         self.launches += 1
         return _lib.gemm(*a, **kw)
 
+    def anchor(self, param):
+        """A fresh scalar leaf that ties this forward's Functions into the autograd graph in place of
+        the nn.Parameter `param` (whose requires_grad it inherits).  Parameter gradients are written
+        straight into the arena by the kernels, never by autograd, and a Parameter's AccumulateGrad
+        node stays bound to the stream of its FIRST backward -- which makes a later CUDA-graph capture
+        on another stream fail with a cross-stream dependency.  A per-forward leaf has no history."""
+        return torch.zeros((), device=self.arena.device, dtype=F32,
+                           requires_grad=bool(param.requires_grad) and torch.is_grad_enabled())
+
     def begin_forward(self, training):
         a = self.arena
         if not a.valid():
@@ -743,7 +752,8 @@ class GatherRowsFn(Function):
     def backward(ctx, dout):
         shape, idx = ctx.s
         dx = torch.zeros(shape, device=dout.device, dtype=BF16)
-        dx.index_copy_(0, idx, dout)  # indexes are unique: plain row copies
+        # real indexes are unique; capacity-mode padding slots repeat row 0 with zero gradient, so add
+        dx.index_add_(0, idx, dout)
         return dx, None, None
 
 

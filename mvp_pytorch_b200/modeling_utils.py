@@ -149,6 +149,16 @@ class PreTrainedModel(nn.Module):
         else:
             super().zero_grad(set_to_none=set_to_none)
 
+    def load_state_dict(self, *a, **kw):
+        """nn.Module.load_state_dict, then re-derive the bf16 compute copy: copies into the parameter
+        views do not bump the arena's version counter, and under a fused optimizer or a captured
+        CUDA graph nothing else would refresh it."""
+        out = super().load_state_dict(*a, **kw)
+        if self._rt is not None and self._rt.arena.valid():
+            self._rt.arena.refresh_shadow(force=True)
+            self._rt._img_w_version = -1
+        return out
+
     def _apply(self, fn, *a, **kw):
         out = super()._apply(fn, *a, **kw)
         self.rebuild_arena()  # .to()/.cuda()/.bfloat16() re-home the parameters

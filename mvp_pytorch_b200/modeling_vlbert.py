@@ -101,7 +101,7 @@ class BiBertImgModel(BertPreTrainedModel):
     def _stage1(self, rt, pf, input_ids_a, token_type_ids_a, attention_mask_a, position_ids_a, input_ids_b,
                 token_type_ids_b, attention_mask_b, position_ids_b, img_feats):
         nl = self.config.num_hidden_layers // 2
-        anchor = self.txt_proj
+        anchor = rt.anchor(self.txt_proj)
         save = torch.is_grad_enabled() and anchor.requires_grad
         ids_a = input_ids_a.to(torch.int64).contiguous()
         ids_b = input_ids_b.to(torch.int64).contiguous()
@@ -135,7 +135,7 @@ class BiBertImgModel(BertPreTrainedModel):
         rt, pf = self._ctx()
         rt.begin_forward(self.training)
         nl = self.config.num_hidden_layers // 2
-        anchor = self.txt_proj
+        anchor = rt.anchor(self.txt_proj)
         txt, vis, mask_a, mask_b = self._stage1(rt, pf, input_ids_a, token_type_ids_a, attention_mask_a,
                                                 position_ids_a, input_ids_b, token_type_ids_b, attention_mask_b,
                                                 position_ids_b, img_feats)
@@ -198,7 +198,7 @@ class BiBertImgModel(BertPreTrainedModel):
         rt.begin_forward(self.training)
         txt, vis, _, _ = self._stage1(rt, pf, input_ids_a, token_type_ids_a, attention_mask_a, position_ids_a,
                                       input_ids_b, token_type_ids_b, attention_mask_b, position_ids_b, img_feats)
-        anchor = self.txt_proj
+        anchor = rt.anchor(self.txt_proj)
         return (E.ClsProjNormFn.apply(txt, rt, pf + "txt_proj", anchor),
                 E.ClsProjNormFn.apply(vis, rt, pf + "vis_proj", anchor))
 
@@ -210,7 +210,7 @@ class BiBertImgModel(BertPreTrainedModel):
         rt, pf = self._ctx()
         rt.begin_forward(self.training)
         nl = self.config.num_hidden_layers // 2
-        anchor = self.txt_proj
+        anchor = rt.anchor(self.txt_proj)
         save = torch.is_grad_enabled() and anchor.requires_grad
         ids = input_ids_a.to(torch.int64).contiguous()
         seg = token_type_ids_a.to(torch.int64).contiguous() if token_type_ids_a is not None else None
@@ -226,7 +226,7 @@ class BiBertImgModel(BertPreTrainedModel):
         rt, pf = self._ctx()
         rt.begin_forward(self.training)
         nl = self.config.num_hidden_layers // 2
-        anchor = self.txt_proj
+        anchor = rt.anchor(self.txt_proj)
         save = torch.is_grad_enabled() and anchor.requires_grad
         ids = input_ids_b.to(torch.int64).contiguous()
         seg = token_type_ids_b.to(torch.int64).contiguous() if token_type_ids_b is not None else None
@@ -250,7 +250,7 @@ class BiBertImgModel(BertPreTrainedModel):
         rt, pf = self._ctx()
         rt.begin_forward(self.training)
         nl = self.config.num_hidden_layers // 2
-        anchor = self.txt_proj
+        anchor = rt.anchor(self.txt_proj)
         joint = E.ConcatRowsFn.apply(txt, vis, int(max_tag_length), row_a, row_b, rt)
         jm = E.mask_additive(rt, mask_a, mask_b, int(max_tag_length), row_a, row_b)
         seq = E.encoder(rt, pf + "mul_encoder", joint, jm, nl, anchor)
@@ -275,13 +275,26 @@ class BertVQAHeads(_ParamOnly):
         self.predictions = BertQAPredictionHead(config)
 
 
-def _mlm_rows(labels2d):
+def _mlm_rows(labels2d, capacity=None, overflow=None):
     """Flat indexes and labels of the positions with a label > -1 (the masked_select of :1231-1235 /
-    :1244-1249).  The dynamic size costs one host sync, so callers do this on the INPUT labels before
-    any encoder work is queued: the host then runs ahead of the GPU for the rest of the step."""
+    :1244-1249).
+
+    Exact mode (capacity None): the dynamic size costs one host sync, so callers do this on the
+    INPUT labels before any encoder work is queued and the host then runs ahead of the GPU.
+    Capacity mode (CUDA-graph capture, graphs.py): a fixed number of rows, no sync -- unused slots
+    point at row 0 with label -1 (ignored by the loss, zero gradient); if more labels than slots
+    ever show up, `overflow` is raised on the device and the graphed step reports it."""
     flat = labels2d.reshape(-1)
-    idx = torch.nonzero(flat > -1).reshape(-1)
-    return idx, flat[idx].contiguous()
+    if capacity is None:
+        idx = torch.nonzero(flat > -1).reshape(-1)
+        return idx, flat[idx].contiguous()
+    sel = flat > -1
+    idx = torch.nonzero_static(sel, size=int(capacity), fill_value=0).reshape(-1)
+    count = sel.sum()
+    lab = torch.where(torch.arange(int(capacity), device=flat.device) < count, flat[idx], -1)
+    if overflow is not None:
+        overflow.logical_or_(count > capacity)
+    return idx, lab.contiguous()
 
 
 def _mlm_loss(rt, top, seq2d, rows, head_prefix, anchor):
@@ -333,15 +346,17 @@ class BiBertImgForPreTraining(BertPreTrainedModel):
                 is_img_match=None, img_index=None, phrase_index=None, phrase_mod='sample', wra_choices=None):
         rt = self.runtime()
         self._adopt(self.bert, "bert.")
-        anchor = self.logit_scale
+        anchor = rt.anchor(self.logit_scale)
         B, La = input_ids_a.shape
         Ltot = La + (attention_mask_b.shape[1] - max_tag_length if attention_mask_b is not None
                      else img_feats.shape[1])
         # label-only bookkeeping first (its host sync must not sit behind the queued forward)
-        vis_rows = _mlm_rows(masked_lm_labels_b)
+        cap = getattr(self, "mlm_capacity", None)  # (tag rows, text rows) or None = exact
+        ovf = getattr(self, "mlm_overflow", None)
+        vis_rows = _mlm_rows(masked_lm_labels_b, cap[0] if cap else None, ovf)
         lab = torch.full((B, Ltot), -1, dtype=torch.int64, device=input_ids_a.device)
         lab[:, :La] = masked_lm_labels_a
-        txt_rows = _mlm_rows(lab)
+        txt_rows = _mlm_rows(lab, cap[1] if cap else None, ovf)
         outputs, single_stream_output, hard_indexes = self.bert(
             input_ids_a=input_ids_a, position_ids_a=position_ids_a, token_type_ids_a=token_type_ids_a,
             attention_mask_a=attention_mask_a, head_mask=head_mask, img_feats=img_feats, input_ids_b=input_ids_b,
@@ -438,7 +453,7 @@ class BiImageBertForRetrieval(BertPreTrainedModel):
 
     def forward_train(self, **kw):
         rt = self._prep()
-        anchor = self.logit_scale
+        anchor = rt.anchor(self.logit_scale)
         outputs, single_stream_output, _ = self.bert(encode_hn=True, **kw)
         sim_mat = single_stream_output[2]
         retrieval_loss, _ = E.VSCFn.apply(sim_mat, rt, "logit_scale", anchor)
@@ -509,7 +524,7 @@ class BiImageBertForSequenceClassification(BertPreTrainedModel):
                 position_ids_b=None, head_mask=None, img_feats=None, soft_label=False):
         rt = self.runtime()
         self._adopt(self.bert, "bert.")
-        anchor = self.classifier.weight
+        anchor = rt.anchor(self.classifier.weight)
         outputs, _, _ = self.bert(input_ids_a=input_ids_a, position_ids_a=position_ids_a,
                                   token_type_ids_a=token_type_ids_a, attention_mask_a=attention_mask_a,
                                   head_mask=head_mask, img_feats=img_feats, use_b=use_b, input_ids_b=input_ids_b,
@@ -553,7 +568,7 @@ class BiImageBertForVQA(BertPreTrainedModel):
                 position_ids_b=None, head_mask=None, img_feats=None, soft_label=False):
         rt = self.runtime()
         self._adopt(self.bert, "bert.")
-        anchor = self.cls.predictions.bias
+        anchor = rt.anchor(self.cls.predictions.bias)
         outputs, _, _ = self.bert(input_ids_a=input_ids_a, position_ids_a=position_ids_a,
                                   token_type_ids_a=token_type_ids_a, attention_mask_a=attention_mask_a,
                                   head_mask=head_mask, img_feats=img_feats, input_ids_b=input_ids_b,
@@ -626,7 +641,7 @@ class BiBertImgForMLM(BertPreTrainedModel):
                 position_ids_b=None, head_mask=None, img_feats=None):
         rt = self.runtime()
         self._adopt(self.bert, "bert.")
-        anchor = self.logit_scale
+        anchor = rt.anchor(self.logit_scale)
         outputs, _, _ = self.bert(input_ids_a=input_ids_a, position_ids_a=position_ids_a,
                                   token_type_ids_a=token_type_ids_a, attention_mask_a=attention_mask_a,
                                   head_mask=head_mask, img_feats=img_feats, input_ids_b=input_ids_b,

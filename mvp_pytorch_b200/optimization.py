@@ -87,6 +87,8 @@ class AdamW(Optimizer):
         self._step = 0
         self._m = self._v = None
         self._norm = None
+        self._dyn = None       # device float[2] {lr, step} for CUDA-graph replays
+        self._dyn_host = None  # its pinned host source
 
     @classmethod
     def for_model(cls, model, **kw):
@@ -103,6 +105,21 @@ class AdamW(Optimizer):
         rt.shadow_managed = True
         return a
 
+    def enable_graph_mode(self):
+        """lr and step count are read from device memory at execution time (see graphs.py)."""
+        a = self._arena()
+        if self._m is None:
+            self._m = torch.zeros_like(a.master)
+            self._v = torch.zeros_like(a.master)
+            self._norm = torch.zeros(1, device=a.device, dtype=torch.float32)
+        self._dyn_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self._dyn = torch.zeros(2, device=a.device, dtype=torch.float32)
+
+    def before_replay(self):
+        """Host side of one graph replay: advance the step, publish {lr, step} in the pinned source."""
+        self._step += 1
+        self._dyn_host[0], self._dyn_host[1] = float(self.param_groups[0]["lr"]), float(self._step)
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
@@ -114,6 +131,11 @@ class AdamW(Optimizer):
             self._norm = torch.zeros(1, device=a.device, dtype=torch.float32)
         self._step += 1
         group = self.param_groups[0]
+        dyn = None
+        if self._dyn is not None:  # graph mode: lr / step travel through pinned host memory -> device
+            self._dyn_host[0], self._dyn_host[1] = float(group["lr"]), float(self._step)
+            self._dyn.copy_(self._dyn_host, non_blocking=True)
+            dyn = self._dyn
         wd = max(gr["weight_decay"] for gr in self.param_groups)
         norm = None
         if self.max_grad_norm > 0:
@@ -123,6 +145,6 @@ class AdamW(Optimizer):
         b1, b2 = group["betas"]
         _lib.call("mvptr_adamw", a.master, g, self._m, self._v, None if a.shadow is a.master else a.shadow,
                   a.numel, a.decay_end, float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(wd),
-                  self._step, int(bool(group["correct_bias"])), norm, self.max_grad_norm)
+                  self._step, int(bool(group["correct_bias"])), norm, self.max_grad_norm, dyn)
         a.mark_shadow_fresh()
         return loss

@@ -318,7 +318,7 @@ def test_adamw_matches_reference_trajectory(lib, golden_dir):
     used = [0.02 * x for x in (0.0, 0.5, 1.0, 0.875, 0.75)]
     for it in range(5):
         grad = (p - tgt) * 2
-        lib.call("mvptr_adamw", p, grad, m, v, p16, 4, 4, used[it], 0.9, 0.999, 1e-6, 0.01, it + 1, 1, None, 0.0)
+        lib.call("mvptr_adamw", p, grad, m, v, p16, 4, 4, used[it], 0.9, 0.999, 1e-6, 0.01, it + 1, 1, None, 0.0, None)
         assert_close(p.cpu(), g["traj"][it], 1e-5, 1e-6, f"adamw step {it}")
     assert torch.equal(p16, p.to(BF16))
     # no-decay tail + clipping
@@ -327,7 +327,7 @@ def test_adamw_matches_reference_trajectory(lib, golden_dir):
     m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda"); ss = torch.zeros(1, device="cuda")
     lib.call("mvptr_sumsq", gr, n, ss)
     assert_close(ss[0], (gr * gr).sum(), 1e-4, 1e-2, "sumsq")
-    lib.call("mvptr_adamw", p, gr, m, v, None, n, n // 2, 0.01, 0.9, 0.999, 1e-6, 0.1, 1, 1, ss, 1.0)
+    lib.call("mvptr_adamw", p, gr, m, v, None, n, n // 2, 0.01, 0.9, 0.999, 1e-6, 0.1, 1, 1, ss, 1.0, None)
     from oracle import mvptr_oracle as O
     scale = min(1.0, 1.0 / (float(gr.norm()) + 1e-6))
     pr, mr, vr = p0.clone().cpu(), torch.zeros(n), torch.zeros(n)
