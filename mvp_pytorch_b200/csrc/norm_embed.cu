@@ -244,156 +244,110 @@ gelu_bwd_colsum_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ pre
 //   dx_drop = dx * input-dropout mask (the dropout that sat between the dense and the
 //             residual add, modeling_bert.py:350-351) ; dbias += sum_r dx_drop
 // ---------------------------------------------------------------------------------
-// LayerNorm backward in two fully-occupied passes (the kernel is HBM-latency bound, so occupancy
-// matters more than the one re-read):
-//   pass A (warp per row, inputs kept PACKED in registers, ~56 regs): dx and dx_drop;
-//   pass B (thread = 8 columns, loops rows, coalesced): dgamma, dbeta, dbias column sums.
+// Single pass over the rows: a persistent grid (2 CTAs of 8 warps per SM) walks the rows warp by
+// warp, writes dx / dx_drop and keeps the three column sums (dgamma, dbeta, dbias) of the columns a
+// lane owns in registers; they are folded warp -> CTA (shared atomics) -> global (one atomicAdd per
+// column per CTA) at the end.  HBM traffic = read dy, x + write dx (+ dx_drop): 3-4 tensors instead of
+// the 7 of a dx pass followed by a column-sum pass.
 template <int NC>
-__global__ void __launch_bounds__(128, 8)
-ln_bwd_dx_kernel(const bf16* __restrict__ dy, RowMap dymap, const bf16* __restrict__ x_in,
-                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const bf16* __restrict__ gamma,
-                 bf16* __restrict__ dx, bf16* __restrict__ dx_drop, int rows, int H, uint32_t out_keep_thr,
-                 float out_inv_keep, uint32_t out_seed, uint32_t in_keep_thr, float in_inv_keep, uint32_t in_seed) {
-  const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(256, 2)
+ln_bwd_kernel(const bf16* __restrict__ dy, RowMap dymap, const bf16* __restrict__ x_in,
+              const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const bf16* __restrict__ gamma,
+              bf16* __restrict__ dx, bf16* __restrict__ dx_drop, float* __restrict__ dgamma,
+              float* __restrict__ dbeta, float* __restrict__ dbias, int rows, int H, uint32_t out_keep_thr,
+              float out_inv_keep, uint32_t out_seed, uint32_t in_keep_thr, float in_inv_keep, uint32_t in_seed) {
+  extern __shared__ float cta_acc[];  // [3][H]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nchunk = H >> 3;
-  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (r >= rows) return;
-  bf16x8 pgam[NC];
+  for (int i = threadIdx.x; i < 3 * H; i += 256) cta_acc[i] = 0.f;
+  __syncthreads();
+  float ag[NC][8], ab[NC][8], ad[NC][8];
 #pragma unroll
   for (int c = 0; c < NC; ++c)
-    if (lane + 32 * c < nchunk) pgam[c] = *reinterpret_cast<const bf16x8*>(gamma + (lane + 32 * c) * 8);
-  const float mean = mean_in[r], rstd = rstd_in[r];
-  const bf16* dyr = dy + dymap.off(r, H);
-  bf16x8 pg[NC], px[NC];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    const int ch = lane + 32 * c;
-    if (ch < nchunk) {
-      pg[c] = *reinterpret_cast<const bf16x8*>(dyr + ch * 8);
-      px[c] = *reinterpret_cast<const bf16x8*>(x_in + (size_t)r * H + ch * 8);
-    }
-  }
-  float s1 = 0.f, s2 = 0.f;
+    for (int j = 0; j < 8; ++j) ag[c][j] = ab[c][j] = ad[c][j] = 0.f;
+  const float inv_h = 1.f / H;
+  for (int r = blockIdx.x * 8 + warp; r < rows; r += gridDim.x * 8) {
+    const float mean = mean_in[r], rstd = rstd_in[r];
+    const bf16* dyr = dy + dymap.off(r, H);
+    bf16x8 pg[NC], px[NC];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    const int ch = lane + 32 * c;
-    if (ch < nchunk) {
-      float g[8], xv[8], gm[8];
-      unpack8(pg[c], g);
-      unpack8(px[c], xv);
-      unpack8(pgam[c], gm);
-      if (out_keep_thr != 0xffffffffu) {
-        dropout8(g, out_seed, (uint32_t)r * (uint32_t)H + ch * 8, out_keep_thr, out_inv_keep);
-        pg[c] = pack8(g);
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float gg = g[j] * gm[j];
-        s1 += gg;
-        s2 += gg * ((xv[j] - mean) * rstd);
+    for (int c = 0; c < NC; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunk) {
+        pg[c] = *reinterpret_cast<const bf16x8*>(dyr + ch * 8);
+        px[c] = *reinterpret_cast<const bf16x8*>(x_in + (size_t)r * H + ch * 8);
       }
     }
-  }
-  s1 = warp_sum(s1) / H;
-  s2 = warp_sum(s2) / H;
+    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    const int ch = lane + 32 * c;
-    if (ch < nchunk) {
-      float g[8], xv[8], o[8], gm[8];
-      unpack8(pg[c], g);
-      unpack8(px[c], xv);
-      unpack8(pgam[c], gm);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = rstd * (g[j] * gm[j] - s1 - (xv[j] - mean) * rstd * s2);
-      if (dx) *reinterpret_cast<bf16x8*>(dx + (size_t)r * H + ch * 8) = pack8(o);
-      if (dx_drop) {
-        dropout8(o, in_seed, (uint32_t)r * (uint32_t)H + ch * 8, in_keep_thr, in_inv_keep);
-        *reinterpret_cast<bf16x8*>(dx_drop + (size_t)r * H + ch * 8) = pack8(o);
-      }
-    }
-  }
-}
-
-// dgamma[n] += sum_r g*xhat ; dbeta[n] += sum_r g ; dbias[n] += sum_r dxb[r,n]
-// (g = dy with the output-dropout mask; dxb = the dx that reached the dense bias)
-__global__ void __launch_bounds__(256)
-ln_bwd_colsum_kernel(const bf16* __restrict__ dy, RowMap dymap, const bf16* __restrict__ x_in,
-                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
-                     const bf16* __restrict__ dxb, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                     float* __restrict__ dbias, int rows, int H, int rows_per_block, uint32_t out_keep_thr,
-                     float out_inv_keep, uint32_t out_seed) {
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int col = (blockIdx.x * 32 + tx) * 8;
-  const int r0 = blockIdx.y * rows_per_block;
-  const int r1 = min(rows, r0 + rows_per_block);
-  float ag[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ab[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ad[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (col < H) {
-    for (int r = r0 + ty; r < r1; r += 16) {
-      const int ra = r, rb = r + 8;
-      const bool hb = rb < r1;
-      const bf16x8 ga = *reinterpret_cast<const bf16x8*>(dy + dymap.off(ra, H) + col);
-      const bf16x8 xa = *reinterpret_cast<const bf16x8*>(x_in + (size_t)ra * H + col);
-      bf16x8 gb = ga, xb = xa, da, db;
-      if (hb) {
-        gb = *reinterpret_cast<const bf16x8*>(dy + dymap.off(rb, H) + col);
-        xb = *reinterpret_cast<const bf16x8*>(x_in + (size_t)rb * H + col);
-      }
-      if (dbias) {
-        da = *reinterpret_cast<const bf16x8*>(dxb + (size_t)ra * H + col);
-        db = hb ? *reinterpret_cast<const bf16x8*>(dxb + (size_t)rb * H + col) : da;
-      }
-      const float ma = mean_in[ra], sa = rstd_in[ra];
-      const float mb = hb ? mean_in[rb] : 0.f, sb = hb ? rstd_in[rb] : 0.f;
-      float g[8], xv[8], q[8];
-      unpack8(ga, g);
-      unpack8(xa, xv);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (out_keep_thr != 0xffffffffu)
-          g[j] = dropout_keep(out_seed, (uint32_t)ra * (uint32_t)H + col + j, out_keep_thr) ? g[j] * out_inv_keep : 0.f;
-        ag[j] += g[j] * ((xv[j] - ma) * sa);
-        ab[j] += g[j];
-      }
-      if (dbias) {
-        unpack8(da, q);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ad[j] += q[j];
-      }
-      if (hb) {
-        unpack8(gb, g);
-        unpack8(xb, xv);
+    for (int c = 0; c < NC; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunk) {
+        float g[8], xv[8], gm[8];
+        unpack8(pg[c], g);
+        unpack8(px[c], xv);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + ch * 8)), gm);
+        if (out_keep_thr != 0xffffffffu) {
+          dropout8(g, out_seed, (uint32_t)r * (uint32_t)H + ch * 8, out_keep_thr, out_inv_keep);
+          pg[c] = pack8(g);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          if (out_keep_thr != 0xffffffffu)
-            g[j] = dropout_keep(out_seed, (uint32_t)rb * (uint32_t)H + col + j, out_keep_thr) ? g[j] * out_inv_keep : 0.f;
-          ag[j] += g[j] * ((xv[j] - mb) * sb);
-          ab[j] += g[j];
+          const float xh = (xv[j] - mean) * rstd;
+          const float gg = g[j] * gm[j];
+          s1 += gg;
+          s2 += gg * xh;
+          ag[c][j] += g[j] * xh;
+          ab[c][j] += g[j];
         }
-        if (dbias) {
-          unpack8(db, q);
+      }
+    }
+    s1 = warp_sum(s1) * inv_h;
+    s2 = warp_sum(s2) * inv_h;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) ad[j] += q[j];
+    for (int c = 0; c < NC; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunk) {
+        float g[8], xv[8], o[8], gm[8];
+        unpack8(pg[c], g);
+        unpack8(px[c], xv);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + ch * 8)), gm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (g[j] * gm[j] - s1 - (xv[j] - mean) * rstd * s2);
+        bf16x8 pk = pack8(o);
+        if (dx) *reinterpret_cast<bf16x8*>(dx + (size_t)r * H + ch * 8) = pk;
+        if (dx_drop) {
+          dropout8(o, in_seed, (uint32_t)r * (uint32_t)H + ch * 8, in_keep_thr, in_inv_keep);
+          pk = pack8(o);
+          *reinterpret_cast<bf16x8*>(dx_drop + (size_t)r * H + ch * 8) = pk;
+        }
+        if (dbias) {  // column sum of exactly what the dense layer's backward reads (the bf16 rounding)
+          unpack8(pk, o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ad[c][j] += o[j];
         }
       }
     }
   }
-  __shared__ float red[8][32 * 8 + 1];
-  for (int pass = 0; pass < (dbias ? 3 : 2); ++pass) {
-    __syncthreads();
+  // j outer: the 32 lanes of a warp then hit 32 addresses 8 words apart (4-way bank conflict at worst)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) red[ty][tx * 8 + j] = pass == 0 ? ag[j] : (pass == 1 ? ab[j] : ad[j]);
-    __syncthreads();
-    if (ty == 0 && col < H) {
-      float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dbias);
+  for (int c = 0; c < NC; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nchunk) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) s += red[w][tx * 8 + j];
-        atomicAdd(dst + col + j, s);
+        atomicAdd(&cta_acc[ch * 8 + j], ag[c][j]);
+        atomicAdd(&cta_acc[H + ch * 8 + j], ab[c][j]);
+        if (dbias) atomicAdd(&cta_acc[2 * H + ch * 8 + j], ad[c][j]);
       }
     }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H; i += 256) {
+    atomicAdd(dgamma + i, cta_acc[i]);
+    atomicAdd(dbeta + i, cta_acc[H + i]);
+    if (dbias) atomicAdd(dbias + i, cta_acc[2 * H + i]);
   }
 }
 
@@ -709,13 +663,14 @@ extern "C" int mvptr_ln_bwd(const void* dy, int dy_rows_per_batch, long long dy_
   RowMap dm{dy_rows_per_batch > 0 ? dy_rows_per_batch : rows, dy_rows_per_batch > 0 ? dy_batch_stride : 0};
   if (!dgamma || !dbeta) MVPTR_FAIL(MVPTR_ERR_ARG, "ln_bwd: dgamma/dbeta accumulators are required");
   if (dbias && !dx && !dx_drop) MVPTR_FAIL(MVPTR_ERR_ARG, "ln_bwd: dbias needs dx or dx_drop to be written");
-  const int grid = (rows + 3) / 4;
   const int nc = (H + 255) / 256;
-  const int smem = 0;
+  int grid = (rows + 7) / 8;
+  if (grid > 2 * kNumSMs) grid = 2 * kNumSMs;  // persistent: 2 CTAs per SM
+  const int smem = 3 * H * (int)sizeof(float);
 #define LN_BWD_LAUNCH(NC)                                                                                          \
-  ln_bwd_dx_kernel<NC><<<grid, 128, smem, (cudaStream_t)stream>>>(                                                 \
-      (const bf16*)dy, dm, (const bf16*)x, mean, rstd, (const bf16*)gamma, (bf16*)dx, (bf16*)dx_drop, rows, H,      \
-      thr(out_p_drop), invk(out_p_drop), out_seed, thr(in_p_drop), invk(in_p_drop), in_seed)
+  ln_bwd_kernel<NC><<<grid, 256, smem, (cudaStream_t)stream>>>(                                                    \
+      (const bf16*)dy, dm, (const bf16*)x, mean, rstd, (const bf16*)gamma, (bf16*)dx, (bf16*)dx_drop, dgamma, dbeta, \
+      dbias, rows, H, thr(out_p_drop), invk(out_p_drop), out_seed, thr(in_p_drop), invk(in_p_drop), in_seed)
   switch (nc) {
     case 1: LN_BWD_LAUNCH(1); break;
     case 2: LN_BWD_LAUNCH(2); break;
@@ -723,14 +678,6 @@ extern "C" int mvptr_ln_bwd(const void* dy, int dy_rows_per_batch, long long dy_
     default: LN_BWD_LAUNCH(4); break;
   }
 #undef LN_BWD_LAUNCH
-  MVPTR_CHECK_LAUNCH("ln_bwd_dx");
-  {
-    const int rpb = 64;  // many small blocks: the pass is latency bound, it wants loads of many rows in flight
-    dim3 g2((H + 255) / 256, (rows + rpb - 1) / rpb);
-    ln_bwd_colsum_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(
-        (const bf16*)dy, dm, (const bf16*)x, mean, rstd, (const bf16*)(dx_drop ? dx_drop : dx), dgamma, dbeta, dbias,
-        rows, H, rpb, thr(out_p_drop), invk(out_p_drop), out_seed);
-  }
   MVPTR_CHECK_LAUNCH("ln_bwd");
   return 0;
 }
