@@ -450,8 +450,8 @@ embed_pos_type_bwd_kernel(const bf16* __restrict__ dpre, const int64_t* __restri
 template <typename T>
 __global__ void pad_cast_kernel(const T* __restrict__ src, long long ld_src, bf16* __restrict__ dst, int ld_dst,
                                 int rows, int K) {
-  const int r = blockIdx.y;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.x;  // rows on grid.x: config 5 has 102 400 region rows (> the 65 535 limit of grid.y)
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
   if (c >= ld_dst) return;
   float v = 0.f;
   if (c < K) v = (float)src[(size_t)r * ld_src + c];
@@ -713,7 +713,7 @@ extern "C" int mvptr_pad_cast(const void* src, int src_is_f32, long long ld_src,
                               void* stream) {
   MVPTR_PROF("pad_cast", 0, stream);
   if (rows <= 0) return 0;
-  dim3 grid((ld_dst + 255) / 256, rows);
+  dim3 grid(rows, (ld_dst + 255) / 256);
   if (src_is_f32)
     pad_cast_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src, ld_src, (bf16*)dst, ld_dst, rows, K);
   else
