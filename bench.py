@@ -360,14 +360,14 @@ def run_b200(args):
     ms, launches = timed(lambda i: train_step(resident[i % n_batches]), args.steps)
     host_ms = timed.host_ms
     clocks = sampler.stop() if sampler else None
-    # +2 launches / step: fused AdamW and the gradient sum of squares.  Under a CUDA graph the host does
-    # not launch kernels one by one: count the kernels of one (eager) step instead -- the graph replays them.
+    # The library counts its own launches (mvptr_launch_count, AdamW and the gradient norm included).  Under a
+    # CUDA graph the host does not launch kernels one by one: count one (eager) step -- the graph replays it.
     if graphed is not None:
         l0 = rt.launches
         eager_step(resident[0])
         launches = (rt.launches - l0) * args.steps
         graphed.check_overflow()
-    launches_per_step = launches / args.steps + 2
+    launches_per_step = launches / args.steps
 
     # ---- (2) end to end: pinned host inputs copied every step (prefetched on a copy stream), six
     #          losses read back every step into pinned memory

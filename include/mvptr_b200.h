@@ -32,6 +32,9 @@ extern "C" {
 #define MVPTR_ABI_VERSION 1
 
 int mvptr_abi_version(void);
+/* Number of kernels this library has launched in this process (every launch is counted at its
+ * launch site): what bench.py reports as gpu_launches. */
+unsigned long long mvptr_launch_count(void);
 const char* mvptr_last_error(void);
 /* Optional per-launch profiler: when enabled, every entry point brackets its kernel launches with
  * CUDA events on the launching stream; collect() synchronises and returns (name, work, ms). */

@@ -124,6 +124,11 @@ class LaunchProfiler:
 PROFILER = None
 
 
+def launch_count():
+    """Kernels launched by libmvptr_b200.so in this process so far (counted at the launch sites)."""
+    return int(lib().mvptr_launch_count())
+
+
 def profile_enable(on):
     lib().mvptr_profile_enable(int(bool(on)))
 
@@ -196,6 +201,7 @@ def lib():
         L = ctypes.CDLL(LIB_PATH)
         L.mvptr_last_error.restype = ctypes.c_char_p
         L.mvptr_abi_version.restype = ctypes.c_int
+        L.mvptr_launch_count.restype = ctypes.c_ulonglong
         for name, spec in SIGNATURES.items():
             fn = getattr(L, name)  # AttributeError here = header/library mismatch: fail loudly
             fn.argtypes = [_CT[c] for c in spec]

@@ -6,6 +6,7 @@
 #include "common.cuh"
 
 namespace mvptr {
+unsigned long long g_launch_count = 0;
 static thread_local char g_err[512] = "";
 void set_last_error(const char* fmt, ...) {
   va_list ap;
@@ -64,6 +65,7 @@ extern "C" int mvptr_profile_collect(const char** names, double* work, float* ms
   return n;
 }
 
+extern "C" unsigned long long mvptr_launch_count(void) { return mvptr::g_launch_count; }
 extern "C" int mvptr_abi_version(void) { return MVPTR_ABI_VERSION; }
 extern "C" const char* mvptr_last_error(void) { return mvptr::g_err; }
 

@@ -13,6 +13,8 @@
 //
 // Backward is recompute-based (flash style): pass 1 (warp owns 16 queries) produces dQ,
 // pass 2 (warp owns 16 keys) produces dK, dV.  No atomics, no [L,L] buffers.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mvptr {
@@ -462,6 +464,205 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const BwdParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward for L <= 128: no recomputation.  Phase A (warp = 16 queries): S and dP for ALL keys of the
+// head (independent accumulator chains per 16-key pair -> ILP instead of occupancy), P / dropout / dS
+// in registers, dQ = dS K straight from the register fragments; the dropped probabilities and dS go to
+// shared memory as bf16 [q][k].  Phase B (warp = 16 keys): dV = P^T dO and dK = dS^T Q with the
+// transposed A fragments read by ldmatrix.trans.  5 tile products instead of the 7 of the
+// recompute kernel above, one exp / one dropout hash per score instead of two.
+// ---------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT * 16) attn_bwd_smem_kernel(const BwdParams p) {
+  constexpr int LP = NT * 8;
+  constexpr int NW = NT / 2;    // warps == 16-row tiles
+  constexpr int PLD = LP + 8;   // padded pitch of the [q][k] tiles: conflict-free 4-byte stores and ldmatrix rows
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  bf16* Qs = reinterpret_cast<bf16*>(smem_attn);
+  bf16* Ks = Qs + LP * LDS;
+  bf16* Vs = Ks + LP * LDS;
+  bf16* dOs = Vs + LP * LDS;
+  bf16* Ps = dOs + LP * LDS;     // dropped, rescaled probabilities
+  bf16* dSs = Ps + LP * PLD;
+  bf16* Stg = dSs + LP * PLD;    // [NW][16][LDS]
+  float* Ms = reinterpret_cast<float*>(Stg + NW * 16 * LDS);
+  float* Ls = Ms + LP;
+  float* Ds = Ls + LP;
+  float* Cs = Ds + LP;
+  const int b = blockIdx.y, h = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int L = p.L;
+  const size_t row0 = (size_t)b * L;
+  const bf16* base = p.qkv + row0 * p.ld_qkv + h * D;
+  load_tile(Qs, base, p.ld_qkv, LP, L);
+  load_tile(Ks, base + p.H, p.ld_qkv, LP, L);
+  load_tile(Vs, base + 2 * p.H, p.ld_qkv, LP, L);
+  load_tile(dOs, p.dctx + row0 * p.ld_ctx + h * D, p.ld_ctx, LP, L);
+  const float* lse = p.lse + ((size_t)b * p.nh + h) * L;
+  for (int i = threadIdx.x; i < LP; i += blockDim.x) {
+    Ms[i] = i < L ? p.maskadd[row0 + i] * kLog2e : -INFINITY;
+    Ls[i] = i < L ? lse[i] * kLog2e : INFINITY;
+  }
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) Cs[i] = 0.f;
+  // D[q] = sum_d dO[q,d] * O[q,d]: 4 lanes per query, O straight from global while the tiles land
+  {
+    const int q = threadIdx.x >> 2, part = threadIdx.x & 3;  // blockDim = 4 * LP threads / 16 ... NW*32 = 2*LP
+    for (int qq = q; qq < LP; qq += blockDim.x >> 2) {
+      float acc = 0.f;
+      if (qq < L) {
+        const bf16* orow = p.ctx + (row0 + qq) * p.ld_ctx + h * D + part * 16;
+        const bf16* drow = p.dctx + (row0 + qq) * p.ld_ctx + h * D + part * 16;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float ov[8], dv[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(orow + c * 8), ov);
+          unpack8(*reinterpret_cast<const bf16x8*>(drow + c * 8), dv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc += ov[j] * dv[j];
+        }
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (part == 0) Ds[qq] = acc;
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  const int g = lane >> 2, t = lane & 3;
+  const float sc = p.scale * kLog2e;
+  const bool drop = p.keep_thr != 0xffffffffu;
+  const uint32_t hb = ((uint32_t)b * p.nh + h) * L;
+  const uint32_t Lp = (uint32_t)(L + 1) & ~1u;
+  bf16* stg = Stg + warp * 16 * LDS;
+  float cs[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+  auto colsum_staged = [&](int which) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const float2 v = __bfloat1622float2(*reinterpret_cast<const bf162*>(stg + r * LDS + 2 * lane));
+      cs[which][0] += v.x;
+      cs[which][1] += v.y;
+    }
+  };
+  auto store_staged = [&](int row_first, int col_block) {  // 16 x 64 staged tile -> dqkv rows row_first.., 16-byte stores
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int id = lane + 32 * i, r = id >> 3, c = id & 7;
+      const int row = row_first + r;
+      if (row < L)
+        *reinterpret_cast<uint4*>(p.dqkv + (row0 + row) * p.ld_qkv + col_block * p.H + h * D + c * 8) =
+            *reinterpret_cast<const uint4*>(stg + r * LDS + c * 8);
+    }
+  };
+
+  // ---------------- phase A: warp owns queries [16 warp, 16 warp + 16) ----------------
+  {
+    const int qt = warp;
+    uint32_t qa[4][4], da[4][4];
+    load_a_frags(Qs, qt * 16, lane, qa);
+    load_a_frags(dOs, qt * 16, lane, da);
+    const int q0 = qt * 16 + g, q1 = q0 + 8;
+    const float l0 = Ls[q0], l1 = Ls[q1], d0 = Ds[q0], d1 = Ds[q1];
+    const uint32_t rb0 = (hb + q0) * Lp, rb1 = (hb + q1) * Lp;
+    float dq[8][4];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) dq[d][0] = dq[d][1] = dq[d][2] = dq[d][3] = 0.f;
+#pragma unroll
+    for (int kp = 0; kp < NT / 2; ++kp) {
+      float s[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, dp[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+      mma_a_rowsT(s, qa, Ks, kp * 16, lane);
+      mma_a_rowsT(dp, da, Vs, kp * 16, lane);
+      float ds[8];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int k = kp * 16 + u * 8 + 2 * t;
+        const float2 m = *reinterpret_cast<const float2*>(Ms + k);
+        float pr[4] = {fast_exp2(fmaf(s[u][0], sc, m.x - l0)), fast_exp2(fmaf(s[u][1], sc, m.y - l0)),
+                       fast_exp2(fmaf(s[u][2], sc, m.x - l1)), fast_exp2(fmaf(s[u][3], sc, m.y - l1))};
+        float dpp[4] = {dp[u][0], dp[u][1], dp[u][2], dp[u][3]};
+        float pd[4] = {pr[0], pr[1], pr[2], pr[3]};
+        if (drop) {
+          bool k0, k1, k2, k3;
+          dropout_pair(p.seed, rb0 + k, p.keep_thr, k0, k1);
+          dropout_pair(p.seed, rb1 + k, p.keep_thr, k2, k3);
+          dpp[0] = k0 ? dpp[0] * p.inv_keep : 0.f; pd[0] = k0 ? pd[0] * p.inv_keep : 0.f;
+          dpp[1] = k1 ? dpp[1] * p.inv_keep : 0.f; pd[1] = k1 ? pd[1] * p.inv_keep : 0.f;
+          dpp[2] = k2 ? dpp[2] * p.inv_keep : 0.f; pd[2] = k2 ? pd[2] * p.inv_keep : 0.f;
+          dpp[3] = k3 ? dpp[3] * p.inv_keep : 0.f; pd[3] = k3 ? pd[3] * p.inv_keep : 0.f;
+        }
+        ds[4 * u + 0] = pr[0] * (dpp[0] - d0);
+        ds[4 * u + 1] = pr[1] * (dpp[1] - d0);
+        ds[4 * u + 2] = pr[2] * (dpp[2] - d1);
+        ds[4 * u + 3] = pr[3] * (dpp[3] - d1);
+        *reinterpret_cast<uint32_t*>(Ps + q0 * PLD + k) = pack2(pd[0], pd[1]);
+        *reinterpret_cast<uint32_t*>(Ps + q1 * PLD + k) = pack2(pd[2], pd[3]);
+      }
+      const uint32_t pa[4] = {pack2(ds[0], ds[1]), pack2(ds[2], ds[3]), pack2(ds[4], ds[5]), pack2(ds[6], ds[7])};
+      const int kc = kp * 16 + 2 * t;
+      *reinterpret_cast<uint32_t*>(dSs + q0 * PLD + kc) = pa[0];
+      *reinterpret_cast<uint32_t*>(dSs + q1 * PLD + kc) = pa[1];
+      *reinterpret_cast<uint32_t*>(dSs + q0 * PLD + kc + 8) = pa[2];
+      *reinterpret_cast<uint32_t*>(dSs + q1 * PLD + kc + 8) = pa[3];
+      mma_p_rows(dq, pa, Ks, kp * 16, lane);
+    }
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      *reinterpret_cast<uint32_t*>(stg + g * LDS + d * 8 + 2 * t) = pack2(dq[d][0] * p.scale, dq[d][1] * p.scale);
+      *reinterpret_cast<uint32_t*>(stg + (g + 8) * LDS + d * 8 + 2 * t) = pack2(dq[d][2] * p.scale, dq[d][3] * p.scale);
+    }
+    __syncwarp();
+    if (p.dbias) colsum_staged(0);
+    store_staged(qt * 16, 0);
+  }
+  __syncthreads();
+
+  // ---------------- phase B: warp owns keys [16 warp, 16 warp + 16) ----------------
+  {
+    const int kt = warp;
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      dk[d][0] = dk[d][1] = dk[d][2] = dk[d][3] = 0.f;
+      dv[d][0] = dv[d][1] = dv[d][2] = dv[d][3] = 0.f;
+    }
+    // transposed A fragments: matrix mi of the x4 load = rows q0 + 8 (mi >> 1) .., columns key0 + 8 (mi & 1) ..
+    const int mi = lane >> 3;
+    const int frag_off = ((lane & 7) + 8 * (mi >> 1)) * PLD + kt * 16 + 8 * (mi & 1);
+#pragma unroll
+    for (int qc = 0; qc < NT / 2; ++qc) {
+      uint32_t pa[4], sa[4];
+      ldsm_x4_t(smem_u32(Ps + qc * 16 * PLD + frag_off), pa[0], pa[1], pa[2], pa[3]);
+      ldsm_x4_t(smem_u32(dSs + qc * 16 * PLD + frag_off), sa[0], sa[1], sa[2], sa[3]);
+      mma_p_rows(dv, pa, dOs, qc * 16, lane);
+      mma_p_rows(dk, sa, Qs, qc * 16, lane);
+    }
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      __syncwarp();
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        const float f = which == 0 ? p.scale : 1.f;
+        const float(&src)[4] = which == 0 ? dk[d] : dv[d];
+        *reinterpret_cast<uint32_t*>(stg + g * LDS + d * 8 + 2 * t) = pack2(src[0] * f, src[1] * f);
+        *reinterpret_cast<uint32_t*>(stg + (g + 8) * LDS + d * 8 + 2 * t) = pack2(src[2] * f, src[3] * f);
+      }
+      __syncwarp();
+      if (p.dbias) colsum_staged(which + 1);
+      store_staged(kt * 16, which + 1);
+    }
+  }
+  if (p.dbias) {
+#pragma unroll
+    for (int w = 0; w < 3; ++w) {
+      atomicAdd(Cs + w * D + 2 * lane, cs[w][0]);
+      atomicAdd(Cs + w * D + 2 * lane + 1, cs[w][1]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * D; i += blockDim.x)
+      atomicAdd(p.dbias + (i / D) * p.H + h * D + (i % D), Cs[i]);
+  }
+}
+
 template <int NT>
 static int launch_fwd(const FwdParams& p, cudaStream_t s) {
   constexpr int LP = NT * 8;
@@ -497,6 +698,22 @@ static int launch_bwd(const BwdParams& p, cudaStream_t s) {
   return 0;
 }
 
+template <int NT>
+static int launch_bwd_smem(const BwdParams& p, cudaStream_t s) {
+  constexpr int LP = NT * 8, NW = NT / 2;
+  constexpr int smem = 4 * LP * LDS * 2 + 2 * LP * (LP + 8) * 2 + NW * 16 * LDS * 2 + 3 * LP * 4 + 3 * D * 4;
+  auto kern = attn_bwd_smem_kernel<NT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) MVPTR_FAIL(MVPTR_ERR_CUDA, "attn bwd smem attr: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  kern<<<dim3(p.nh, p.B), NW * 32, smem, s>>>(p);
+  MVPTR_CHECK_LAUNCH("attn_bwd");
+  return 0;
+}
+
 }  // namespace attn
 }  // namespace mvptr
 
@@ -517,9 +734,17 @@ extern "C" int mvptr_attn_fwd(const void* qkv, int ld_qkv, const float* maskadd,
   attn::FwdParams p{(const bf16*)qkv, ld_qkv, maskadd, (bf16*)ctx, ld_ctx, lse, B, L, nh, H, 0.125f,
                     keep_threshold(p_drop), p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f, seed};
   cudaStream_t s = (cudaStream_t)stream;
-  if (L <= 64) return attn::launch_fwd<8>(p, s);
-  if (L <= 96) return attn::launch_fwd<12>(p, s);
-  if (L <= 128) return attn::launch_fwd<16>(p, s);
+  switch ((L + 15) / 16) {  // keys padded to a multiple of 16, not further: L = 40 runs 48 wide, not 64
+    case 1: return attn::launch_fwd<2>(p, s);
+    case 2: return attn::launch_fwd<4>(p, s);
+    case 3: return attn::launch_fwd<6>(p, s);
+    case 4: return attn::launch_fwd<8>(p, s);
+    case 5: return attn::launch_fwd<10>(p, s);
+    case 6: return attn::launch_fwd<12>(p, s);
+    case 7: return attn::launch_fwd<14>(p, s);
+    case 8: return attn::launch_fwd<16>(p, s);
+    default: break;
+  }
   if (L <= 192) return attn::launch_fwd<24>(p, s);
   return attn::launch_fwd<32>(p, s);
 }
@@ -532,6 +757,20 @@ extern "C" int mvptr_attn_bwd(const void* qkv, int ld_qkv, const float* maskadd,
   attn::BwdParams p{(const bf16*)qkv, ld_qkv, maskadd, (const bf16*)ctx, (const bf16*)dctx, ld_ctx, lse, (bf16*)dqkv,
                     dbias, B, L, nh, H, 0.125f, keep_threshold(p_drop), p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f, seed};
   cudaStream_t s = (cudaStream_t)stream;
+  static const bool force_recompute = getenv("MVPTR_ATTN_BWD_RECOMPUTE") != nullptr;  // A/B switch for tests
+  if (!force_recompute) {
+    switch ((L + 15) / 16) {
+      case 1: return attn::launch_bwd_smem<2>(p, s);
+      case 2: return attn::launch_bwd_smem<4>(p, s);
+      case 3: return attn::launch_bwd_smem<6>(p, s);
+      case 4: return attn::launch_bwd_smem<8>(p, s);
+      case 5: return attn::launch_bwd_smem<10>(p, s);
+      case 6: return attn::launch_bwd_smem<12>(p, s);
+      case 7: return attn::launch_bwd_smem<14>(p, s);
+      case 8: return attn::launch_bwd_smem<16>(p, s);
+      default: break;
+    }
+  }
   if (L <= 64) return attn::launch_bwd<8>(p, s);
   if (L <= 96) return attn::launch_bwd<12>(p, s);
   if (L <= 128) return attn::launch_bwd<16>(p, s);

@@ -17,8 +17,12 @@ void set_last_error(const char* fmt, ...);
     ::mvptr::set_last_error(__VA_ARGS__); \
     return (code);                       \
   } while (0)
+// every kernel launch of the library passes through here (or through gemm's launch()): the exact
+// count backs bench.py's `gpu_launches` (mvptr_launch_count)
+extern unsigned long long g_launch_count;
 #define MVPTR_CHECK_LAUNCH(name)                                                          \
   do {                                                                                    \
+    ++::mvptr::g_launch_count;                                                            \
     cudaError_t e__ = cudaGetLastError();                                                 \
     if (e__ != cudaSuccess) MVPTR_FAIL(MVPTR_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e__)); \
   } while (0)
@@ -77,10 +81,19 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // erf-GELU (reference modeling_bert.py:142-148) and its derivative.  erf through Abramowitz-Stegun
 // 7.1.26 (|err| <= 1.5e-7, far below bf16 output rounding): 2 MUFU + ~10 FMA instead of erff's
 // branchy ~25-instruction path -- the FFN epilogues run this per element next to the tensor pipe.
+__device__ __forceinline__ float rcp_approx(float x) {  // one MUFU.RCP, no range fix-ups (x in [1, 1e19) here)
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {  // one MUFU.EX2, no denormal fix-ups
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void erf_gauss(float x, float& erf_v, float& gauss) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));  // MUFU.RCP, ~1 ulp
-  gauss = __expf(-z * z);  // exp(-x^2/2)
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, fabsf(x), 1.0f));
+  gauss = ex2_approx(x * x * -0.72134752044448170f);  // exp(-x^2/2) = 2^(-x^2 log2(e) / 2)
   float p = fmaf(t, 1.061405429f, -1.453152027f);
   p = fmaf(t, p, 1.421413741f);
   p = fmaf(t, p, -0.284496736f);
@@ -90,7 +103,8 @@ __device__ __forceinline__ void erf_gauss(float x, float& erf_v, float& gauss) {
 __device__ __forceinline__ float gelu_erf(float x) {
   float e, g;
   erf_gauss(x, e, g);
-  return 0.5f * x * (1.0f + e);
+  const float hx = 0.5f * x;
+  return fmaf(hx, e, hx);
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   float e, g;

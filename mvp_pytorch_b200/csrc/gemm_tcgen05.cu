@@ -193,13 +193,15 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool 
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <int BN, int CTAS = 1>
+template <int BN, int CTAS = 1, bool DUAL = false>
 struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;            // 16 KB (per CTA)
   static constexpr int kBBytes = (BN / CTAS) * BK * 2;   // a CTA pair splits the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (kStageBytes == 48 * 1024) ? 4 : 6;
-  static constexpr int kOutBytes = kEpiWarps * kSlabBytes;  // one TMA-store slab per epilogue warp
+  // DUAL (two outputs per tile: pre-activation and activation) pays for its second set of store slabs
+  // with one pipeline stage
+  static constexpr int kStages = DUAL ? ((kStageBytes == 48 * 1024) ? 3 : 5) : ((kStageBytes == 48 * 1024) ? 4 : 6);
+  static constexpr int kOutBytes = kEpiWarps * kSlabBytes * (DUAL ? 2 : 1);  // TMA-store slab(s) per epilogue warp
   static constexpr int kBarBytes = 256;
   static constexpr int kTotal = kStages * kStageBytes + kOutBytes + kBarBytes + 1024;  // + alignment slack
 };
@@ -208,11 +210,14 @@ struct SmemLayout {
 // leader CTA; each CTA stages its own 128 A rows and HALF of the B tile, so the bytes per FLOP that
 // every SM pulls through L2 drop by a third and six 32 KB stages fit: the 4-stage single-CTA ring
 // could not cover the TMA latency at K=768 (tensor pipe 63 % active in ncu, profiles/).
-template <int BN, bool A_MN, bool B_MN, bool F32OUT, int CTAS>
+// DUAL: the tile is stored twice through two slabs and two tensor maps -- tmP receives acc + bias (the
+// pre-activation backward needs), tmD receives gelu(acc + bias): BertIntermediate (modeling_bert.py:394-397)
+// in ONE pass over the accumulator, no separate GELU kernel and no re-read of the pre-activation.
+template <int BN, bool A_MN, bool B_MN, bool F32OUT, int CTAS, bool DUAL = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmD, const Params p) {
-  using L = SmemLayout<BN, CTAS>;
+            const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmP, const Params p) {
+  using L = SmemLayout<BN, CTAS, DUAL>;
   constexpr bool kPair = CTAS == 2;
   const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
@@ -238,6 +243,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmD) : "memory");
+    if constexpr (DUAL) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmP) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -364,6 +370,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int q = warp & 3;          // TMEM lane quarter == warp % 4
     const int hf = (warp - 4) >> 2;  // column half of the tile
     uint8_t* slab = out_stage + (warp - 4) * kSlabBytes;
+    uint8_t* slab_pre = slab + kEpiWarps * kSlabBytes;  // DUAL only
     constexpr int kHalf = BN / 2;
     constexpr int kChunks = kHalf / 32;  // 32-column TMEM loads per tile per warp
     constexpr int kChunksPerStore = F32OUT ? 1 : 2;
@@ -432,8 +439,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if (n0 + j < p.N) v[j] += __ldg(b + n0 + j);
           }
         }
+        const int h = c % kChunksPerStore;  // position of this chunk inside the store box
+        if (h == 0 && store_pending) {
+          if (lane == 0 && !(p.debug & 1)) tma_wait_read<0>();  // previous box(es) have been read out of the slab(s)
+          __syncwarp();
+          store_pending = false;
+        }
+        if constexpr (DUAL) {
+          uint8_t* prow = slab_pre + lane * 128;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            *reinterpret_cast<bf16x8*>(prow + (((h * 4 + u) ^ (lane & 7)) << 4)) = pack8(v + u * 8);
+        }
         const size_t aux_off = (size_t)m * p.ld_aux + n0;
-        if (p.pre_act != nullptr && row_ok) {
+        if (!DUAL && p.pre_act != nullptr && row_ok) {
 #pragma unroll
           for (int u = 0; u < 4; ++u)
             if (n0 + u * 8 + 8 <= p.N) *reinterpret_cast<bf16x8*>(p.pre_act + aux_off + u * 8) = pack8(v + u * 8);
@@ -471,12 +490,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
         }
         // registers -> 128B-swizzled slab (16-byte unit u of row r lands at unit u ^ (r & 7))
-        const int h = c % kChunksPerStore;  // position of this chunk inside the store box
-        if (h == 0 && store_pending) {
-          if (lane == 0 && !(p.debug & 1)) tma_wait_read<0>();  // previous box has been read out of the slab
-          __syncwarp();
-          store_pending = false;
-        }
         uint8_t* row = slab + lane * 128;
         if constexpr (F32OUT) {
 #pragma unroll
@@ -498,6 +511,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tma_reduce_add_2d(&tmD, smem_u32(slab), ng0, m_base + q * 32);
             else
               tma_store_2d(&tmD, smem_u32(slab), ng0, m_base + q * 32);
+            if constexpr (DUAL) tma_store_2d(&tmP, smem_u32(slab_pre), ng0, m_base + q * 32);
             tma_commit();
           }
           store_pending = true;
@@ -562,11 +576,11 @@ static int make_map(CUtensorMap* map, const void* base, bool f32, uint64_t inner
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool F32OUT, int CTAS>
+template <int BN, bool A_MN, bool B_MN, bool F32OUT, int CTAS, bool DUAL = false>
 static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, const Params& p,
-                  cudaStream_t stream) {
-  auto kern = gemm_kernel<BN, A_MN, B_MN, F32OUT, CTAS>;
-  constexpr int smem = SmemLayout<BN, CTAS>::kTotal;
+                  cudaStream_t stream, const CUtensorMap* pre = nullptr) {
+  auto kern = gemm_kernel<BN, A_MN, B_MN, F32OUT, CTAS, DUAL>;
+  constexpr int smem = SmemLayout<BN, CTAS, DUAL>::kTotal;
   static bool configured = false;  // per template instantiation
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -590,7 +604,8 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap&
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, b, d, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, b, d, pre ? *pre : d, p);
+  ++g_launch_count;
   if (e != cudaSuccess) MVPTR_FAIL(MVPTR_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
   return 0;
 }
@@ -681,8 +696,21 @@ extern "C" int mvptr_gemm(const mvptr_gemm_args* g, void* stream_) {
   else             rc = make_map(&td, g->D, false, g->N, g->M, (uint64_t)g->ldd * 2, 64, 32);
   if (rc) return rc;
 
+  // bias + GELU with the pre-activation saved: both outputs leave through TMA stores (DUAL tiles)
+  const bool dual = g->pre_act && g->act == 1 && !g->a_mn && !g->b_mn && !g->d_is_f32 && split == 1 && bn == 256 &&
+                    !g->gelu_grad_of && !g->residual && !p.use_dropout &&
+                    (reinterpret_cast<uintptr_t>(g->pre_act) & 15) == 0;
+  CUtensorMap tp;
+  if (dual) {
+    rc = make_map(&tp, g->pre_act, false, g->N, g->M, (uint64_t)g->ld_aux * 2, 64, 32);
+    if (rc) return rc;
+  }
   static const char* kNames[4] = {"gemm[k,k]", "gemm[k,mn]", "gemm[mn,k]", "gemm[mn,mn]"};
   MVPTR_PROF(kNames[(g->a_mn ? 2 : 0) | (g->b_mn ? 1 : 0)], 2.0 * g->M * g->N * g->K, stream);
+  if (dual) {
+    if (ctas == 2) return launch<256, false, false, false, 2, true>(ta, tb, td, p, stream, &tp);
+    return launch<256, false, false, false, 1, true>(ta, tb, td, p, stream, &tp);
+  }
   if (ctas == 2) return dispatch<256, 2>(g, ta, tb, td, p, stream);
   return bn == 256 ? dispatch<256, 1>(g, ta, tb, td, p, stream) : dispatch<128, 1>(g, ta, tb, td, p, stream);
 }

@@ -1,6 +1,8 @@
 // One encoder layer (CaptionBertLayer, modeling_vlbert.py:191-199) forward / backward as ONE
 // C-ABI call each: the host launches the 7 (fwd) / 13 (bwd) kernels back to back from C++, so
 // the Python side pays one ctypes call per layer instead of one per kernel.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #define TRY(expr)              \
@@ -61,12 +63,23 @@ extern "C" int mvptr_layer_fwd(const mvptr_layer_args* a, void* stream) {
   }
   TRY(mvptr_add_ln_fwd(a->tmp, a->x, a->p_hidden, a->seed1, save ? a->pre1 : nullptr, a->ln1_g, a->ln1_b, a->a1, save ? a->st1 : nullptr,
                        save ? a->st1 + M : nullptr, M, H, a->eps, s));
-  {  // BertIntermediate: gelu(dense(a1)), modeling_bert.py:394-397
-    mvptr_gemm_args g = gemm_base(a->a1, H, a->w_i, H, a->pre_g, I, M, I, H);
-    g.bias = a->b_i;
-    TRY(mvptr_gemm(&g, s));
+  {  // BertIntermediate: gelu(dense(a1)), modeling_bert.py:394-397.  GELU runs in the GEMM epilogue (MUFU-cheap
+     // erf, common.cuh); in training the tile is stored twice -- pre-activation (for GELU') and activation --
+     // through the DUAL TMA-store slabs, so the [M, I] pre-activation is never read back in forward.
+    static const bool fused = !(getenv("MVPTR_FFN1_FUSED") && atoi(getenv("MVPTR_FFN1_FUSED")) == 0);
+    if (fused) {
+      mvptr_gemm_args g = gemm_base(a->a1, H, a->w_i, H, a->inter, I, M, I, H);
+      g.bias = a->b_i;
+      g.act = 1;
+      if (save) { g.pre_act = a->pre_g; g.ld_aux = I; }
+      TRY(mvptr_gemm(&g, s));
+    } else {
+      mvptr_gemm_args g = gemm_base(a->a1, H, a->w_i, H, a->pre_g, I, M, I, H);
+      g.bias = a->b_i;
+      TRY(mvptr_gemm(&g, s));
+      TRY(mvptr_gelu_fwd(a->pre_g, a->inter, (size_t)M * I, s));
+    }
   }
-  TRY(mvptr_gelu_fwd(a->pre_g, a->inter, (size_t)M * I, s));
   {  // BertOutput: LN(dropout(dense(inter)) + a1), modeling_bert.py:407-411
     mvptr_gemm_args g = gemm_base(a->inter, I, a->w_o2, I, a->tmp, H, M, H, I);
     g.bias = a->b_o2;

@@ -37,7 +37,7 @@ class Runtime:
         self.seed_ctr = 0
         self.img_w16 = None
         self._img_w_version = -1
-        self.launches = 0
+        self._launch_base = _lib.launch_count()
         self.layer_protos = {}
 
     # ---- bookkeeping -------------------------------------------------------------------
@@ -45,12 +45,15 @@ class Runtime:
         self.seed_ctr += 1
         return (self.seed_base * 2654435761 + self.seed_ctr * 974711) & 0xFFFFFFFF
 
+    @property
+    def launches(self):
+        """Kernels launched by the library since this runtime was created (the library's own count)."""
+        return _lib.launch_count() - self._launch_base
+
     def call(self, name, *args):
-        self.launches += 1
         _lib.call(name, *args)
 
     def gemm(self, *a, **kw):
-        self.launches += 1
         return _lib.gemm(*a, **kw)
 
     def anchor(self, param):
@@ -186,8 +189,7 @@ class EncoderFn(Function):
             la.lse = f0
             la.st1 = f0 + 4 * B * nh * L
             la.st2 = f0 + 4 * (B * nh * L + 2 * M)
-            _lib.layer_call("mvptr_layer_fwd", la, 9)
-            rt.launches += 9
+            _lib.layer_call("mvptr_layer_fwd", la, 7)
             if save:
                 saved.append((pf, la, x, blk, f32, out))
             x = out
@@ -220,8 +222,7 @@ class EncoderFn(Function):
             la.datt = s0 + 2 * M * 5 * H
             la.dqkv = s0 + 2 * M * 6 * H
             la.dpre_g = s0 + 2 * M * 9 * H
-            _lib.layer_call("mvptr_layer_bwd", la, 14)
-            rt.launches += 14
+            _lib.layer_call("mvptr_layer_bwd", la, 12)
             sync = getattr(rt, "grad_sync", None)
             if sync is not None and sync.enabled:  # this layer's gradients are final: reduce them now
                 offs = rt.arena.offsets

@@ -21,7 +21,7 @@ def _header_functions():
     hdr = open(os.path.join(ROOT, "include", "mvptr_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     out = {}
-    for m in re.finditer(r"\b(?:int|const char\*)\s+(mvptr_\w+)\(([^;{}]*?)\);", hdr, flags=re.S):
+    for m in re.finditer(r"\b(?:int|const char\*|unsigned long long)\s+(mvptr_\w+)\(([^;{}]*?)\);", hdr, flags=re.S):
         out[m.group(1)] = [a.strip() for a in m.group(2).split(",") if a.strip() and a.strip() != "void"]
     return out
 
@@ -49,7 +49,7 @@ def test_ctypes_signatures_match_header(built):
             elif a.startswith("size_t"): kinds += "z"
             else: kinds += "i"
         assert kinds == spec, f"{name}: header {kinds} vs binding {spec}"
-    declared = set(fns) - {"mvptr_abi_version", "mvptr_last_error", "mvptr_wra_max_phrases", "mvptr_profile_enable",
+    declared = set(fns) - {"mvptr_abi_version", "mvptr_last_error", "mvptr_launch_count", "mvptr_wra_max_phrases", "mvptr_profile_enable",
                                "mvptr_profile_collect"}
     assert declared == set(built.SIGNATURES), declared ^ set(built.SIGNATURES)
 

@@ -142,7 +142,7 @@ def attn_ref(qkv, maskadd, B, L, nh, H):
     return (p @ v).permute(0, 2, 1, 3).reshape(B * L, H)
 
 
-@pytest.mark.parametrize("L", [35, 70, 90, 105, 183, 193])
+@pytest.mark.parametrize("L", [7, 16, 35, 40, 70, 90, 105, 128, 133, 183, 193])
 def test_attention_fwd_bwd(lib, L):
     B, nh = 3, 12
     H = nh * 64
@@ -188,6 +188,46 @@ def test_attention_dropout_consistency(lib):
     rhs = (dctx.float().view(B, L, nh, 64) * ctx.float().view(B, L, nh, 64)).sum(dim=(1, 3))
     assert_close(lhs, rhs, 3e-2, 0.5, "dropout adjoint identity")
     assert (ctx.float() - (p @ v).permute(0, 2, 1, 3).reshape(B * L, H)).abs().max() > 0.05  # dropout did something
+
+
+@pytest.mark.parametrize("L", [40, 90, 150])
+def test_attention_dropout_matches_autograd_with_the_extracted_mask(lib, L):
+    """The keep mask depends only on (seed, batch, head, query, key): extract it by pushing one-hot V
+    columns through the forward kernel, then check forward AND backward (dQ, dK, dV) against torch
+    autograd using that exact mask.  L=40/90 run the shared-memory backward, L=150 the recompute one."""
+    B, nh, pd, seed = 2, 3, 0.25, 1234
+    H = nh * 64
+    maskadd = torch.zeros(B, L, device="cuda")
+    maskadd[1, L - 4:] = -10000.0
+    keep = torch.zeros(B, nh, L, L, device="cuda")
+    for c in range((L + 63) // 64):
+        probe = torch.zeros(B, L, 3, nh, 64, device="cuda")
+        for k in range(c * 64, min(L, c * 64 + 64)):
+            probe[:, k, 2, :, k - c * 64] = 1.0  # V[k, :] = e_(k - 64c); Q = K = 0 -> uniform P
+        ctx = torch.empty(B * L, H, device="cuda", dtype=BF16)
+        lib.call("mvptr_attn_fwd", probe.view(B * L, 3 * H).to(BF16), 3 * H, torch.zeros(B, L, device="cuda"), ctx, H,
+                 None, B, L, nh, H, pd, seed)
+        pdrop = ctx.float().view(B, L, nh, 64).permute(0, 2, 1, 3)  # [B, nh, q, k - 64c]
+        n = min(64, L - c * 64)
+        keep[:, :, :, c * 64:c * 64 + n] = (pdrop[..., :n] > 0).float()
+    rate = keep.mean().item()
+    assert abs(rate - (1 - pd)) < 0.02, rate
+    qkv = rnd(B * L, 3 * H, seed=L + 1)
+    x = qkv.float().requires_grad_(True)
+    q, k, v = x.view(B, L, 3, nh, 64).permute(2, 0, 3, 1, 4)
+    pr = torch.softmax(q @ k.transpose(-1, -2) / 8.0 + maskadd[:, None, None, :], -1)
+    ref = ((pr * keep / (1 - pd)) @ v).permute(0, 2, 1, 3).reshape(B * L, H)
+    ctx = torch.empty(B * L, H, device="cuda", dtype=BF16); lse = torch.empty(B, nh, L, device="cuda", dtype=F32)
+    lib.call("mvptr_attn_fwd", qkv, 3 * H, maskadd, ctx, H, lse, B, L, nh, H, pd, seed)
+    assert_close(ctx, ref, 2e-2, 2e-2, "attn fwd with dropout")
+    dctx = rnd(B * L, H, seed=6)
+    ref.backward(dctx.float())
+    dqkv = torch.empty_like(qkv)
+    dbias = torch.zeros(3 * H, device="cuda")
+    lib.call("mvptr_attn_bwd", qkv, 3 * H, maskadd, ctx, dctx, H, lse, dqkv, dbias, B, L, nh, H, pd, seed)
+    rel = ((dqkv.float() - x.grad).norm() / x.grad.norm()).item()
+    assert rel < 2e-2, f"attn bwd with dropout rel l2 {rel}"
+    assert_close(dbias, x.grad.sum(0), 2e-2, 0.3, "fused qkv bias grad")
 
 
 # ------------------------------------------------------------------------------------
