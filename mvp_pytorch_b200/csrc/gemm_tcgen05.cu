@@ -213,10 +213,16 @@ struct SmemLayout {
 // DUAL: the tile is stored twice through two slabs and two tensor maps -- tmP receives acc + bias (the
 // pre-activation backward needs), tmD receives gelu(acc + bias): BertIntermediate (modeling_bert.py:394-397)
 // in ONE pass over the accumulator, no separate GELU kernel and no re-read of the pre-activation.
-template <int BN, bool A_MN, bool B_MN, bool F32OUT, int CTAS, bool DUAL = false>
+// EPI selects the epilogue: 0 = generic (run-time flags: alpha, bias, residual, dropout, GELU', ...),
+// 1 = lean bias + GELU, 2 = lean bias + GELU with DUAL stores.  The lean variants carry none of the
+// generic branches: the generic body with GELU inlined 32x per chunk no longer fits the instruction
+// cache (ncu: stall_no_inst), and its bias loads sat behind the TMEM wait.
+template <int BN, bool A_MN, bool B_MN, bool F32OUT, int CTAS, int EPI = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmP, const Params p) {
+  constexpr bool DUAL = EPI == 2;
+  constexpr bool LEAN = EPI != 0;
   using L = SmemLayout<BN, CTAS, DUAL>;
   constexpr bool kPair = CTAS == 2;
   const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
@@ -398,6 +404,51 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int c = 0; c < kChunks; ++c) {
         const int n0 = n_base + c * 32;
         if (n0 >= p.N) break;
+        if constexpr (LEAN) {
+          // host guarantees: bf16 bias, 16-byte aligned, N % 64 == 0, alpha == 1, no split-K
+          uint4 braw[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) braw[u] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.bias) + n0) + u);
+          tc_wait_ld();
+          if (c + 1 < kChunks && n0 + 32 < p.N) tc_ld32(t_row + (c + 1) * 32, rbuf[(c + 1) & 1]);
+          float v[32];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float x[8];
+            unpack8(braw[u], x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[u * 8 + j] = __uint_as_float(rbuf[c & 1][u * 8 + j]) + x[j];
+          }
+          const int h = c & 1;
+          if (h == 0 && store_pending) {
+            if (lane == 0) tma_wait_read<0>();
+            __syncwarp();
+            store_pending = false;
+          }
+          if constexpr (DUAL) {
+            uint8_t* prow = slab_pre + lane * 128;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              *reinterpret_cast<bf16x8*>(prow + (((h * 4 + u) ^ (lane & 7)) << 4)) = pack8(v + u * 8);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          uint8_t* row = slab + lane * 128;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            *reinterpret_cast<bf16x8*>(row + (((h * 4 + u) ^ (lane & 7)) << 4)) = pack8(v + u * 8);
+          if (h == 1) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmD, smem_u32(slab), n0 - 32, m_base + q * 32);
+              if constexpr (DUAL) tma_store_2d(&tmP, smem_u32(slab_pre), n0 - 32, m_base + q * 32);
+              tma_commit();
+            }
+            store_pending = true;
+          }
+          continue;
+        }
         tc_wait_ld();
         if (c + 1 < kChunks && n0 + 32 < p.N) tc_ld32(t_row + (c + 1) * 32, rbuf[(c + 1) & 1]);
         float v[32];
@@ -445,14 +496,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           __syncwarp();
           store_pending = false;
         }
-        if constexpr (DUAL) {
-          uint8_t* prow = slab_pre + lane * 128;
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            *reinterpret_cast<bf16x8*>(prow + (((h * 4 + u) ^ (lane & 7)) << 4)) = pack8(v + u * 8);
-        }
         const size_t aux_off = (size_t)m * p.ld_aux + n0;
-        if (!DUAL && p.pre_act != nullptr && row_ok) {
+        if (p.pre_act != nullptr && row_ok) {
 #pragma unroll
           for (int u = 0; u < 4; ++u)
             if (n0 + u * 8 + 8 <= p.N) *reinterpret_cast<bf16x8*>(p.pre_act + aux_off + u * 8) = pack8(v + u * 8);
@@ -511,7 +556,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tma_reduce_add_2d(&tmD, smem_u32(slab), ng0, m_base + q * 32);
             else
               tma_store_2d(&tmD, smem_u32(slab), ng0, m_base + q * 32);
-            if constexpr (DUAL) tma_store_2d(&tmP, smem_u32(slab_pre), ng0, m_base + q * 32);
             tma_commit();
           }
           store_pending = true;
@@ -576,11 +620,11 @@ static int make_map(CUtensorMap* map, const void* base, bool f32, uint64_t inner
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool F32OUT, int CTAS, bool DUAL = false>
+template <int BN, bool A_MN, bool B_MN, bool F32OUT, int CTAS, int EPI = 0>
 static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, const Params& p,
                   cudaStream_t stream, const CUtensorMap* pre = nullptr) {
-  auto kern = gemm_kernel<BN, A_MN, B_MN, F32OUT, CTAS, DUAL>;
-  constexpr int smem = SmemLayout<BN, CTAS, DUAL>::kTotal;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, F32OUT, CTAS, EPI>;
+  constexpr int smem = SmemLayout<BN, CTAS, EPI == 2>::kTotal;
   static bool configured = false;  // per template instantiation
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -653,9 +697,12 @@ extern "C" int mvptr_gemm(const mvptr_gemm_args* g, void* stream_) {
   // cta_pair: 0 auto, 1 off, 2 on.  Auto (measured, profiles/bench_gemm_pair_r1.txt): CTA pairs win
   // 8-13 % when the mainloop is long (K >= 1536) or an operand is MN-major (dgrad / wgrad); the short
   // K-major K=768 forward GEMMs are a wash or slightly slower, so they keep single-CTA tiles.
+  // (DUAL-store GELU tiles give one pipeline stage to the second slab set: 5 x 32 KB stages of a pair
+  // cover the TMA latency, 3 x 48 KB of a single CTA do not -- 216 vs 243 us on FFN1, tools/bench_ffn1.py)
+  const bool want_dual = g->act == 1 && g->pre_act && !g->a_mn && !g->b_mn && !g->d_is_f32 && split == 1 && bn == 256;
   int ctas = g->cta_pair == 1 ? 1
            : g->cta_pair == 2 ? 2
-           : (bn == 256 && g->M > BM && (g->K >= 1536 || g->a_mn || g->b_mn)) ? 2 : 1;
+           : (bn == 256 && g->M > BM && (g->K >= 1536 || g->a_mn || g->b_mn || want_dual)) ? 2 : 1;
   if (ctas == 2 && bn != 256) MVPTR_FAIL(MVPTR_ERR_ARG, "gemm: CTA pairs need block_n 256");
   const int tile_m = BM * ctas;
 
@@ -696,10 +743,13 @@ extern "C" int mvptr_gemm(const mvptr_gemm_args* g, void* stream_) {
   else             rc = make_map(&td, g->D, false, g->N, g->M, (uint64_t)g->ldd * 2, 64, 32);
   if (rc) return rc;
 
-  // bias + GELU with the pre-activation saved: both outputs leave through TMA stores (DUAL tiles)
-  const bool dual = g->pre_act && g->act == 1 && !g->a_mn && !g->b_mn && !g->d_is_f32 && split == 1 && bn == 256 &&
-                    !g->gelu_grad_of && !g->residual && !p.use_dropout &&
-                    (reinterpret_cast<uintptr_t>(g->pre_act) & 15) == 0;
+  // bias + GELU (BertIntermediate) takes the lean epilogue; with the pre-activation saved for backward both
+  // outputs leave through TMA stores (DUAL slabs)
+  const bool lean = g->act == 1 && !g->a_mn && !g->b_mn && !g->d_is_f32 && split == 1 && bn == 256 && g->bias &&
+                    g->bias_is_bf16 && (reinterpret_cast<uintptr_t>(g->bias) & 15) == 0 && (g->N % 64) == 0 &&
+                    g->alpha == 1.0f && !g->accumulate && !g->gelu_grad_of && !g->residual && !p.use_dropout &&
+                    (!g->pre_act || (reinterpret_cast<uintptr_t>(g->pre_act) & 15) == 0);
+  const bool dual = lean && g->pre_act;
   CUtensorMap tp;
   if (dual) {
     rc = make_map(&tp, g->pre_act, false, g->N, g->M, (uint64_t)g->ld_aux * 2, 64, 32);
@@ -708,8 +758,12 @@ extern "C" int mvptr_gemm(const mvptr_gemm_args* g, void* stream_) {
   static const char* kNames[4] = {"gemm[k,k]", "gemm[k,mn]", "gemm[mn,k]", "gemm[mn,mn]"};
   MVPTR_PROF(kNames[(g->a_mn ? 2 : 0) | (g->b_mn ? 1 : 0)], 2.0 * g->M * g->N * g->K, stream);
   if (dual) {
-    if (ctas == 2) return launch<256, false, false, false, 2, true>(ta, tb, td, p, stream, &tp);
-    return launch<256, false, false, false, 1, true>(ta, tb, td, p, stream, &tp);
+    if (ctas == 2) return launch<256, false, false, false, 2, 2>(ta, tb, td, p, stream, &tp);
+    return launch<256, false, false, false, 1, 2>(ta, tb, td, p, stream, &tp);
+  }
+  if (lean) {
+    if (ctas == 2) return launch<256, false, false, false, 2, 1>(ta, tb, td, p, stream);
+    return launch<256, false, false, false, 1, 1>(ta, tb, td, p, stream);
   }
   if (ctas == 2) return dispatch<256, 2>(g, ta, tb, td, p, stream);
   return bn == 256 ? dispatch<256, 1>(g, ta, tb, td, p, stream) : dispatch<128, 1>(g, ta, tb, td, p, stream);
