@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const FwdParams p) {
   const int b = blockIdx.y, h = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int L = p.L;
+  const uint32_t dseed = site_seed(p.seed);
   const bf16* base = p.qkv + (size_t)b * L * p.ld_qkv + h * D;
   load_tile(Qs, base, p.ld_qkv, LP, L);
   load_tile(Ks, base + p.H, p.ld_qkv, LP, L);
@@ -203,8 +204,8 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const FwdParams p) {
         if (drop) {
           const uint32_t k = j * 8 + 2 * t;
           bool k0, k1, k2, k3;
-          dropout_pair(p.seed, rbase0 + k, p.keep_thr, k0, k1);
-          dropout_pair(p.seed, rbase1 + k, p.keep_thr, k2, k3);
+          dropout_pair(dseed, rbase0 + k, p.keep_thr, k0, k1);
+          dropout_pair(dseed, rbase1 + k, p.keep_thr, k2, k3);
           pv[4 * u + 0] = k0 ? pv[4 * u + 0] : 0.f;
           pv[4 * u + 1] = k1 ? pv[4 * u + 1] : 0.f;
           pv[4 * u + 2] = k2 ? pv[4 * u + 2] : 0.f;
@@ -271,6 +272,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const BwdParams p) {
   const int b = blockIdx.y, h = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int L = p.L;
+  const uint32_t dseed = site_seed(p.seed);
   const size_t row0 = (size_t)b * L;
   const bf16* base = p.qkv + row0 * p.ld_qkv + h * D;
   load_tile(Qs, base, p.ld_qkv, LP, L);
@@ -348,8 +350,8 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const BwdParams p) {
         float dpp[4] = {dp[u][0], dp[u][1], dp[u][2], dp[u][3]};
         if (drop) {
           bool k0, k1, k2, k3;
-          dropout_pair(p.seed, (hb + q0) * Lp + k, p.keep_thr, k0, k1);
-          dropout_pair(p.seed, (hb + q1) * Lp + k, p.keep_thr, k2, k3);
+          dropout_pair(dseed, (hb + q0) * Lp + k, p.keep_thr, k0, k1);
+          dropout_pair(dseed, (hb + q1) * Lp + k, p.keep_thr, k2, k3);
           dpp[0] = k0 ? dpp[0] * p.inv_keep : 0.f;
           dpp[1] = k1 ? dpp[1] * p.inv_keep : 0.f;
           dpp[2] = k2 ? dpp[2] * p.inv_keep : 0.f;
@@ -409,10 +411,10 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const BwdParams p) {
         float dpp[4] = {dp[u][0], dp[u][1], dp[u][2], dp[u][3]};
         float pd[4] = {pr[0], pr[1], pr[2], pr[3]};
         if (drop) {
-          const bool kp0 = dropout_keep(p.seed, (hb + q) * Lp + k0, p.keep_thr);
-          const bool kp1 = dropout_keep(p.seed, (hb + q + 1) * Lp + k0, p.keep_thr);
-          const bool kp2 = dropout_keep(p.seed, (hb + q) * Lp + k1, p.keep_thr);
-          const bool kp3 = dropout_keep(p.seed, (hb + q + 1) * Lp + k1, p.keep_thr);
+          const bool kp0 = dropout_keep(dseed, (hb + q) * Lp + k0, p.keep_thr);
+          const bool kp1 = dropout_keep(dseed, (hb + q + 1) * Lp + k0, p.keep_thr);
+          const bool kp2 = dropout_keep(dseed, (hb + q) * Lp + k1, p.keep_thr);
+          const bool kp3 = dropout_keep(dseed, (hb + q + 1) * Lp + k1, p.keep_thr);
           dpp[0] = kp0 ? dpp[0] * p.inv_keep : 0.f; pd[0] = kp0 ? pd[0] * p.inv_keep : 0.f;
           dpp[1] = kp1 ? dpp[1] * p.inv_keep : 0.f; pd[1] = kp1 ? pd[1] * p.inv_keep : 0.f;
           dpp[2] = kp2 ? dpp[2] * p.inv_keep : 0.f; pd[2] = kp2 ? pd[2] * p.inv_keep : 0.f;
@@ -492,6 +494,7 @@ __global__ void __launch_bounds__(NT * 16) attn_bwd_smem_kernel(const BwdParams 
   const int b = blockIdx.y, h = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int L = p.L;
+  const uint32_t dseed = site_seed(p.seed);
   const size_t row0 = (size_t)b * L;
   const bf16* base = p.qkv + row0 * p.ld_qkv + h * D;
   load_tile(Qs, base, p.ld_qkv, LP, L);
@@ -583,8 +586,8 @@ __global__ void __launch_bounds__(NT * 16) attn_bwd_smem_kernel(const BwdParams 
         float pd[4] = {pr[0], pr[1], pr[2], pr[3]};
         if (drop) {
           bool k0, k1, k2, k3;
-          dropout_pair(p.seed, rb0 + k, p.keep_thr, k0, k1);
-          dropout_pair(p.seed, rb1 + k, p.keep_thr, k2, k3);
+          dropout_pair(dseed, rb0 + k, p.keep_thr, k0, k1);
+          dropout_pair(dseed, rb1 + k, p.keep_thr, k2, k3);
           dpp[0] = k0 ? dpp[0] * p.inv_keep : 0.f; pd[0] = k0 ? pd[0] * p.inv_keep : 0.f;
           dpp[1] = k1 ? dpp[1] * p.inv_keep : 0.f; pd[1] = k1 ? pd[1] * p.inv_keep : 0.f;
           dpp[2] = k2 ? dpp[2] * p.inv_keep : 0.f; pd[2] = k2 ? pd[2] * p.inv_keep : 0.f;

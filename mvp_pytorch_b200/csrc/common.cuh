@@ -138,8 +138,11 @@ static __device__ uint32_t g_dropout_epoch = 0;
 
 // One 32-bit hash serves TWO neighbouring elements (idx, idx^1): 16 random bits each, compared
 // against keep_thr >> 16 (p_keep resolution 1.5e-5).  Halves the integer work of the dropout sites.
+// Kernels mix the epoch into their site seed ONCE (site_seed) and pass the result to the helpers below:
+// reading the epoch word inside dropout_bits put a dependent global load in front of every hash.
+__device__ __forceinline__ uint32_t site_seed(uint32_t seed) { return seed + g_dropout_epoch * 0x85EBCA6Bu; }
 __device__ __forceinline__ uint32_t dropout_bits(uint32_t seed, uint32_t idx) {
-  return hash32((idx >> 1) * 0x9E3779B9u + seed + g_dropout_epoch * 0x85EBCA6Bu);
+  return hash32((idx >> 1) * 0x9E3779B9u + seed);
 }
 __device__ __forceinline__ bool dropout_keep(uint32_t seed, uint32_t idx, uint32_t keep_thr) {
   // keep_thr = floor(keep_prob * 2^32)

@@ -381,6 +381,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     constexpr int kChunks = kHalf / 32;  // 32-column TMEM loads per tile per warp
     constexpr int kChunksPerStore = F32OUT ? 1 : 2;
     const bool bias_vec = p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
+    const uint32_t dseed = p.use_dropout ? site_seed(p.seed) : 0u;
     int local = 0;
     bool store_pending = false;
     for (int t = cta_first; t < p.num_tiles; t += cta_stride, ++local) {
@@ -522,7 +523,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (p.use_dropout) {
           const uint32_t base = (uint32_t)m * (uint32_t)p.N + (uint32_t)n0;  // multiple of 8 when N % 8 == 0
 #pragma unroll
-          for (int u = 0; u < 4; ++u) dropout8(v + u * 8, p.seed, base + u * 8, p.keep_thr, p.inv_keep);
+          for (int u = 0; u < 4; ++u) dropout8(v + u * 8, dseed, base + u * 8, p.keep_thr, p.inv_keep);
         }
         if (p.residual != nullptr && row_ok && lead) {
 #pragma unroll

@@ -47,7 +47,8 @@ embed_ln_fwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__
                     const bf16* __restrict__ pos, const bf16* __restrict__ type, const bf16* __restrict__ gamma,
                     const bf16* __restrict__ beta, bf16* __restrict__ y, RowMap ymap, bf16* __restrict__ pre,
                     float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int L, int H, float eps,
-                    int vocab, int max_pos, int n_types, uint32_t keep_thr, float inv_keep, uint32_t seed) {
+                    int vocab, int max_pos, int n_types, uint32_t keep_thr, float inv_keep, uint32_t seed_) {
+  const uint32_t seed = site_seed(seed_);
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -106,8 +107,9 @@ __global__ void __launch_bounds__(128)
 ln_fwd_kernel(const bf16* __restrict__ x_in, const bf16* __restrict__ residual, bf16* __restrict__ pre_out,
               const bf16* __restrict__ gamma, const bf16* __restrict__ beta, bf16* __restrict__ y, RowMap ymap,
               float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int H, float eps,
-              uint32_t in_keep_thr, float in_inv_keep, uint32_t in_seed, uint32_t keep_thr, float inv_keep,
-              uint32_t seed) {
+              uint32_t in_keep_thr, float in_inv_keep, uint32_t in_seed_, uint32_t keep_thr, float inv_keep,
+              uint32_t seed_) {
+  const uint32_t in_seed = site_seed(in_seed_), seed = site_seed(seed_);
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -255,7 +257,8 @@ ln_bwd_kernel(const bf16* __restrict__ dy, RowMap dymap, const bf16* __restrict_
               const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const bf16* __restrict__ gamma,
               bf16* __restrict__ dx, bf16* __restrict__ dx_drop, float* __restrict__ dgamma,
               float* __restrict__ dbeta, float* __restrict__ dbias, int rows, int H, uint32_t out_keep_thr,
-              float out_inv_keep, uint32_t out_seed, uint32_t in_keep_thr, float in_inv_keep, uint32_t in_seed) {
+              float out_inv_keep, uint32_t out_seed_, uint32_t in_keep_thr, float in_inv_keep, uint32_t in_seed_) {
+  const uint32_t out_seed = site_seed(out_seed_), in_seed = site_seed(in_seed_);
   extern __shared__ float cta_acc[];  // [3][H]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nchunk = H >> 3;
