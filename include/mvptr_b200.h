@@ -59,6 +59,8 @@ int mvptr_profile_collect(const char** names_host, double* work_host, float* ms_
  *   pre_act[m,n] = bf16(v)                       (saved for backward)
  *   v = act(v)            act: 0 none, 1 erf-GELU, 2 tanh
  *   v *= gelu'(gelu_grad_of[m,n])                (backward of act=1)
+ *   colsum[n] += sum_m bf16(v)                   (fp32 atomics; only with gelu_grad_of: the bias gradient of
+ *                                                 the GELU layer, i.e. the column sums of exactly what is stored)
  *   v = keep(seed, m*N+n) ? v/keep_prob : 0      (dropout, p_drop > 0)
  *   v += residual[m,n]
  *   D[m,n] = v   or   D[m,n] += v  (accumulate=1: TMA reduce-add; required when split_k > 1)
@@ -86,6 +88,7 @@ typedef struct {
   uint32_t seed;
   int block_n;  /* 0 = auto, else 128 or 256 */
   int cta_pair; /* 0 = auto, 1 = single-CTA tiles (128 x block_n), 2 = CTA-pair tiles (256 x 256, cta_group::2) */
+  float* colsum; /* fp32 [N] (+=), nullable; requires gelu_grad_of and the lean GELU' epilogue (see mvptr_gemm) */
 } mvptr_gemm_args;
 
 int mvptr_gemm(const mvptr_gemm_args* args, void* stream);

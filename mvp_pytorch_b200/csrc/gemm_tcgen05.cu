@@ -38,6 +38,7 @@ struct Params {
   int act;
   const bf16* gelu_grad_of;
   const bf16* residual;
+  float* colsum;
   int ld_aux;
   float inv_keep;
   uint32_t keep_thr;
@@ -193,16 +194,18 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool 
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <int BN, int CTAS = 1, bool DUAL = false>
+template <int BN, int CTAS = 1, int SLABS = 1>  // SLABS: TMA slabs per epilogue warp (1 plain, 2 DUAL stores, 4 GELU' dgrad)
 struct SmemLayout {
+  static constexpr bool DUAL = SLABS >= 2;
   static constexpr int kABytes = BM * BK * 2;            // 16 KB (per CTA)
   static constexpr int kBBytes = (BN / CTAS) * BK * 2;   // a CTA pair splits the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   // DUAL (two outputs per tile: pre-activation and activation) pays for its second set of store slabs
   // with one pipeline stage
-  static constexpr int kStages = DUAL ? ((kStageBytes == 48 * 1024) ? 3 : 5) : ((kStageBytes == 48 * 1024) ? 4 : 6);
-  static constexpr int kOutBytes = kEpiWarps * kSlabBytes * (DUAL ? 2 : 1);  // TMA-store slab(s) per epilogue warp
-  static constexpr int kBarBytes = 256;
+  // (a pair's 32 KB stage is a 256x256x64 block = 1024 tensor cycles, so even 3 stages look 1.6 us ahead)
+  static constexpr int kStages = SLABS == 4 ? 3 : DUAL ? ((kStageBytes == 48 * 1024) ? 3 : 5) : ((kStageBytes == 48 * 1024) ? 4 : 6);
+  static constexpr int kOutBytes = kEpiWarps * kSlabBytes * SLABS;
+  static constexpr int kBarBytes = 512;  // pipeline + accumulator barriers, TMEM slot, 16 epilogue load barriers
   static constexpr int kTotal = kStages * kStageBytes + kOutBytes + kBarBytes + 1024;  // + alignment slack
 };
 
@@ -221,9 +224,10 @@ template <int BN, bool A_MN, bool B_MN, bool F32OUT, int CTAS, int EPI = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmP, const Params p) {
-  constexpr bool DUAL = EPI == 2;
-  constexpr bool LEAN = EPI != 0;
-  using L = SmemLayout<BN, CTAS, DUAL>;
+  constexpr bool DUAL = EPI == 2;  // two store slabs per epilogue warp
+  constexpr bool LEAN = EPI == 1 || EPI == 2;
+  constexpr bool GGRAD = EPI == 3;  // D = bf16(acc * gelu'(P)), colsum += column sums; P arrives by TMA through tmP
+  using L = SmemLayout<BN, CTAS, GGRAD ? 4 : DUAL ? 2 : 1>;
   constexpr bool kPair = CTAS == 2;
   const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
@@ -236,6 +240,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint8_t* out_stage = smem + kStages * L::kStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + L::kOutBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kAccStages);
+  const uint32_t load_bar = smem_u32(bars + 2 * kStages + 2 * kAccStages + 2);  // [8 epilogue warps][2 sets][2 boxes] (GGRAD)
 
   const uint32_t full_bar = smem_u32(bars);
   const uint32_t empty_bar = smem_u32(bars + kStages);
@@ -260,6 +265,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(tfull_bar + 8 * i, 1);
       mbar_init(tempty_bar + 8 * i, kEpiWarps * CTAS);
     }
+    if constexpr (GGRAD)
+      for (int i = 0; i < 4 * kEpiWarps; ++i) mbar_init(load_bar + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -395,6 +402,91 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const bool row_ok = m < p.M;
       const bool lead = (split == 0);  // bias / residual are added by the first K-split only
       const int n_base = n_blk * BN + hf * kHalf;
+      if constexpr (GGRAD) {
+        // Two slab SETS per warp (tile parity), two 64-column boxes per set.  The pre-activation boxes of tile
+        // i+1 are requested by TMA while tile i is still being multiplied, so their HBM latency never sits in
+        // front of an accumulator that is already waiting; each box is multiplied in place, column-summed and
+        // stored from the same slab.
+        auto slab_of = [&](int set, int bx) { return out_stage + (((set * 2 + bx) * kEpiWarps) + (warp - 4)) * kSlabBytes; };
+        const uint32_t lb = load_bar + (warp - 4) * 32;  // [set][box]
+        auto request = [&](int set, int nb, int mb) {      // lane 0 only
+#pragma unroll
+          for (int bx = 0; bx < 2; ++bx)
+            if (nb + 64 * bx < p.N) {
+              mbar_expect_tx(lb + 8 * (set * 2 + bx), kSlabBytes);
+              tma_load_2d(smem_u32(slab_of(set, bx)), &tmP, lb + 8 * (set * 2 + bx), nb + 64 * bx, mb);
+            }
+        };
+        const int set = local & 1;
+        const uint32_t lph = (local >> 1) & 1u;
+        if (local == 0 && lane == 0) request(0, n_base, m_base + q * 32);
+        mbar_wait(tfull_bar + 8 * as, aph);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + hf * kHalf;
+        uint32_t rbuf[2][32];
+        if (n_base < p.N) tc_ld32(t_row, rbuf[0]);
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          const int n0 = n_base + c * 32;
+          if (n0 >= p.N) break;
+          const int bx = c >> 1, h = c & 1;
+          uint8_t* sl = slab_of(set, bx);
+          if (h == 0) mbar_wait(lb + 8 * (set * 2 + bx), lph);
+          tc_wait_ld();
+          if (c + 1 < kChunks && n0 + 32 < p.N) tc_ld32(t_row + (c + 1) * 32, rbuf[(c + 1) & 1]);
+          uint8_t* row = sl + lane * 128;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            bf16x8* unit = reinterpret_cast<bf16x8*>(row + (((h * 4 + u) ^ (lane & 7)) << 4));
+            float x[8], o[8];
+            unpack8(*unit, x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(rbuf[c & 1][u * 8 + j]) * gelu_erf_grad(x[j]);
+            *unit = pack8(o);
+          }
+          if (h == 1) {
+            __syncwarp();
+            if (p.colsum != nullptr) {
+              // lane l owns columns 2l, 2l+1 of the box: 32 conflict-free 4-byte reads down the rows
+              float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+              for (int r = 0; r < 32; ++r) {
+                const float2 v2 = __bfloat1622float2(*reinterpret_cast<const bf162*>(
+                    sl + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + ((lane & 3) << 2)));
+                s0 += v2.x;
+                s1 += v2.y;
+              }
+              atomicAdd(p.colsum + n_base + 64 * bx + 2 * lane, s0);
+              atomicAdd(p.colsum + n_base + 64 * bx + 2 * lane + 1, s1);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmD, smem_u32(sl), n_base + 64 * bx, m_base + q * 32);
+              tma_commit();
+              if (bx == 0) {
+                // the other set was last stored one tile ago: everything but the store just issued has been
+                // read out of shared memory -> its slabs can take the next tile's pre-activation boxes
+                const int tn = t + cta_stride;
+                if (tn < p.num_tiles) {
+                  tma_wait_read<1>();
+                  const int mn2 = tn % tiles_mn;
+                  const int mb2 = mn2 / p.n_tiles, nb2 = mn2 - mb2 * p.n_tiles;
+                  request(set ^ 1, nb2 * BN + hf * kHalf, mb2 * kTileM + (int)cta_rank * BM + q * 32);
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (kPair && !leader) mbar_arrive_remote(tempty_bar + 8 * as, 0);
+          else mbar_arrive(tempty_bar + 8 * as);
+        }
+        store_pending = true;
+        continue;
+      }
       mbar_wait(tfull_bar + 8 * as, aph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + hf * kHalf;
@@ -625,7 +717,8 @@ template <int BN, bool A_MN, bool B_MN, bool F32OUT, int CTAS, int EPI = 0>
 static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, const Params& p,
                   cudaStream_t stream, const CUtensorMap* pre = nullptr) {
   auto kern = gemm_kernel<BN, A_MN, B_MN, F32OUT, CTAS, EPI>;
-  constexpr int smem = SmemLayout<BN, CTAS, EPI == 2>::kTotal;
+  constexpr int smem = SmemLayout<BN, CTAS, EPI == 3 ? 4 : EPI == 2 ? 2 : 1>::kTotal;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool configured = false;  // per template instantiation
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -724,6 +817,7 @@ extern "C" int mvptr_gemm(const mvptr_gemm_args* g, void* stream_) {
   p.act = g->act;
   p.gelu_grad_of = reinterpret_cast<const bf16*>(g->gelu_grad_of);
   p.residual = reinterpret_cast<const bf16*>(g->residual);
+  p.colsum = g->colsum;
   p.ld_aux = g->ld_aux;
   p.use_dropout = g->p_drop > 0.f;
   p.inv_keep = p.use_dropout ? 1.0f / (1.0f - g->p_drop) : 1.0f;
@@ -751,13 +845,24 @@ extern "C" int mvptr_gemm(const mvptr_gemm_args* g, void* stream_) {
                     g->alpha == 1.0f && !g->accumulate && !g->gelu_grad_of && !g->residual && !p.use_dropout &&
                     (!g->pre_act || (reinterpret_cast<uintptr_t>(g->pre_act) & 15) == 0);
   const bool dual = lean && g->pre_act;
+  // dgrad of the GELU layer (B MN-major): acc * gelu'(pre) [+ bias-gradient column sums] with the
+  // pre-activation tile fetched by TMA
+  const bool ggrad = g->gelu_grad_of && !g->a_mn && g->b_mn && !g->d_is_f32 && split == 1 && bn == 256 && ctas == 2 &&
+                     !g->bias && g->act == 0 && !g->pre_act && !g->residual && !p.use_dropout && g->alpha == 1.0f &&
+                     !g->accumulate && (g->N % 64) == 0 && (reinterpret_cast<uintptr_t>(g->gelu_grad_of) & 15) == 0;
+  if (g->colsum && !ggrad) MVPTR_FAIL(MVPTR_ERR_ARG, "gemm: colsum needs the lean GELU' epilogue (see header)");
   CUtensorMap tp;
+  if (ggrad) {
+    rc = make_map(&tp, g->gelu_grad_of, false, g->N, g->M, (uint64_t)g->ld_aux * 2, 64, 32);
+    if (rc) return rc;
+  }
   if (dual) {
     rc = make_map(&tp, g->pre_act, false, g->N, g->M, (uint64_t)g->ld_aux * 2, 64, 32);
     if (rc) return rc;
   }
   static const char* kNames[4] = {"gemm[k,k]", "gemm[k,mn]", "gemm[mn,k]", "gemm[mn,mn]"};
   MVPTR_PROF(kNames[(g->a_mn ? 2 : 0) | (g->b_mn ? 1 : 0)], 2.0 * g->M * g->N * g->K, stream);
+  if (ggrad) return launch<256, false, true, false, 2, 3>(ta, tb, td, p, stream, &tp);
   if (dual) {
     if (ctas == 2) return launch<256, false, false, false, 2, 2>(ta, tb, td, p, stream, &tp);
     return launch<256, false, false, false, 1, 2>(ta, tb, td, p, stream, &tp);

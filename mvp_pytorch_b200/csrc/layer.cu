@@ -99,13 +99,22 @@ extern "C" int mvptr_layer_bwd(const mvptr_layer_args* a, void* stream) {
                    a->g_ln2_b, a->g_b_o2, M, H, 0.f, 0, a->p_hidden, a->seed2, s));
   const void* dY2 = drop ? a->dpre2d : a->dpre2;
   TRY(wgrad(dY2, H, a->inter, I, H, I, M, a->g_w_o2, s));
-  {  // dinter = dY2 . W_o2 (plain epilogue), then dpre_g = dinter * gelu'(pre_g) fused with db_i
+  // ---- BertIntermediate: dpre_g = (dY2 . W_o2) * gelu'(pre_g), db_i += column sums -- both in the dgrad GEMM's
+  // epilogue (pre_g tiles arrive by TMA); MVPTR_GELU_BWD_FUSED=0 restores the separate HBM pass for A/B runs
+  {
+    static const bool fused = !(getenv("MVPTR_GELU_BWD_FUSED") && atoi(getenv("MVPTR_GELU_BWD_FUSED")) == 0);
     mvptr_gemm_args g = gemm_base(dY2, H, a->w_o2, I, a->dpre_g, I, M, I, H);
     g.b_mn = 1;
-    TRY(mvptr_gemm(&g, s));
+    if (fused && (I % 64) == 0 && M > 128) {
+      g.gelu_grad_of = a->pre_g;
+      g.ld_aux = I;
+      g.colsum = a->g_b_i;
+      TRY(mvptr_gemm(&g, s));
+    } else {
+      TRY(mvptr_gemm(&g, s));
+      TRY(mvptr_gelu_bwd_colsum(a->dpre_g, a->pre_g, a->dpre_g, a->g_b_i, M, I, s));
+    }
   }
-  // ---- BertIntermediate
-  TRY(mvptr_gelu_bwd_colsum(a->dpre_g, a->pre_g, a->dpre_g, a->g_b_i, M, I, s));
   TRY(wgrad(a->dpre_g, I, a->a1, H, I, H, M, a->g_w_i, s));
   {  // da1 = dpre_g . W_i + dpre2 (residual branch)
     mvptr_gemm_args g = gemm_base(a->dpre_g, I, a->w_i, H, a->da1, H, M, H, I);

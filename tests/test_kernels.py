@@ -81,6 +81,35 @@ def test_gemm_epilogues(lib):
     assert_close(o3[~dropped], raw[~dropped] / 0.9, 3e-3, 3e-3, "kept")
 
 
+@pytest.mark.parametrize("M,N", [(515, 3072), (1000, 320), (4100, 512)])
+def test_gemm_lean_gelu_epilogues(lib, M, N):
+    """The lean tcgen05 epilogues of the FFN: bias+GELU (single store), bias+GELU with the pre-activation
+    saved (DUAL TMA stores, CTA pairs) and the dgrad epilogue acc * gelu'(pre) with the fused bias-gradient
+    column sums (pre tiles fetched by TMA).  N = 320 leaves a half-empty 256-wide tile, M a ragged row tile."""
+    K = 768
+    A, B, bias = rnd(M, K, scale=0.5, seed=1), rnd(N, K, scale=0.05, seed=2), rnd(N, seed=3)
+    z = A.float() @ B.float().t() + bias.float()
+    out = torch.empty(M, N, device="cuda", dtype=BF16)
+    lib.gemm(A, B, out, M, N, K, lda=K, ldb=K, ldd=N, bias=bias, act="gelu")
+    assert_close(out, F.gelu(z), 1e-2, 2e-2, "lean gelu")
+    for pair in (1, 2):
+        out2 = torch.zeros(M, N, device="cuda", dtype=BF16); pre = torch.zeros_like(out2)
+        lib.gemm(A, B, out2, M, N, K, lda=K, ldb=K, ldd=N, bias=bias, act="gelu", pre_act=pre, ld_aux=N, cta_pair=pair)
+        assert_close(pre, z, 1e-2, 2e-2, f"dual pre (cta_pair={pair})")
+        assert torch.equal(out2, out), "dual and single-store GELU tiles must agree bit for bit"
+    # dgrad: dX[M, N] = dY[M, K2] . W[K2, N] (W stored [K2][N]: MN-major B), times gelu'(pre), column sums
+    K2 = 256
+    dY, W = rnd(M, K2, scale=0.5, seed=5), rnd(K2, N, scale=0.05, seed=6)
+    dx = torch.zeros(M, N, device="cuda", dtype=BF16)
+    cs = torch.full((N,), 0.5, device="cuda", dtype=F32)  # accumulates (+=)
+    lib.gemm(dY, W, dx, M, N, K2, lda=K2, ldb=N, ldd=N, b_mn=True, gelu_grad_of=pre, ld_aux=N, colsum=cs)
+    x = pre.float().requires_grad_(True)
+    F.gelu(x).sum().backward()
+    ref = (dY.float() @ W.float()) * x.grad
+    assert_close(dx, ref, 1e-2, 2e-2, "acc * gelu'(pre)")
+    assert_close(cs, 0.5 + dx.float().sum(0), 1e-3, 2e-2, "fused bias-gradient column sums")
+
+
 # ------------------------------------------------------------------------------------
 def ln_ref(x, w, b, eps):
     mu = x.mean(-1, keepdim=True)
