@@ -30,29 +30,52 @@ __device__ __forceinline__ float block_reduce_max(float v, float* red) {
 // CrossEntropyLoss(ignore_index) over fp32 logits [n, V] (pitch ld)
 // modeling_vlbert.py:1229,1235,1249 ; one block per row
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+// Forward: the whole row is staged in registers by 16-byte loads (512 threads x NV float4), so the logits are
+// read from HBM exactly once and every load of the row is in flight at the same time.  Rows whose label is
+// ignored (the padding slots of the fixed-capacity masked-LM selection) are skipped.
+template <int NV>
+__global__ void __launch_bounds__(512)
 ce_fwd_kernel(const float* __restrict__ logits, int ld, const int64_t* __restrict__ labels, int V, int ignore_index,
               float* __restrict__ row_lse, float* __restrict__ loss_sum, float* __restrict__ n_valid) {
-  __shared__ float red[8];
+  __shared__ float red[16];
   const int r = blockIdx.x;
+  const long long lab = labels[r];
+  if (lab == ignore_index || lab < 0 || lab >= V) {  // block-uniform
+    if (threadIdx.x == 0) row_lse[r] = 0.f;
+    return;
+  }
   const float* x = logits + (size_t)r * ld;
-  float mx = -INFINITY;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) mx = fmaxf(mx, x[i]);
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  const int nvec = V >> 2;
+  float4 buf[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = threadIdx.x + k * 512;
+    buf[k] = i < nvec ? x4[i] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  }
+  const int ti = 4 * nvec + threadIdx.x;
+  const float tail = ti < V ? x[ti] : -INFINITY;  // V % 4 leftover elements
+  float mx = tail;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) mx = fmaxf(mx, fmaxf(fmaxf(buf[k].x, buf[k].y), fmaxf(buf[k].z, buf[k].w)));
   mx = block_reduce_max(mx, red);
-  float s = 0.f;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) s += __expf(x[i] - mx);
+  const float m2 = mx * 1.4426950408889634f;
+  float s = ex2_approx(fmaf(tail, 1.4426950408889634f, -m2));
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+    s += ex2_approx(fmaf(buf[k].x, 1.4426950408889634f, -m2)) + ex2_approx(fmaf(buf[k].y, 1.4426950408889634f, -m2)) +
+         ex2_approx(fmaf(buf[k].z, 1.4426950408889634f, -m2)) + ex2_approx(fmaf(buf[k].w, 1.4426950408889634f, -m2));
   s = block_reduce_sum(s, red);
   if (threadIdx.x == 0) {
     const float lse = mx + logf(s);
     row_lse[r] = lse;
-    const long long lab = labels[r];
-    if (lab != ignore_index && lab >= 0 && lab < V) {
-      atomicAdd(loss_sum, lse - x[lab]);
-      atomicAdd(n_valid, 1.0f);
-    }
+    atomicAdd(loss_sum, lse - x[lab]);
+    atomicAdd(n_valid, 1.0f);
   }
 }
-// dlogits = (softmax - onehot) * (*gscale) / n_valid     -> bf16 [n, ld_d]
+
+// Backward: dlogits = (softmax - onehot) * g / n_valid as bf16, 8 columns (two 16-byte loads, one 16-byte
+// store) per thread and step.
 __global__ void __launch_bounds__(256)
 ce_bwd_kernel(const float* __restrict__ logits, int ld, const int64_t* __restrict__ labels, int V, int ignore_index,
               const float* __restrict__ row_lse, const float* __restrict__ n_valid, const float* __restrict__ gscale,
@@ -64,11 +87,26 @@ ce_bwd_kernel(const float* __restrict__ logits, int ld, const int64_t* __restric
   const bool valid = lab != ignore_index && lab >= 0 && lab < V;
   const float nv = *n_valid;
   const float sc = valid && nv > 0.f ? (gscale ? *gscale : 1.f) / nv : 0.f;
-  const float lse = row_lse[r];
-  for (int i = threadIdx.x; i < ld_d; i += blockDim.x) {
-    float g = 0.f;
-    if (i < V) g = (__expf(x[i] - lse) - (i == lab ? 1.f : 0.f)) * sc;
-    d[i] = __float2bfloat16(g);
+  const float l2 = row_lse[r] * 1.4426950408889634f;
+  const bool vec = (ld & 3) == 0 && (ld_d & 7) == 0 && ld >= ld_d;  // whole 8-column groups are readable
+  if (vec) {
+    for (int i = threadIdx.x * 8; i < ld_d; i += blockDim.x * 8) {
+      float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (valid) {
+        const float4 a = *reinterpret_cast<const float4*>(x + i), b = *reinterpret_cast<const float4*>(x + i + 4);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          g[j] = i + j < V ? (ex2_approx(fmaf(v[j], 1.4426950408889634f, -l2)) - (i + j == lab ? 1.f : 0.f)) * sc : 0.f;
+      }
+      *reinterpret_cast<bf16x8*>(d + i) = pack8(g);
+    }
+  } else {
+    for (int i = threadIdx.x; i < ld_d; i += blockDim.x) {
+      float g = 0.f;
+      if (i < V && valid) g = (__expf(x[i] - row_lse[r]) - (i == lab ? 1.f : 0.f)) * sc;
+      d[i] = __float2bfloat16(g);
+    }
   }
 }
 
@@ -322,7 +360,17 @@ extern "C" int mvptr_ce_fwd(const float* logits, int ld, const int64_t* labels, 
                             float* row_lse, float* loss_sum, float* n_valid, void* stream) {
   MVPTR_PROF("ce_fwd", 4.0*n*V, stream);
   if (n <= 0) return 0;
-  ce_fwd_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(logits, ld, labels, V, ignore_index, row_lse, loss_sum, n_valid);
+  if ((ld & 3) || (reinterpret_cast<uintptr_t>(logits) & 15))
+    MVPTR_FAIL(MVPTR_ERR_ARG, "ce_fwd: logits must be 16-byte aligned with a pitch that is a multiple of 4");
+  const int per_thread = ((V >> 2) + 511) / 512;  // float4 per thread
+  if (per_thread <= 4)
+    ce_fwd_kernel<4><<<n, 512, 0, (cudaStream_t)stream>>>(logits, ld, labels, V, ignore_index, row_lse, loss_sum, n_valid);
+  else if (per_thread <= 16)
+    ce_fwd_kernel<16><<<n, 512, 0, (cudaStream_t)stream>>>(logits, ld, labels, V, ignore_index, row_lse, loss_sum, n_valid);
+  else if (per_thread <= 48)
+    ce_fwd_kernel<48><<<n, 512, 0, (cudaStream_t)stream>>>(logits, ld, labels, V, ignore_index, row_lse, loss_sum, n_valid);
+  else
+    MVPTR_FAIL(MVPTR_ERR_UNSUPPORTED, "ce_fwd: more than 98304 classes per row");
   MVPTR_CHECK_LAUNCH("ce_fwd");
   return 0;
 }

@@ -420,12 +420,14 @@ embed_word_bwd_kernel(const bf16* __restrict__ dpre, const int64_t* __restrict__
 __global__ void __launch_bounds__(128)
 embed_pos_type_bwd_kernel(const bf16* __restrict__ dpre, const int64_t* __restrict__ type_ids,
                           float* __restrict__ dpos, float* __restrict__ dtype, int B, int L, int H, int n_types) {
-  // block = one position p; thread = 8 columns; loop over the batch
+  // block = one position p and one slice of the batch (grid.y); thread = 8 columns
   const int p = blockIdx.x;
+  const int b_per = (B + gridDim.y - 1) / gridDim.y;
+  const int b_lo = blockIdx.y * b_per, b_hi = min(B, b_lo + b_per);
   for (int col = threadIdx.x * 8; col < H; col += blockDim.x * 8) {
     float accp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     float acct[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};
-    for (int b = 0; b < B; ++b) {
+    for (int b = b_lo; b < b_hi; ++b) {
       const int r = b * L + p;
       float v[8];
       unpack8(*reinterpret_cast<const bf16x8*>(dpre + (size_t)r * H + col), v);
@@ -706,7 +708,9 @@ extern "C" int mvptr_embed_bwd(const void* dpre, const int64_t* ids, const int64
   embed_word_bwd_kernel<<<(rows + 3) / 4, 128, 0, (cudaStream_t)stream>>>((const bf16*)dpre, ids, dword, rows, H,
                                                                           vocab, padding_idx);
   MVPTR_CHECK_LAUNCH("embed_word_bwd");
-  embed_pos_type_bwd_kernel<<<L, 128, 0, (cudaStream_t)stream>>>((const bf16*)dpre, type_ids, dpos, dtype, B, L, H,
+  // L alone (40 / 20 blocks) would leave most SMs idle: also split the batch
+  const int bsplit = B >= 64 ? 16 : (B >= 8 ? 4 : 1);
+  embed_pos_type_bwd_kernel<<<dim3(L, bsplit), 128, 0, (cudaStream_t)stream>>>((const bf16*)dpre, type_ids, dpos, dtype, B, L, H,
                                                                  n_types);
   MVPTR_CHECK_LAUNCH("embed_pos_type_bwd");
   return 0;

@@ -34,10 +34,10 @@ class GraphedTrainStep:
         dev = next(model.parameters()).device
         self.static = {k: v.to(dev).clone() for k, v in sample_batch.items()}
         if mlm_capacity is None and "masked_lm_labels_a" in sample_batch:
-            # 1.35x the sample's count (BERT masking is binomial: > 10 sigma at batch 256), 256-row granules
+            # 1.2x the sample's count + 64 (BERT masking is binomial: ~8 sigma at batch 256), 128-row granules
             n_txt = int((sample_batch["masked_lm_labels_a"] > -1).sum())
             n_vis = int((sample_batch["masked_lm_labels_b"] > -1).sum())
-            mlm_capacity = (_round_up(max(n_vis * 1.35, n_vis + 64), 256), _round_up(max(n_txt * 1.35, n_txt + 64), 256))
+            mlm_capacity = (_round_up(n_vis * 1.2 + 64, 128), _round_up(n_txt * 1.2 + 64, 128))
         if mlm_capacity is not None:
             model.mlm_capacity = tuple(int(c) for c in mlm_capacity)
             model.mlm_overflow = torch.zeros((), dtype=torch.bool, device=dev)
