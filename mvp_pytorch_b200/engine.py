@@ -564,6 +564,58 @@ class BCEFn(Function):
         return decoder_backward(rt, t, dlogits, wname, n_out, bias_name), None, None, None, None, None, None
 
 
+class LinearFn(Function):
+    """nn.Linear on an arbitrary [n, K] activation: y = act(x W^T + b), act in {None, 'relu', 'tanh'}; or, with
+    kn=True, y = x P for a projection stored [K, N] (txt_proj / vis_proj, modeling_vlbert.py:525-526).  The thin
+    task heads (classifier MLPs :1730-1744, single_mapping :1991-1995) are built from it; N and K must be
+    multiples of 8 (narrower outputs go through SmallHeadFn)."""
+
+    @staticmethod
+    def forward(ctx, x, rt, wname, bname, act, kn, anchor):
+        x = x.to(BF16).contiguous()
+        n, K = x.shape
+        a = rt.arena
+        W = a.w(wname)
+        N = W.shape[1] if kn else W.shape[0]
+        y = torch.empty(n, N, device=x.device, dtype=BF16)
+        bias = a.w(bname) if bname is not None else None
+        if kn:
+            rt.gemm(x, W, y, n, N, K, lda=K, ldb=N, ldd=N, b_mn=True, bias=bias)
+        else:
+            rt.gemm(x, W, y, n, N, K, lda=K, ldb=K, ldd=N, bias=bias, act="tanh" if act == "tanh" else None)
+        if act == "relu":
+            y = torch.relu_(y)
+        ctx.rt, ctx.s = rt, (x, wname, bname, act, kn, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        rt = ctx.rt
+        x, wname, bname, act, kn, y = ctx.s
+        n, K = x.shape
+        N = y.shape[1]
+        a = rt.arena
+        W = a.w(wname)
+        if act == "relu":
+            dpre = (dy * (y > 0)).to(BF16).contiguous()
+        elif act == "tanh":
+            yf = y.float()
+            dpre = (dy.float() * (1.0 - yf * yf)).to(BF16)
+        else:
+            dpre = dy.to(BF16).contiguous()
+        if bname is not None:
+            rt.call("mvptr_colsum", dpre, N, a.g(bname), n, N)
+        dx = torch.empty(n, K, device=dy.device, dtype=BF16)
+        if kn:
+            # dP[k, n'] += sum_r x[r, k] dpre[r, n'] ; dx[r, k] = sum_n' dpre[r, n'] P[k, n']
+            rt.gemm(x, dpre, a.g(wname), K, N, n, lda=K, ldb=N, ldd=N, a_mn=True, b_mn=True, accumulate=True)
+            rt.gemm(dpre, W, dx, n, K, N, lda=N, ldb=N, ldd=K)
+        else:
+            wgrad(rt, dpre, N, x, K, N, K, n, a.g(wname))
+            dgrad(rt, dpre, N, W, K, n, N, K, dx)
+        return dx, None, None, None, None, None, None
+
+
 class SmallHeadFn(Function):
     """x W^T + b with a handful of outputs (ITM / retrieval classifier, modeling_vlbert.py:1247,
     :1680, :1708) -> fp32 logits."""

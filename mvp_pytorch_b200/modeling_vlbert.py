@@ -63,6 +63,25 @@ def _mask2d(mask, like):
     raise NotImplementedError  # same as the reference for any other rank (:435, :451)
 
 
+def negative_sampling_probs(sim_mat, logit):
+    """Row-wise sampling distributions of hn_mod='sample' (:535-540): softmax over logit * sim with the
+    matched pair pushed down by 10000 -- (text -> image, image -> text).  [B, B] fp32, plumbing-sized."""
+    n = sim_mat.shape[0]
+    masked = (logit * sim_mat) - 10000 * torch.eye(n, dtype=sim_mat.dtype, device=sim_mat.device)
+    return torch.softmax(masked, dim=1), torch.softmax(masked.t(), dim=1)
+
+
+def sample_negatives(sim_mat, logit):
+    """One multinomial draw per row from negative_sampling_probs: the same two torch.multinomial calls, in
+    the same order, as the reference (:537-540)."""
+    if logit is None:
+        raise ValueError("hn_mod='sample' needs the temperature `logit` (the reference multiplies by it, :536)")
+    p_t2i, p_i2t = negative_sampling_probs(sim_mat.float(), logit)
+    hard_img_index = torch.multinomial(p_t2i, num_samples=1).squeeze(1)
+    hard_txt_index = torch.multinomial(p_i2t, num_samples=1).squeeze(1)
+    return hard_img_index, hard_txt_index
+
+
 class BiBertImgModel(BertPreTrainedModel):
     """Two-stage encoder: uni-modal text / visual encoders, then the cross-modal encoder."""
 
@@ -151,7 +170,7 @@ class BiBertImgModel(BertPreTrainedModel):
             if hn_mod == 'hard':
                 hard_img_index, hard_txt_index = E.hard_negatives(rt, sim_mat.detach())
             elif hn_mod == 'sample':
-                raise NotImplementedError("hn_mod='sample' (multinomial negatives, :535-540) is a listed next step")
+                hard_img_index, hard_txt_index = sample_negatives(sim_mat.detach(), logit)
             else:
                 raise NotImplementedError
             n = B
@@ -239,8 +258,44 @@ class BiBertImgModel(BertPreTrainedModel):
         vis = E.encoder(rt, pf + "vis_encoder", emb, E.mask_additive(rt, mask), nl, anchor)
         return vis, mask, E.ClsProjNormFn.apply(vis, rt, pf + "vis_proj", anchor)
 
-    def forward_joint(self, *args, **kwargs):
-        raise NotImplementedError("forward_joint (two-image input, :725-869) is a listed next step (SURVEY f-3)")
+    def forward_joint(self, input_ids_a, token_type_ids_a=None, attention_mask_a=None, max_tag_length=None,
+                      position_ids_a=None, input_ids_b=None, token_type_ids_b=None, attention_mask_b=None,
+                      position_ids_b2=None, input_ids_b2=None, token_type_ids_b2=None, attention_mask_b2=None,
+                      img_feats2=None, position_ids_b=None, head_mask=None, img_feats=None,
+                      encoder_history_states=None):
+        """Two-image input (:725-869): the text and BOTH images go through stage 1 (the two visual streams
+        as one batch of 2B sequences through the shared vis_encoder), stage 2 runs over
+        [text | regions of image 1 | regions of image 2] -> (sequence_output, pooled_output)."""
+        _check_unsupported(self.config, head_mask, encoder_history_states)
+        rt, pf = self._ctx()
+        rt.begin_forward(self.training)
+        nl = self.config.num_hidden_layers // 2
+        anchor = rt.anchor(self.txt_proj)
+        Lt = int(max_tag_length)
+        txt, mask_a, _ = self.encode_text(input_ids_a, token_type_ids_a, attention_mask_a, position_ids_a)
+        B = txt.shape[0]
+        if token_type_ids_b is None:   # the reference defaults BOTH tag segments to 0 (:745-749)
+            token_type_ids_b = torch.zeros_like(input_ids_b)
+        if token_type_ids_b2 is None:
+            token_type_ids_b2 = torch.zeros_like(input_ids_b2)
+        both = lambda u, v: None if u is None and v is None else torch.cat([u, v], dim=0)
+        if (position_ids_b is None) != (position_ids_b2 is None):
+            raise ValueError("forward_joint: give position ids for both images or for neither")
+        def full_mask(m, ids, feats):  # default: every tag and every region is valid
+            return m if m is not None else torch.ones(ids.shape[0], ids.shape[1] + feats.shape[1], dtype=torch.int64,
+                                                      device=ids.device)
+        mb1, mb2 = full_mask(attention_mask_b, input_ids_b, img_feats), full_mask(attention_mask_b2, input_ids_b2, img_feats2)
+        vis12, mask12, _ = self.encode_image(torch.cat([input_ids_b, input_ids_b2], 0), both(token_type_ids_b, token_type_ids_b2),
+                                             torch.cat([mb1, mb2], 0), torch.cat([img_feats, img_feats2], 0),
+                                             both(position_ids_b, position_ids_b2))
+        vis1, vis2 = vis12[:B], vis12[B:]
+        m1, m2 = mask12[:B].contiguous(), mask12[B:].contiguous()
+        j1 = E.ConcatRowsFn.apply(txt, vis1.contiguous(), Lt, None, None, rt)          # [text | regions 1]
+        joint = E.ConcatRowsFn.apply(j1, vis2.contiguous(), Lt, None, None, rt)        # [... | regions 2]
+        jmask_int = torch.cat([mask_a, m1[:, Lt:], m2[:, Lt:]], dim=1).contiguous()
+        seq = E.encoder(rt, pf + "mul_encoder", joint, E.mask_additive(rt, jmask_int), nl, anchor)
+        pooled = E.ClsDenseFn.apply(seq, rt, pf + "pooler.dense.weight", pf + "pooler.dense.bias", "tanh", anchor)
+        return (seq, pooled)
 
     # ---- stage-2-only entry used by the retrieval scorer ---------------------------------
     def forward_stage2(self, txt, vis, mask_a, mask_b, max_tag_length, row_a, row_b):
@@ -477,7 +532,7 @@ class BiImageBertForRetrieval(BertPreTrainedModel):
     def forward_fine(self, **kw):
         rt = self._prep()
         outputs, _, _ = self.bert(encode_hn=False, **kw)
-        return E.SmallHeadFn.apply(outputs[1], rt, "classifier.weight", "classifier.bias", self.logit_scale)
+        return E.SmallHeadFn.apply(outputs[1], rt, "classifier.weight", "classifier.bias", rt.anchor(self.logit_scale))
 
 
 def _cls_loss(self, logits, labels, soft_label, num_labels):
@@ -497,6 +552,89 @@ def _cls_loss(self, logits, labels, soft_label, num_labels):
     return nn.functional.cross_entropy(logits.view(-1, num_labels), labels.view(-1))
 
 
+def _make_classifier(config, in_features, num_labels, default_in=None):
+    """The classifier variants of :1730-1744 / :1996-2010 as parameter containers with the reference's keys
+    (classifier.weight | classifier.0.weight + classifier.2.weight)."""
+    if hasattr(config, 'classifier'):
+        if not hasattr(config, 'cls_hidden_scale'):
+            config.cls_hidden_scale = 2
+        if config.classifier == 'linear':
+            return _Linear(in_features, num_labels)
+        if config.classifier == 'mlp':
+            hid = config.hidden_size * config.cls_hidden_scale
+            return nn.Sequential(_Linear(in_features, hid), nn.ReLU(), _Linear(hid, num_labels))
+        raise NotImplementedError(f"classifier={config.classifier!r}")
+    return _Linear(default_in if default_in is not None else in_features, num_labels)
+
+
+def _apply_classifier(model, rt, x, anchor, prefix="classifier"):
+    """logits = classifier(x) for the linear / mlp variants (fp32 [n, num_labels])."""
+    mod = getattr(model, prefix)
+    last = prefix
+    if isinstance(mod, nn.Sequential):
+        x = E.LinearFn.apply(x, rt, prefix + ".0.weight", prefix + ".0.bias", "relu", False, anchor)
+        last = prefix + ".2"
+    n_out = rt.arena.w(last + ".weight").shape[0]
+    if n_out <= 64:
+        return E.SmallHeadFn.apply(x.to(torch.bfloat16), rt, last + ".weight", last + ".bias", anchor)
+    return E.DecoderFn.apply(x.to(torch.bfloat16), rt, last + ".weight", n_out, last + ".bias", anchor)
+
+
+class BiImageBertForSequenceClassificationPlus(BertPreTrainedModel):
+    """Visual entailment head (:1975-2070, run_ve.py:921): classifier(dropout([pooled ; single_mapping(dropout(
+    [t ; v ; v - t ; v * t]))])) with t / v the un-normalised projections of the two stage-1 CLS tokens."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.num_labels = config.num_labels
+        self.loss_type = config.loss_type
+        self.bert = BiBertImgModel(config)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+        H = config.hidden_size
+        self.single_mapping = nn.Sequential(_Linear(4 * H, 2 * H), nn.ReLU(), _Linear(2 * H, H))
+        self.classifier = _make_classifier(config, 2 * H, config.num_labels, default_in=H)
+        self.apply(self.init_weights)
+
+    def reinit_cls_head(self):
+        self.classifier.apply(self.init_weights)
+
+    def freeze_backbone(self):
+        for param in self.bert.parameters():
+            param.requires_grad = False
+
+    def unfreeze_backbone(self):
+        for param in self.bert.parameters():
+            param.requires_grad = True
+
+    def forward(self, input_ids_a, token_type_ids_a=None, attention_mask_a=None, labels=None, input_ids_b=None,
+                token_type_ids_b=None, attention_mask_b=None, max_tag_length=20, position_ids_a=None,
+                position_ids_b=None, head_mask=None, img_feats=None, soft_label=False):
+        rt = self.runtime()
+        self._adopt(self.bert, "bert.")
+        anchor = rt.anchor(self.single_mapping[0].weight)
+        outputs, (txt, vis, _), _ = self.bert(
+            input_ids_a=input_ids_a, position_ids_a=position_ids_a, token_type_ids_a=token_type_ids_a,
+            attention_mask_a=attention_mask_a, head_mask=head_mask, img_feats=img_feats, input_ids_b=input_ids_b,
+            position_ids_b=position_ids_b, token_type_ids_b=token_type_ids_b, attention_mask_b=attention_mask_b,
+            max_tag_length=max_tag_length, encode_hn=False)
+        pooled = outputs[1]
+        p_drop = self.config.hidden_dropout_prob if self.training else 0.0
+        drop = (lambda t: nn.functional.dropout(t, p_drop, True)) if p_drop > 0 else (lambda t: t)
+        gt = E.LinearFn.apply(txt[:, 0], rt, "bert.txt_proj", None, None, True, anchor).float()
+        gi = E.LinearFn.apply(vis[:, 0], rt, "bert.vis_proj", None, None, True, anchor).float()
+        single_out = torch.cat([gt, gi, gi - gt, gi * gt], dim=1)                               # :2041
+        hid = E.LinearFn.apply(drop(single_out), rt, "single_mapping.0.weight", "single_mapping.0.bias", "relu",
+                               False, anchor)
+        single_hidden = E.LinearFn.apply(hid, rt, "single_mapping.2.weight", "single_mapping.2.bias", None, False,
+                                         anchor)
+        feats = drop(torch.cat([pooled, single_hidden], dim=1))                                 # :2044
+        logits = _apply_classifier(self, rt, feats, anchor)
+        out = (logits,) + outputs[2:]
+        if labels is not None:
+            out = (_cls_loss(self, logits, labels, soft_label, self.num_labels),) + out
+        return out
+
+
 class BiImageBertForSequenceClassification(BertPreTrainedModel):
     """classifier(dropout(pooled)) with the reference loss switch (:1715-1798)."""
 
@@ -506,9 +644,7 @@ class BiImageBertForSequenceClassification(BertPreTrainedModel):
         self.loss_type = config.loss_type
         self.bert = BiBertImgModel(config)
         self.dropout = nn.Dropout(config.hidden_dropout_prob)
-        if hasattr(config, 'classifier') and config.classifier == 'mlp':
-            raise NotImplementedError("classifier='mlp' is not on the CUDA path")
-        self.classifier = _Linear(config.hidden_size, self.config.num_labels)
+        self.classifier = _make_classifier(config, config.hidden_size, self.config.num_labels)
         self.apply(self.init_weights)
 
     def freeze_backbone(self):
@@ -524,7 +660,7 @@ class BiImageBertForSequenceClassification(BertPreTrainedModel):
                 position_ids_b=None, head_mask=None, img_feats=None, soft_label=False):
         rt = self.runtime()
         self._adopt(self.bert, "bert.")
-        anchor = rt.anchor(self.classifier.weight)
+        anchor = rt.anchor(next(self.classifier.parameters()))
         outputs, _, _ = self.bert(input_ids_a=input_ids_a, position_ids_a=position_ids_a,
                                   token_type_ids_a=token_type_ids_a, attention_mask_a=attention_mask_a,
                                   head_mask=head_mask, img_feats=img_feats, use_b=use_b, input_ids_b=input_ids_b,
@@ -533,10 +669,7 @@ class BiImageBertForSequenceClassification(BertPreTrainedModel):
         pooled = outputs[1]
         if self.training and self.config.hidden_dropout_prob > 0:
             pooled = nn.functional.dropout(pooled, self.config.hidden_dropout_prob, True)
-        if self.num_labels <= 64:
-            logits = E.SmallHeadFn.apply(pooled, rt, "classifier.weight", "classifier.bias", anchor)
-        else:
-            logits = E.DecoderFn.apply(pooled, rt, "classifier.weight", self.num_labels, "classifier.bias", anchor)
+        logits = _apply_classifier(self, rt, pooled, anchor)
         out = (logits,) + outputs[2:]
         if labels is not None:
             out = (_cls_loss(self, logits, labels, soft_label, self.num_labels),) + out

@@ -383,6 +383,63 @@ def rep_forward(sd: SD, cfg: Cfg, *args, **kw):
     return outs[0], outs[1], single[:2]
 
 
+def negative_sampling_probs(sim_mat, logit):
+    """hn_mod='sample', modeling_vlbert.py:535-540: the two row-wise multinomial distributions."""
+    masked = (logit * sim_mat) - 10000 * torch.eye(sim_mat.shape[0], dtype=sim_mat.dtype)
+    return F.softmax(masked, dim=1), F.softmax(masked.t(), dim=1)
+
+
+def forward_joint(sd: SD, cfg: Cfg, input_ids_a, token_type_ids_a, attention_mask_a, max_tag_length,
+                  input_ids_b, token_type_ids_b, attention_mask_b, img_feats,
+                  input_ids_b2, token_type_ids_b2, attention_mask_b2, img_feats2, bert="bert"):
+    """BiBertImgModel.forward_joint, modeling_vlbert.py:725-869: text + two images ->
+    mul_encoder over [text | regions 1 | regions 2] -> (sequence_output, pooled_output)."""
+    eps = cfg.layer_norm_eps
+    nl, nh = cfg.num_hidden_layers // 2, cfg.num_attention_heads
+    txt, vis, ma, mb = stage1(sd, cfg, input_ids_a, token_type_ids_a, attention_mask_a,
+                              input_ids_b, token_type_ids_b, attention_mask_b, img_feats, bert)
+    _, vis2, _, mb2 = stage1(sd, cfg, input_ids_a, token_type_ids_a, attention_mask_a,
+                             input_ids_b2, token_type_ids_b2, attention_mask_b2, img_feats2, bert)
+    cut = max_tag_length
+    joint = torch.cat([txt, vis[:, cut:], vis2[:, cut:]], dim=1)               # :852
+    jmask = torch.cat([ma, mb[:, :, :, cut:], mb2[:, :, :, cut:]], dim=-1)    # :853
+    seq, _ = encoder(sd, bert + ".mul_encoder", joint, jmask, nl, nh, eps, None)
+    return seq, pooler(sd, bert + ".pooler", seq)
+
+
+def ve_plus_forward(sd: SD, cfg: Cfg, input_ids_a, token_type_ids_a, attention_mask_a, labels,
+                    input_ids_b, token_type_ids_b, attention_mask_b, img_feats, max_tag_length=20):
+    """BiImageBertForSequenceClassificationPlus.forward (eval / dropout 0), modeling_vlbert.py:2029-2068,
+    classifier='linear', cross-entropy loss."""
+    outs, single, _ = bibert_forward(sd, cfg, input_ids_a, token_type_ids_a, attention_mask_a,
+                                     max_tag_length=max_tag_length, input_ids_b=input_ids_b,
+                                     token_type_ids_b=token_type_ids_b, attention_mask_b=attention_mask_b,
+                                     img_feats=img_feats, encode_hn=False)
+    txt, vis, _ = single
+    gt = txt[:, 0, :] @ sd["bert.txt_proj"]
+    gi = vis[:, 0, :] @ sd["bert.vis_proj"]
+    single_out = torch.cat([gt, gi, gi - gt, gi * gt], dim=1)
+    hid = F.relu(linear(single_out, sd, "single_mapping.0"))
+    single_hidden = linear(hid, sd, "single_mapping.2")
+    logits = linear(torch.cat([outs[1], single_hidden], dim=1), sd, "classifier")
+    if labels is None:
+        return (logits,)
+    return cross_entropy(logits.view(-1, cfg.num_labels), labels.view(-1), ignore_index=-100), logits
+
+
+def seqcls_mlp_forward(sd: SD, cfg: Cfg, input_ids_a, token_type_ids_a, attention_mask_a, labels,
+                       input_ids_b, token_type_ids_b, attention_mask_b, img_feats, max_tag_length=20):
+    """BiImageBertForSequenceClassification.forward with classifier='mlp' (:1730-1744, :1762-1798)."""
+    outs, _, _ = bibert_forward(sd, cfg, input_ids_a, token_type_ids_a, attention_mask_a,
+                                max_tag_length=max_tag_length, input_ids_b=input_ids_b,
+                                token_type_ids_b=token_type_ids_b, attention_mask_b=attention_mask_b,
+                                img_feats=img_feats, encode_hn=False)
+    logits = linear(F.relu(linear(outs[1], sd, "classifier.0")), sd, "classifier.2")
+    if labels is None:
+        return (logits,)
+    return cross_entropy(logits.view(-1, cfg.num_labels), labels.view(-1), ignore_index=-100), logits
+
+
 # --------------------------------------------------------------------------
 # Retrieval scoring loop (run_retrieval.py)
 # --------------------------------------------------------------------------
@@ -494,6 +551,19 @@ def state_dict_keys(cfg: Cfg, head: str):
         lm("cls.predictions", cfg.num_labels, True)
     elif head == "rep":
         pass
+    elif head == "ve":  # BiImageBertForSequenceClassificationPlus with classifier='linear', modeling_vlbert.py:1975-2010
+        shapes["single_mapping.0.weight"] = (2 * H, 4 * H)
+        shapes["single_mapping.0.bias"] = (2 * H,)
+        shapes["single_mapping.2.weight"] = (H, 2 * H)
+        shapes["single_mapping.2.bias"] = (H,)
+        shapes["classifier.weight"] = (cfg.num_labels, 2 * H)
+        shapes["classifier.bias"] = (cfg.num_labels,)
+    elif head == "cls_mlp":  # BiImageBertForSequenceClassification with classifier='mlp', :1730-1744
+        hid = H * 2
+        shapes["classifier.0.weight"] = (hid, H)
+        shapes["classifier.0.bias"] = (hid,)
+        shapes["classifier.2.weight"] = (cfg.num_labels, hid)
+        shapes["classifier.2.bias"] = (cfg.num_labels,)
     else:
         raise ValueError(head)
     return shapes
