@@ -218,6 +218,17 @@ int mvptr_wra_fwd(const void* seq, int B, int Ltot, int H, const int64_t* phrase
 int mvptr_wra_bwd(const void* seq, int B, int Ltot, int H, const int64_t* phrase_index, const int64_t* neg_img,
                   const int* sel_pos, const int* sel_neg, const float* dpos, const float* dneg, float* dseq,
                   void* stream);
+
+/* ---- referring-expression head ------------------------------------------------------------
+ * BiImageBertForRE.forward mod 1 / mod 2 (modeling_vlbert.py:1936-1956): logits[b, j] = score of region token
+ * first + j against the [CLS] token of sequence b -- cosine similarity (normalize=1: F.normalize + bmm) or raw
+ * dot product (normalize=0).  p_drop > 0 applies self.dropout(sequence_output) (:1932) on the fly.
+ * inv_norm [B*R, 2] fp32 is saved for backward; dseq must be zeroed by the caller. */
+int mvptr_cls_region_score_fwd(const void* seq, int B, int Ltot, int H, int first, int R, int normalize, float* logits,
+                               float* inv_norm, float p_drop, uint32_t seed, void* stream);
+int mvptr_cls_region_score_bwd(const void* seq, int B, int Ltot, int H, int first, int R, int normalize,
+                               const float* logits, const float* inv_norm, const float* dlogits, void* dseq,
+                               float p_drop, uint32_t seed, void* stream);
 /* dx = dy * gelu'(pre): backward of the head-transform activation, modeling_bert.py:489 */
 int mvptr_gelu_bwd(const void* dy, const void* pre, void* dx, size_t n, void* stream);
 /* instance_bce_with_logits, modeling_vlbert.py:878-883 (VQA loss): loss += sum BCE / n */

@@ -90,6 +90,8 @@ SIGNATURES = {
     "mvptr_match_prob": "ppip",
     "mvptr_wra_fwd": "piiippppp" + "ipppp" + "p",
     "mvptr_wra_bwd": "piiipppppp" + "p" + "p",
+    "mvptr_cls_region_score_fwd": "piiiiii" + "pp" + "fu" + "p",
+    "mvptr_cls_region_score_bwd": "piiiiii" + "pppp" + "fu" + "p",
     "mvptr_gelu_bwd": "pppzp",
     "mvptr_bce_fwd": "pipiipp",
     "mvptr_bce_bwd": "pipiippip",

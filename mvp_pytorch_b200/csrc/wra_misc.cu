@@ -172,6 +172,121 @@ bce_bwd_kernel(const float* __restrict__ logits, int ld, const float* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------
+// Referring-expression head (BiImageBertForRE, modeling_vlbert.py:1936-1956): score of every region
+// token against the [CLS] token of its own sequence -- cosine similarity (mod 1) or raw dot product
+// (mod 2).  seq [B, Ltot, H] bf16 (an optional dropout between encoder and head is applied in place on
+// the fly, same hash as the row kernels); regions are tokens [first, first + R).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void load_row_dropped(const bf16* row, int H, int lane, uint32_t seed, uint32_t base,
+                                                 uint32_t keep_thr, float inv_keep, float (&x)[4][8]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < (H >> 3)) {
+      unpack8(*reinterpret_cast<const bf16x8*>(row + ch * 8), x[c]);
+      if (keep_thr != 0xffffffffu) dropout8(x[c], seed, base + ch * 8, keep_thr, inv_keep);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[c][j] = 0.f;
+    }
+  }
+}
+// one warp per (b, region): logits[b, j], plus 1/|cls|, 1/|region| for backward
+__global__ void __launch_bounds__(128)
+cls_region_score_fwd_kernel(const bf16* __restrict__ seq, int B, int Ltot, int H, int first, int R, int normalize,
+                            float* __restrict__ logits, float* __restrict__ inv_norm, uint32_t keep_thr,
+                            float inv_keep, uint32_t seed_) {
+  const uint32_t seed = site_seed(seed_);
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (w >= B * R) return;
+  const int b = w / R, j = w - b * R;
+  const size_t rc = (size_t)b * Ltot, rr = rc + first + j;
+  float c[4][8], r[4][8];
+  load_row_dropped(seq + rc * H, H, lane, seed, (uint32_t)rc * (uint32_t)H, keep_thr, inv_keep, c);
+  load_row_dropped(seq + rr * H, H, lane, seed, (uint32_t)rr * (uint32_t)H, keep_thr, inv_keep, r);
+  float dot = 0.f, cc = 0.f, r2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      dot += c[k][i] * r[k][i];
+      cc += c[k][i] * c[k][i];
+      r2 += r[k][i] * r[k][i];
+    }
+  dot = warp_sum(dot); cc = warp_sum(cc); r2 = warp_sum(r2);
+  if (lane == 0) {
+    float ic = 1.f, ir = 1.f;
+    if (normalize) {  // F.normalize: x / max(|x|, 1e-12)
+      ic = 1.f / fmaxf(sqrtf(cc), 1e-12f);
+      ir = 1.f / fmaxf(sqrtf(r2), 1e-12f);
+    }
+    logits[w] = dot * ic * ir;
+    inv_norm[2 * w] = ic;
+    inv_norm[2 * w + 1] = ir;
+  }
+}
+// one CTA per sample: dseq rows of the regions and of [CLS] (sum over regions); other rows stay zero
+__global__ void __launch_bounds__(256)
+cls_region_score_bwd_kernel(const bf16* __restrict__ seq, int B, int Ltot, int H, int first, int R, int normalize,
+                            const float* __restrict__ logits, const float* __restrict__ inv_norm,
+                            const float* __restrict__ dlogits, bf16* __restrict__ dseq, uint32_t keep_thr,
+                            float inv_keep, uint32_t seed_) {
+  extern __shared__ float dcls[];  // [8 warps][H]
+  const uint32_t seed = site_seed(seed_);
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t rc = (size_t)b * Ltot;
+  float c[4][8], acc[4][8];
+  load_row_dropped(seq + rc * H, H, lane, seed, (uint32_t)rc * (uint32_t)H, keep_thr, inv_keep, c);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
+  for (int j = warp; j < R; j += 8) {
+    const int w = b * R + j;
+    const size_t rr = rc + first + j;
+    const float g = dlogits[w], s = logits[w], ic = inv_norm[2 * w], ir = inv_norm[2 * w + 1];
+    float r[4][8];
+    load_row_dropped(seq + rr * H, H, lane, seed, (uint32_t)rr * (uint32_t)H, keep_thr, inv_keep, r);
+    // s = <c, r> ic ir ;  ds/dr = ic ir c - (normalize ? s ir^2 r : 0) ;  ds/dc symmetric
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ch = lane + 32 * k;
+      if (ch < (H >> 3)) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          o[i] = g * (ic * ir * c[k][i] - (normalize ? s * ir * ir * r[k][i] : 0.f));
+          acc[k][i] += g * (ic * ir * r[k][i] - (normalize ? s * ic * ic * c[k][i] : 0.f));
+        }
+        if (keep_thr != 0xffffffffu) dropout8(o, seed, (uint32_t)rr * (uint32_t)H + ch * 8, keep_thr, inv_keep);
+        *reinterpret_cast<bf16x8*>(dseq + rr * H + ch * 8) = pack8(o);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int ch = lane + 32 * k;
+    if (ch < (H >> 3))
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dcls[warp * H + ch * 8 + i] = acc[k][i];
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < (H >> 3); ch += blockDim.x) {
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float t = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) t += dcls[w8 * H + ch * 8 + i];
+      o[i] = t;
+    }
+    if (keep_thr != 0xffffffffu) dropout8(o, seed, (uint32_t)rc * (uint32_t)H + ch * 8, keep_thr, inv_keep);
+    *reinterpret_cast<bf16x8*>(dseq + rc * H + ch * 8) = pack8(o);
+  }
+}
+
 }  // namespace mvptr
 
 using namespace mvptr;
@@ -218,5 +333,29 @@ extern "C" int mvptr_bce_bwd(const float* logits, int ld, const float* labels, i
   if (n <= 0) return 0;
   bce_bwd_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(logits, ld, labels, n, C, gscale, (bf16*)dlogits, ld_d);
   MVPTR_CHECK_LAUNCH("bce_bwd");
+  return 0;
+}
+
+extern "C" int mvptr_cls_region_score_fwd(const void* seq, int B, int Ltot, int H, int first, int R, int normalize,
+                                          float* logits, float* inv_norm, float p_drop, uint32_t seed, void* stream) {
+  if (B <= 0 || R <= 0) return 0;
+  if ((H & 7) || H > 1024) MVPTR_FAIL(MVPTR_ERR_UNSUPPORTED, "cls_region_score: hidden size %d", H);
+  if (first < 1 || first + R > Ltot) MVPTR_FAIL(MVPTR_ERR_ARG, "cls_region_score: regions [%d, %d) outside 1..%d", first, first + R, Ltot);
+  cls_region_score_fwd_kernel<<<(B * R + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
+      (const bf16*)seq, B, Ltot, H, first, R, normalize, logits, inv_norm, keep_threshold(p_drop),
+      p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f, seed);
+  MVPTR_CHECK_LAUNCH("cls_region_score_fwd");
+  return 0;
+}
+/* dseq must be zero-initialised by the caller: only the [CLS] row and the region rows are written */
+extern "C" int mvptr_cls_region_score_bwd(const void* seq, int B, int Ltot, int H, int first, int R, int normalize,
+                                          const float* logits, const float* inv_norm, const float* dlogits, void* dseq,
+                                          float p_drop, uint32_t seed, void* stream) {
+  if (B <= 0 || R <= 0) return 0;
+  if ((H & 7) || H > 1024) MVPTR_FAIL(MVPTR_ERR_UNSUPPORTED, "cls_region_score: hidden size %d", H);
+  cls_region_score_bwd_kernel<<<B, 256, 8 * H * sizeof(float), (cudaStream_t)stream>>>(
+      (const bf16*)seq, B, Ltot, H, first, R, normalize, logits, inv_norm, dlogits, (bf16*)dseq, keep_threshold(p_drop),
+      p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f, seed);
+  MVPTR_CHECK_LAUNCH("cls_region_score_bwd");
   return 0;
 }

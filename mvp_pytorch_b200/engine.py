@@ -616,6 +616,33 @@ class LinearFn(Function):
         return dx, None, None, None, None, None, None
 
 
+class ClsRegionScoreFn(Function):
+    """logits[b, j] = cos / dot of region token (first + j) with the [CLS] token, after an optional dropout of the
+    sequence output: BiImageBertForRE mod 1 / mod 2 (modeling_vlbert.py:1931-1951) -> fp32 [B, R]."""
+
+    @staticmethod
+    def forward(ctx, seq, first, normalize, p_drop, rt):
+        seq = seq.contiguous()
+        B, Ltot, H = seq.shape
+        R = Ltot - first
+        logits = torch.empty(B, R, device=seq.device, dtype=F32)
+        inv = torch.empty(B * R, 2, device=seq.device, dtype=F32)
+        seed = rt.next_seed() if p_drop > 0 else 0
+        rt.call("mvptr_cls_region_score_fwd", seq, B, Ltot, H, first, R, int(normalize), logits, inv, float(p_drop), seed)
+        ctx.rt, ctx.s = rt, (seq, first, normalize, p_drop, seed, logits, inv)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dl):
+        rt = ctx.rt
+        seq, first, normalize, p_drop, seed, logits, inv = ctx.s
+        B, Ltot, H = seq.shape
+        dseq = torch.zeros_like(seq)
+        rt.call("mvptr_cls_region_score_bwd", seq, B, Ltot, H, first, Ltot - first, int(normalize), logits, inv,
+                dl.to(F32).contiguous(), dseq, float(p_drop), seed)
+        return dseq, None, None, None, None
+
+
 class SmallHeadFn(Function):
     """x W^T + b with a handful of outputs (ITM / retrieval classifier, modeling_vlbert.py:1247,
     :1680, :1708) -> fp32 logits."""

@@ -676,6 +676,69 @@ class BiImageBertForSequenceClassification(BertPreTrainedModel):
         return out
 
 
+class BiImageBertForRE(BertPreTrainedModel):
+    """Referring-expression head (:1873-1971, run_re.py:28): every region token is scored against [CLS] --
+    mod 1 cosine similarity + MSE, mod 2 dot product + BCE on hard labels (returns sigmoid scores), mod 3 a
+    linear classifier per region + BCE.  phrase_layer selects a mid-encoder output (:1921-1926)."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.num_labels = 1
+        self.loss_type = config.loss_type
+        self.bert = BiBertImgModel(config)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+        self.classifier = _make_classifier(config, config.hidden_size, self.config.num_labels)
+        self.apply(self.init_weights)
+
+    def freeze_backbone(self):
+        for param in self.bert.parameters():
+            param.requires_grad = False
+
+    def unfreeze_backbone(self):
+        for param in self.bert.parameters():
+            param.requires_grad = True
+
+    def reinit_cls_head(self):
+        self.classifier.apply(self.init_weights)
+
+    def forward(self, input_ids_a, token_type_ids_a=None, attention_mask_a=None, labels=None, phrase_layer=None,
+                input_ids_b=None, token_type_ids_b=None, attention_mask_b=None, max_tag_length=20, mod=1,
+                position_ids_a=None, position_ids_b=None, head_mask=None, img_feats=None, soft_label=False):
+        rt = self.runtime()
+        self._adopt(self.bert, "bert.")
+        anchor = rt.anchor(next(self.classifier.parameters()))
+        res = self.bert(input_ids_a=input_ids_a, position_ids_a=position_ids_a, token_type_ids_a=token_type_ids_a,
+                        attention_mask_a=attention_mask_a, head_mask=head_mask, img_feats=img_feats,
+                        phrase_layer=phrase_layer, input_ids_b=input_ids_b, position_ids_b=position_ids_b,
+                        token_type_ids_b=token_type_ids_b, attention_mask_b=attention_mask_b,
+                        max_tag_length=max_tag_length, encode_hn=False)
+        sequence_output = res[0][0] if phrase_layer is None else res[3][0]
+        La = input_ids_a.shape[1]
+        p_drop = self.config.hidden_dropout_prob if self.training else 0.0
+        label_mask = labels >= 0
+        if mod == 1:      # MSE on the cosine similarity (:1937-1944)
+            logits = E.ClsRegionScoreFn.apply(sequence_output, La, True, p_drop, rt)
+            loss = nn.functional.mse_loss(torch.masked_select(labels, label_mask).float(),
+                                          torch.masked_select(logits, label_mask))
+        elif mod == 2:    # BCE with [CLS] as the classifier (:1946-1952)
+            raw = E.ClsRegionScoreFn.apply(sequence_output, La, False, p_drop, rt)
+            hard_labels = (labels >= 0.5).float()
+            loss = nn.functional.binary_cross_entropy_with_logits(torch.masked_select(raw, label_mask),
+                                                                  torch.masked_select(hard_labels, label_mask))
+            logits = torch.sigmoid(raw)
+        elif mod == 3:    # per-region linear classifier (:1954-1958); the loss uses the SOFT labels, as the reference
+            vis = sequence_output[:, La:]
+            if p_drop > 0:
+                vis = nn.functional.dropout(vis, p_drop, True)
+            B, R, H = vis.shape
+            logits = _apply_classifier(self, rt, vis.reshape(B * R, H), anchor).view(B, R)
+            loss = nn.functional.binary_cross_entropy_with_logits(torch.masked_select(logits, label_mask),
+                                                                  torch.masked_select(labels, label_mask).float())
+        else:
+            raise NotImplementedError
+        return (loss, logits)
+
+
 class BiImageBertForVQA(BertPreTrainedModel):
     """dropout(sequence_output[:,0]) -> BertQAPredictionHead -> loss switch (:1801-1870)."""
 

@@ -96,6 +96,34 @@ def main():
     print("sample probs", close(o_p1, seen[0]), close(o_p2, seen[1]))
     out["sample"] = dict(logit=14.0, dice=dice, draw_img=draw_img, draw_txt=draw_txt, p_t2i=seen[0], p_i2t=seen[1],
                          hard_seq=outs[2], hard_pooled=outs[3], hard_txt_index=hard[0], hard_img_index=hard[1], sim=single[2])
+    # ---- referring-expression head: mods 1-3, plus the mid-encoder (phrase_layer) variant, fwd + bwd ----
+    cfg4 = O.Cfg(**dict(TINY, num_labels=1))
+    sd4 = O.random_state_dict(cfg4, "re", seed=10)
+    b4 = O.synthetic_batch(cfg4, B, La, Lt, R, seed=19, ragged=True)
+    gl = torch.Generator().manual_seed(4)
+    re_labels = torch.rand(B, R, generator=gl)
+    re_labels[b4["attention_mask_b"][:, Lt:] == 0] = -1.0   # padded regions carry no label
+    model = mv.BiImageBertForRE(ref_shim.make_config(mv, cfg4)).train()
+    model.load_state_dict(sd4, strict=True)
+    re_out = dict(wseed=10, bseed=19, labels=re_labels, cases={})
+    keep = ["bert.mul_encoder.layer.0.output.dense.weight", "bert.txt_encoder.layer.1.attention.self.key.weight",
+            "bert.img_embedding.weight"]
+    for name, kw in (("mod1", dict(mod=1)), ("mod2", dict(mod=2)), ("mod3", dict(mod=3)),
+                     ("mod1_mid", dict(mod=1, phrase_layer=0))):
+        loss, logits = model(labels=re_labels, max_tag_length=Lt, **kw, **b4)
+        model.zero_grad()
+        loss.backward()
+        with torch.no_grad():
+            o_loss, o_logits = O.re_forward(sd4, cfg4, b4["input_ids_a"], b4["token_type_ids_a"], b4["attention_mask_a"],
+                                            re_labels, b4["input_ids_b"], b4["token_type_ids_b"], b4["attention_mask_b"],
+                                            b4["img_feats"], max_tag_length=Lt, **kw)
+        print("re", name, "loss", close(o_loss, loss), "logits", close(o_logits, logits))
+        params = dict(model.named_parameters())
+        grads = {k: params[k].grad.clone() for k in keep}
+        if name == "mod3":
+            grads["classifier.weight"] = params["classifier.weight"].grad.clone()
+        re_out["cases"][name] = dict(kw=kw, loss=loss.detach(), logits=logits.detach(), grads=grads)
+    out["re"] = re_out
     torch.save(out, os.path.join(OUT, "heads_tiny.pt"))
     print("wrote", os.path.join(OUT, "heads_tiny.pt"), os.path.getsize(os.path.join(OUT, "heads_tiny.pt")) // 1024, "KiB")
 

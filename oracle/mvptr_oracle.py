@@ -427,6 +427,33 @@ def ve_plus_forward(sd: SD, cfg: Cfg, input_ids_a, token_type_ids_a, attention_m
     return cross_entropy(logits.view(-1, cfg.num_labels), labels.view(-1), ignore_index=-100), logits
 
 
+def re_forward(sd: SD, cfg: Cfg, input_ids_a, token_type_ids_a, attention_mask_a, labels, input_ids_b,
+               token_type_ids_b, attention_mask_b, img_feats, max_tag_length=20, mod=1, phrase_layer=None):
+    """BiImageBertForRE.forward (eval / dropout 0), modeling_vlbert.py:1913-1966."""
+    res = bibert_forward(sd, cfg, input_ids_a, token_type_ids_a, attention_mask_a, max_tag_length=max_tag_length,
+                         input_ids_b=input_ids_b, token_type_ids_b=token_type_ids_b, attention_mask_b=attention_mask_b,
+                         img_feats=img_feats, encode_hn=False, phrase_layer=phrase_layer)
+    seq = res[0][0] if phrase_layer is None else res[3][0]
+    La = input_ids_a.shape[1]
+    vis, cls_tok = seq[:, La:], seq[:, 0]
+    label_mask = labels >= 0
+    if mod == 1:
+        logits = torch.bmm(F.normalize(vis, p=2, dim=-1), F.normalize(cls_tok, p=2, dim=-1).unsqueeze(-1)).squeeze(-1)
+        loss = F.mse_loss(torch.masked_select(labels, label_mask), torch.masked_select(logits, label_mask))
+    elif mod == 2:
+        logits = torch.bmm(vis, cls_tok.unsqueeze(-1)).squeeze(-1)
+        loss = F.binary_cross_entropy_with_logits(torch.masked_select(logits, label_mask),
+                                                  torch.masked_select((labels >= 0.5).float(), label_mask))
+        logits = torch.sigmoid(logits)
+    elif mod == 3:
+        logits = linear(vis, sd, "classifier").squeeze(-1)
+        loss = F.binary_cross_entropy_with_logits(torch.masked_select(logits, label_mask),
+                                                  torch.masked_select(labels, label_mask))
+    else:
+        raise NotImplementedError
+    return loss, logits
+
+
 def seqcls_mlp_forward(sd: SD, cfg: Cfg, input_ids_a, token_type_ids_a, attention_mask_a, labels,
                        input_ids_b, token_type_ids_b, attention_mask_b, img_feats, max_tag_length=20):
     """BiImageBertForSequenceClassification.forward with classifier='mlp' (:1730-1744, :1762-1798)."""
@@ -557,6 +584,9 @@ def state_dict_keys(cfg: Cfg, head: str):
         shapes["single_mapping.2.weight"] = (H, 2 * H)
         shapes["single_mapping.2.bias"] = (H,)
         shapes["classifier.weight"] = (cfg.num_labels, 2 * H)
+        shapes["classifier.bias"] = (cfg.num_labels,)
+    elif head == "re":  # BiImageBertForRE, :1873-1903 (default linear classifier, num_labels from the config)
+        shapes["classifier.weight"] = (cfg.num_labels, H)
         shapes["classifier.bias"] = (cfg.num_labels,)
     elif head == "cls_mlp":  # BiImageBertForSequenceClassification with classifier='mlp', :1730-1744
         hid = H * 2

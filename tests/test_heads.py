@@ -141,3 +141,39 @@ def test_sampled_hard_negatives_match_reference_golden(gold):
     P.close(outs[3], s["hard_pooled"], 2e-2, 2e-2, "hard pooled")
     with pytest.raises(ValueError):
         model.bert(encode_hn=True, hn_mod="sample", max_tag_length=Lt, **P.to_cuda({k: b1[k] for k in ENC}))
+
+
+def test_oracle_re_head_matches_reference_golden(gold):
+    g = gold["re"]
+    cfg = O.Cfg(**dict(gold["cfg"], num_labels=1))
+    sd = O.random_state_dict(cfg, "re", seed=g["wseed"])
+    b, Lt = _batch(cfg, gold, g["bseed"])
+    for name, case in g["cases"].items():
+        with torch.no_grad():
+            loss, logits = O.re_forward(sd, cfg, b["input_ids_a"], b["token_type_ids_a"], b["attention_mask_a"], g["labels"],
+                                        b["input_ids_b"], b["token_type_ids_b"], b["attention_mask_b"], b["img_feats"],
+                                        max_tag_length=Lt, **case["kw"])
+        assert torch.allclose(logits, case["logits"], atol=2e-5), name
+        assert torch.allclose(loss, case["loss"], atol=2e-5), name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["mod1", "mod2", "mod3", "mod1_mid"])
+def test_referring_expression_head_matches_reference_golden(gold, name):
+    g = gold["re"]
+    case = g["cases"][name]
+    cfg = O.Cfg(**dict(gold["cfg"], num_labels=1))
+    sd = O.random_state_dict(cfg, "re", seed=g["wseed"])
+    b, Lt = _batch(cfg, gold, g["bseed"])
+    model = P.build("BiImageBertForRE", cfg, sd, train=True)
+    assert set(model.state_dict()) == set(sd)
+    loss, logits = model(labels=g["labels"].cuda(), max_tag_length=Lt, **case["kw"], **P.to_cuda({k: b[k] for k in ENC}))
+    model.zero_grad()
+    loss.backward()
+    valid = (g["labels"] >= 0)
+    P.close(logits.detach().cpu()[valid], case["logits"][valid], 3e-2, 3e-2, f"re {name} logits")  # padded regions unspecified
+    P.close(loss.detach(), case["loss"], 2e-2, 1e-2, f"re {name} loss")
+    params = dict(model.named_parameters())
+    for k, gr in case["grads"].items():
+        rel = P.rel_l2(params[k].grad, gr)
+        assert rel < 6e-2, f"re {name} grad {k}: relative L2 error {rel:.4f}"
