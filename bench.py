@@ -401,6 +401,15 @@ def run_b200(args):
     ms_e2e, _ = timed(e2e_step, args.steps)
     assert torch.isfinite(loss_host).all(), "non-finite loss in the end-to-end run"
 
+    # The captured graph holds NCCL work: release it before anything tears the communicator down
+    # (destroying a communicator under a live graph hangs).
+    if graphed is not None:
+        torch.cuda.synchronize()
+        graphed.release()
+        graphed_was_used = True
+    else:
+        graphed_was_used = False
+
     # ---- (3) one instrumented step: CUDA events around every kernel launch -> per-kernel roofline
     #          (every rank runs the step -- it contains collectives -- only rank 0 records)
     prof = None
@@ -416,9 +425,7 @@ def run_b200(args):
     itm = itm_scoring_pairs_per_s(dev, world, rank)
 
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        _shutdown(world)
         return
 
     sustained, burst, hbm, how = peaks()
@@ -439,7 +446,7 @@ def run_b200(args):
                                "dropout 0.1, BASELINE.json configs[1]",
                    "batch_per_gpu": B, "global_batch": B * world, "text_phrase_len": W["La"], "tags": W["Lt"],
                    "regions": W["R"], "img_dim": W["img_dim"], "parallelism": f"dp{world}",
-                   "master_weights": "fp32", "cuda_graph": graphed is not None, "l2": "inputs larger than L2: per-step working set (~11 GB activations, "
+                   "master_weights": "fp32", "cuda_graph": graphed_was_used, "l2": "inputs larger than L2: per-step working set (~11 GB activations, "
                                                     "2.4 GB weights/grads/moments) >> 126 MB L2, 4 rotating batches"},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
                      "frac": achieved / sustained, "traffic": None,
@@ -465,9 +472,32 @@ def run_b200(args):
                                 "sample": f"oracle port of BiBertImgForPreTraining fwd+bwd (fp32), batch 8, "
                                           f"median of 3 after 1 warm-up ({t:.2f} s/step)"}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    _shutdown(world)
+
+
+def _shutdown(world):
+    """Leave a multi-rank run without ever blocking the launcher: barrier, then tear the process group down
+    on a helper thread and hard-exit if NCCL has not finished within a few seconds (the result line is
+    already printed and flushed at this point)."""
+    if world <= 1:
+        return
+    import threading
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    done = threading.Event()
+
+    def _destroy():
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        finally:
+            done.set()
+
+    threading.Thread(target=_destroy, daemon=True).start()
+    if not done.wait(20.0):
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

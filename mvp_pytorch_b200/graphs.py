@@ -82,6 +82,12 @@ class GraphedTrainStep:
         self.graph.replay()
         return self.losses
 
+    def release(self):
+        """Drop the captured graph (and the NCCL work recorded in it).  Call before destroying the process
+        group; the model and optimizer stay usable for eager steps."""
+        self.graph.reset()
+        self.graph = None
+
     def check_overflow(self):
         """Raises if any replay saw more masked-LM labels than the captured capacity (host sync)."""
         ovf = getattr(self.model, "mlm_overflow", None)
