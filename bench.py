@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 if not os.environ.get("MVPTR_KEEP_NCCL_DEBUG"):
     os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (the image default prints the NCCL version)
+    os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(tempfile.gettempdir(), "mvptr_nccl_%h_%p.log"))
 
 import torch  # noqa: E402
 
