@@ -340,6 +340,9 @@ def run_b200(args):
             ms = float(t)
         return ms, rt.launches - l0
 
+    if world > 1:
+        # leave a few SMs to the NCCL kernels that reduce gradients during backward (see mvptr_gemm_set_max_ctas)
+        _lib.set_gemm_max_ctas(int(os.environ.get("MVPTR_GEMM_MAX_CTAS", str(DP_GEMM_CTAS))))
     sampler = ClockSampler(local) if rank == 0 else None  # NVML initialised outside the timed region
     # ---- warm-up (also builds the arena, cuTensorMap entry point, allocator pools)
     for i in range(max(args.warmup, 3)):
@@ -369,6 +372,16 @@ def run_b200(args):
         launches = (rt.launches - l0) * args.steps
         graphed.check_overflow()
     launches_per_step = launches / args.steps
+
+    if args.quick:  # A/B runs: the resident step only
+        if rank == 0:
+            print(json.dumps({"quick": True, "n_gpus": world, "ms_per_step": ms / args.steps,
+                              "pairs_per_s": B * world * args.steps / (ms / 1e3)}), flush=True)
+        if graphed is not None:
+            torch.cuda.synchronize()
+            graphed.release()
+        _shutdown(world)
+        return
 
     # ---- (2) end to end: pinned host inputs copied every step (prefetched on a copy stream), six
     #          losses read back every step into pinned memory
@@ -476,6 +489,9 @@ def run_b200(args):
     _shutdown(world)
 
 
+DP_GEMM_CTAS = 0  # persistent GEMM CTAs in data-parallel runs (0 = all SMs); tuned in profiles/README.md
+
+
 def _shutdown(world):
     """Leave a multi-rank run without ever blocking the launcher: barrier, then tear the process group down
     on a helper thread and hard-exit if NCCL has not finished within a few seconds (the result line is
@@ -509,6 +525,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="pairs per GPU (default: the 256 of BASELINE.json)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--quick", action="store_true", help="time the resident step only (A/B experiments)")
     ap.add_argument("--no-graph", action="store_true", help="run the eager step instead of the CUDA-graph step")
     ap.add_argument("--profile-step", action="store_true",
                     help="warm up, then run ONE step between cudaProfilerStart/Stop (for ncu) and exit")

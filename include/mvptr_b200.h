@@ -92,6 +92,9 @@ typedef struct {
 } mvptr_gemm_args;
 
 int mvptr_gemm(const mvptr_gemm_args* args, void* stream);
+/* Persistent CTAs a GEMM launch may occupy (0 = all 148 SMs, the default).  Data-parallel runs leave a few SMs
+ * to the NCCL kernels that overlap with backward (mvp_pytorch_b200/parallel.py). */
+int mvptr_gemm_set_max_ctas(int n);
 
 
 /* ---- embeddings + LayerNorm ---------------------------------------------------

@@ -83,6 +83,7 @@ SIGNATURES = {
     "mvptr_small_head_fwd": "pipppiiip",
     "mvptr_small_head_bwd": "ppippippiiip",
     "mvptr_small_ce": "ppiipppp",
+    "mvptr_gemm_set_max_ctas": "i",
     "mvptr_adamw": "ppppp" + "zz" + "fffff" + "ii" + "pf" + "pp",
     "mvptr_set_dropout_epoch": "pp",
     "mvptr_sumsq": "pzpp",
@@ -125,6 +126,11 @@ class LaunchProfiler:
 
 
 PROFILER = None
+
+
+def set_gemm_max_ctas(n):
+    """Persistent CTAs a GEMM may occupy (0 = all SMs); see include/mvptr_b200.h."""
+    check(lib().mvptr_gemm_set_max_ctas(int(n)), "mvptr_gemm_set_max_ctas")
 
 
 def launch_count():

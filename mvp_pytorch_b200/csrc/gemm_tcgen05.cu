@@ -713,6 +713,11 @@ static int make_map(CUtensorMap* map, const void* base, bool f32, uint64_t inner
   return 0;
 }
 
+// Persistent CTAs the GEMMs may occupy (0 = every SM).  A data-parallel run leaves a few SMs to the NCCL
+// kernels that reduce gradients while backward is still running: a persistent grid that does not fit next
+// to them would run its last CTAs as a second wave (static tile striding), doubling the GEMM's time.
+static int g_max_ctas = 0;
+
 template <int BN, bool A_MN, bool B_MN, bool F32OUT, int CTAS, int EPI = 0>
 static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, const Params& p,
                   cudaStream_t stream, const CUtensorMap* pre = nullptr) {
@@ -728,7 +733,8 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap&
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
   if (CTAS == 2) {
-    const int clusters = p.num_tiles < kNumSMs / 2 ? p.num_tiles : kNumSMs / 2;
+    const int sms = g_max_ctas > 0 ? g_max_ctas : kNumSMs;
+    const int clusters = p.num_tiles < sms / 2 ? p.num_tiles : sms / 2;
     cfg.gridDim = dim3(2 * clusters);
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
@@ -737,7 +743,8 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap&
     cfg.attrs = attr;
     cfg.numAttrs = 1;
   } else {
-    cfg.gridDim = dim3(p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs);
+    const int sms = g_max_ctas > 0 ? g_max_ctas : kNumSMs;
+    cfg.gridDim = dim3(p.num_tiles < sms ? p.num_tiles : sms);
   }
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
@@ -766,6 +773,12 @@ static int dispatch(const mvptr_gemm_args* g, const CUtensorMap& a, const CUtens
 
 }  // namespace gemm
 }  // namespace mvptr
+
+extern "C" int mvptr_gemm_set_max_ctas(int n) {
+  if (n < 0 || n > mvptr::kNumSMs) MVPTR_FAIL(MVPTR_ERR_ARG, "gemm_set_max_ctas: %d outside 0..%d", n, mvptr::kNumSMs);
+  mvptr::gemm::g_max_ctas = n & ~1;  // CTA pairs need an even count
+  return 0;
+}
 
 extern "C" int mvptr_gemm(const mvptr_gemm_args* g, void* stream_) {
   using namespace mvptr;
