@@ -187,6 +187,61 @@ def itm_scoring_pairs_per_s(dev, world, rank, n_img=256, caps_per_img=5, k=64, p
                         "stage-2 only on cached stage-1 outputs"}
 
 
+def cross_modal_encoder_leg(model, dev, B, L, steps=10, warmup=3):
+    """north_star's target kernel chain on its own: the cross-modal (stage-2) encoder forward+backward over the
+    2B x (text+phrases+regions) joint sequences of the pre-training step -- 6 CaptionBertLayers, dropout 0.1,
+    weight gradients reduce-added into the arena.  Timed with CUDA events; algorithmic FLOPs per SURVEY 8d:
+    3 x 6 x (M x F_lin + 2B x 4 L^2 H)."""
+    from mvp_pytorch_b200 import engine as E
+    bert = model.bert
+    rt, pf = bert._ctx()
+    rt.begin_forward(True)
+    sync = getattr(rt, "grad_sync", None)  # a single-GPU kernel measurement: no gradient collectives
+    sync_was = sync.enabled if sync is not None else False
+    if sync is not None:
+        sync.enabled = False
+    H, I = rt.H, rt.I
+    nl = model.config.num_hidden_layers // 2
+    g = torch.Generator(device=dev).manual_seed(11)
+    x = torch.randn(2 * B, L, H, device=dev, generator=g).to(torch.bfloat16).requires_grad_(True)
+    gy = (0.01 * torch.randn(2 * B, L, H, device=dev, generator=g)).to(torch.bfloat16)
+    maskadd = torch.zeros(2 * B, L, device=dev, dtype=torch.float32)
+
+    def one():
+        anchor = rt.anchor(bert.txt_proj)
+        y = E.encoder(rt, pf + "mul_encoder", x, maskadd, nl, anchor)
+        y.backward(gy)
+        x.grad = None
+
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        one()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / steps
+    M = 2 * B * L
+    fl = 3.0 * nl * (M * 2 * (4 * H * H + 2 * H * I) + 2 * B * 4 * L * L * H)
+    model.zero_grad()
+    if sync is not None:
+        sync.enabled = sync_was
+    return ms, fl
+
+
+def measured_gemm_traffic():
+    """DRAM bytes per gemm_kernel launch from the committed ncu pass over one step (profiles/gemm_traffic.json,
+    written by tools/summarize_launches.py); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    try:
+        d = json.load(open(p))["gemm_kernel"]
+        return d["dram_bytes_per_launch"], d["launches"]
+    except Exception:  # noqa: BLE001
+        return None, None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -269,7 +324,8 @@ def run_b200(args):
     W = WORK
     B = args.batch or W["B"]
     torch.manual_seed(1234 + rank)
-    model = BiBertImgForPreTraining(make_config(W["p_drop"])).to(dev).train()
+    p_drop = W["p_drop"] if args.p_drop is None else args.p_drop  # --p-drop: A/B experiments only (with --quick)
+    model = BiBertImgForPreTraining(make_config(p_drop)).to(dev).train()
     if world > 1:  # identical replicas: broadcast rank-0 weights through the flat arena
         rt = model.runtime()
         dist.broadcast(rt.arena.master, 0)
@@ -435,6 +491,9 @@ def run_b200(args):
         prof = _lib.profile_collect()
         _lib.profile_enable(False)
 
+    # ---- (3b) the cross-modal encoder alone (north_star's >= 50 % target is quoted on it)
+    xenc_ms, xenc_fl = cross_modal_encoder_leg(model, dev, B, W["La"] + W["R"])
+
     # ---- (4) ITM scoring throughput (the other half of the metric); frees the training state first
     itm = itm_scoring_pairs_per_s(dev, world, rank)
 
@@ -452,6 +511,7 @@ def run_b200(args):
     total_prof_ms = sum(v["ms"] for v in prof.values())
     achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     top = sorted(((v["ms"], k, v["launches"]) for k, v in prof.items()), reverse=True)[:8]
+    traffic, traffic_launches = measured_gemm_traffic()
     line = {
         "metric": "image-text pairs/sec (pretrain step)", "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -463,7 +523,9 @@ def run_b200(args):
                    "master_weights": "fp32", "cuda_graph": graphed_was_used, "l2": "inputs larger than L2: per-step working set (~11 GB activations, "
                                                     "2.4 GB weights/grads/moments) >> 126 MB L2, 4 rotating batches"},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
-                     "frac": achieved / sustained, "traffic": None,
+                     "frac": achieved / sustained, "traffic": traffic,
+                     "traffic_note": (f"DRAM read+write bytes per gemm_kernel launch, ncu pass over the {traffic_launches} "
+                                      "GEMM launches of one step (profiles/gemm_traffic.json)") if traffic else None,
                      "kernel": "gemm_kernel (tcgen05/TMEM/TMA), all launches of one step",
                      "launches_per_step": gemm_n, "gemm_ms_per_step": gemm_ms,
                      "gemm_share_of_kernel_time": gemm_ms / total_prof_ms if total_prof_ms else None,
@@ -480,6 +542,12 @@ def run_b200(args):
         "clocks": clocks,
     }
     line["itm_scoring"] = itm
+    xt = xenc_fl / (xenc_ms / 1e3) / 1e12
+    line["cross_modal_encoder"] = {
+        "workload": f"cross-modal encoder fwd+bwd, {2 * B} joint sequences x {W['La'] + W['R']} tokens "
+                    "(joint + hard-negative pairs of one step), 6 layers, dropout 0.1, eager launches",
+        "ms": xenc_ms, "algorithmic_tflop": xenc_fl / 1e12, "achieved_tflops": xt,
+        "frac_of_sustained": xt / sustained, "frac_of_burst": xt / burst, "target_frac": 0.5}
     if world == 1 and not args.no_cpu:
         v, cores, t = cpu_pretrain_pairs_per_s(8, 3, 1)
         line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
@@ -526,6 +594,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="pairs per GPU (default: the 256 of BASELINE.json)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="time the resident step only (A/B experiments)")
+    ap.add_argument("--p-drop", type=float, default=None, help="override dropout (only with --quick; the bench line uses 0.1)")
     ap.add_argument("--no-graph", action="store_true", help="run the eager step instead of the CUDA-graph step")
     ap.add_argument("--profile-step", action="store_true",
                     help="warm up, then run ONE step between cudaProfilerStart/Stop (for ncu) and exit")
@@ -533,6 +602,8 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
+    if args.p_drop is not None and not args.quick:
+        raise SystemExit("--p-drop is an A/B knob: use it with --quick (the bench line is defined at dropout 0.1)")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU: the product path has no CPU fallback "
                          "(use --impl reference for the CPU arm)")
