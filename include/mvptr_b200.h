@@ -205,6 +205,14 @@ int mvptr_adamw(float* p, const float* g, float* m, float* v, void* p16, size_t 
 /* Copies *src (device or pinned-host word, read when the copy executes) into the dropout epoch mixed
  * into every dropout hash: lets CUDA-graph replays draw fresh masks with baked-in seeds. */
 int mvptr_set_dropout_epoch(const uint32_t* src, void* stream);
+/* Per-replay parameters of a CUDA-graph training step (run_pretrain_ml.py:528-545: scheduler.step() and the
+ * optimizer's step count advance once per iteration).  ring: `slots` 16-byte records {float lr, float step,
+ * uint32 dropout epoch, pad} in PINNED host (or device) memory, filled by the host for replay n at slot
+ * n % slots before it launches the replay; counter: device word = replays executed so far.  One 1-thread
+ * kernel reads record counter % slots at EXECUTION time, publishes {lr, step} to dyn_lr_step (nullable, the
+ * mvptr_adamw argument) and the epoch to every dropout site, then increments the counter -- so a host that
+ * runs several replays ahead still gives every replay its own values. */
+int mvptr_step_params(const void* ring, int slots, uint32_t* counter, float* dyn_lr_step, void* stream);
 int mvptr_sumsq(const float* g, size_t n, float* out, void* stream);
 
 /* ---- weakly-supervised phrase grounding (WRA), batched ----------------------------------

@@ -86,6 +86,7 @@ SIGNATURES = {
     "mvptr_gemm_set_max_ctas": "i",
     "mvptr_adamw": "ppppp" + "zz" + "fffff" + "ii" + "pf" + "pp",
     "mvptr_set_dropout_epoch": "pp",
+    "mvptr_step_params": "pippp",
     "mvptr_sumsq": "pzpp",
     "mvptr_topk_rows": "pliiippp",
     "mvptr_match_prob": "ppip",

@@ -52,25 +52,32 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// 8 bf16 <-> 8 float through one 16-byte access
+// 8 bf16 <-> 8 float through ONE 16-byte access.  The carrier is a trivially copyable POD of four 32-bit
+// words: a struct of __nv_bfloat162 members has user-provided copy operations, which made every
+// `*reinterpret_cast<const bf16x8*>(p)` a member-wise copy -- four LDG.32 / STG.32 per lane instead of one
+// LDG.128 / STG.128 (seen in the SASS of every row kernel).
 struct alignas(16) bf16x8 {
-  bf162 v[4];
+  uint32_t w[4];
 };
-__device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
+__device__ __forceinline__ void unpack8(const uint4& p, float* f) {
+  const uint4 v = p;  // ONE 16-byte load when p refers to memory (member-wise reads were emitted as four LDG.32)
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(p.v[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
+    f[2 * i] = __uint_as_float(w[i] << 16);             // low half = element 2i
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);  // high half = element 2i + 1
   }
 }
-__device__ __forceinline__ void unpack8(const uint4& p, float* f) {
-  unpack8(*reinterpret_cast<const bf16x8*>(&p), f);
+__device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
+  unpack8(*reinterpret_cast<const uint4*>(&p), f);
 }
 __device__ __forceinline__ bf16x8 pack8(const float* f) {
   bf16x8 p;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  for (int i = 0; i < 4; ++i) {
+    const bf162 t = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    p.w[i] = *reinterpret_cast<const uint32_t*>(&t);
+  }
   return p;
 }
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -133,6 +140,14 @@ static __device__ uint32_t g_dropout_epoch = 0;
     cudaError_t e = cudaMemcpyToSymbolAsync(::mvptr::g_dropout_epoch, src, sizeof(uint32_t), 0, cudaMemcpyDefault, \
                                             (cudaStream_t)stream);                                     \
     if (e != cudaSuccess) MVPTR_FAIL(MVPTR_ERR_CUDA, #fn ": %s", cudaGetErrorString(e));                \
+    return 0;                                                                                          \
+  }                                                                                                    \
+  /* device address of this translation unit's epoch word (mvptr_step_params writes all of them) */   \
+  extern "C" int fn##_addr(uint32_t** out) {                                                           \
+    void* ptr = nullptr;                                                                               \
+    cudaError_t e = cudaGetSymbolAddress(&ptr, ::mvptr::g_dropout_epoch);                              \
+    if (e != cudaSuccess) MVPTR_FAIL(MVPTR_ERR_CUDA, #fn "_addr: %s", cudaGetErrorString(e));          \
+    *out = static_cast<uint32_t*>(ptr);                                                                \
     return 0;                                                                                          \
   }
 

@@ -359,3 +359,5 @@ extern "C" int mvptr_cls_region_score_bwd(const void* seq, int B, int Ltot, int 
   MVPTR_CHECK_LAUNCH("cls_region_score_bwd");
   return 0;
 }
+
+MVPTR_DEFINE_EPOCH_SETTER(mvptr_set_epoch_wra)

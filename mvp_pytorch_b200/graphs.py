@@ -6,11 +6,15 @@ the ~500 kernel launches of a step no longer depend on how fast (or how often in
 host thread is, and the launch gaps between them disappear.
 
 What makes the step capturable:
-* dropout: the per-site seeds are baked into the graph; a pinned host counter is copied into the
-  library's dropout epoch word at the start of every replay (`mvptr_set_dropout_epoch`), so each
-  replay draws fresh masks;
-* AdamW: learning rate and step count travel the same way (pinned host -> device float[2]), so LR
-  schedulers keep working (`optimizer.param_groups[0]['lr']` is read before every replay);
+* dropout: the per-site seeds are baked into the graph; the graph's first node (`mvptr_step_params`, one
+  1-thread kernel) reads this replay's record {lr, step, dropout epoch} from a ring in pinned host memory,
+  indexed by a DEVICE-side replay counter, and publishes the epoch to every dropout site, so each replay
+  draws fresh masks;
+* AdamW: learning rate and step count come from the same record, so LR schedulers keep working
+  (`optimizer.param_groups[0]['lr']` is read before every replay).  Because the record is selected by the
+  device counter at execution time, a host that enqueues several replays ahead still gives replay n the values
+  of step n (one host word copied by a memcpy node per replay would hand late replays the newest value);
+  the host blocks only when it is `RING` replays ahead;
 * masked-LM row selection: fixed-capacity `torch.nonzero_static` instead of the synchronising
   `torch.nonzero`; unused slots carry label -1.  More labels than slots raise `overflow`
   (checked by `check_overflow()`), never silently dropped;
@@ -41,15 +45,21 @@ class GraphedTrainStep:
         if mlm_capacity is not None:
             model.mlm_capacity = tuple(int(c) for c in mlm_capacity)
             model.mlm_overflow = torch.zeros((), dtype=torch.bool, device=dev)
-        self.epoch_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        # per-replay parameter ring (pinned host) + device replay counter, see mvptr_step_params
+        self.ring = torch.zeros(self.RING, 4, dtype=torch.int32).pin_memory()
+        self.ring_f = self.ring.view(torch.float32)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.slot_events = [None] * self.RING
+        self.n = 0  # step_params kernels launched for execution so far == value the device counter will reach
         optimizer.enable_graph_mode()
         self.losses = None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(warmup):
-                self.epoch_host[0] += 1
+            for _ in range(max(1, warmup)):  # >= 1: the first call also resolves the library's symbol addresses
+                self._publish(optimizer._step + 1)  # opt.step() inside _step() advances to this value
                 self._step()
+                self._mark_launched()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
@@ -58,15 +68,37 @@ class GraphedTrainStep:
         # the capture pass advanced the optimizer's host step without executing: undo
         optimizer._step -= 1
 
+    RING = 16  # replays the host may run ahead of the device
+
+    def _publish(self, step_value):
+        """Fill the record of the next step_params execution (host side, before it is launched)."""
+        slot = self.n % self.RING
+        ev = self.slot_events[slot]
+        if ev is not None:  # the replay that last read this slot must be done before it is overwritten
+            ev.synchronize()
+        self.ring_f[slot, 0] = float(self.opt.param_groups[0]["lr"])
+        self.ring_f[slot, 1] = float(step_value)
+        self.ring[slot, 2] = (self.n + 1) & 0x7FFFFFFF  # dropout epoch: a fresh value per executed step
+
+    def _mark_launched(self):
+        ev = torch.cuda.Event()
+        ev.record()
+        self.slot_events[self.n % self.RING] = ev
+        self.n += 1
+
     def _step(self):
-        _lib.call("mvptr_set_dropout_epoch", self.epoch_host)
-        self.model.zero_grad()
-        out = self.model(**self.static, **self.kw)
-        out[0].backward()
-        if self.allreduce:
-            from .parallel import allreduce_gradients
-            allreduce_gradients(self.model)
-        self.opt.step()
+        _lib.call("mvptr_step_params", self.ring, self.RING, self.counter, self.opt._dyn)
+        self.opt._dyn_external = True  # {lr, step} were just published on the device by step_params
+        try:
+            self.model.zero_grad()
+            out = self.model(**self.static, **self.kw)
+            out[0].backward()
+            if self.allreduce:
+                from .parallel import allreduce_gradients
+                allreduce_gradients(self.model)
+            self.opt.step()
+        finally:
+            self.opt._dyn_external = False
         self.losses = torch.stack([o.detach().float() for o in out])
 
     def load(self, batch, non_blocking=True):
@@ -77,9 +109,10 @@ class GraphedTrainStep:
     def __call__(self, batch=None):
         if batch is not None:
             self.load(batch)
-        self.epoch_host[0] += 1
-        self.opt.before_replay()
+        self.opt._step += 1
+        self._publish(self.opt._step)
         self.graph.replay()
+        self._mark_launched()
         return self.losses
 
     def release(self):

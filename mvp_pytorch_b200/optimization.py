@@ -89,6 +89,7 @@ class AdamW(Optimizer):
         self._norm = None
         self._dyn = None       # device float[2] {lr, step} for CUDA-graph replays
         self._dyn_host = None  # its pinned host source
+        self._dyn_external = False  # True while graphs.GraphedTrainStep publishes _dyn itself (mvptr_step_params)
 
     @classmethod
     def for_model(cls, model, **kw):
@@ -132,9 +133,10 @@ class AdamW(Optimizer):
         self._step += 1
         group = self.param_groups[0]
         dyn = None
-        if self._dyn is not None:  # graph mode: lr / step travel through pinned host memory -> device
-            self._dyn_host[0], self._dyn_host[1] = float(group["lr"]), float(self._step)
-            self._dyn.copy_(self._dyn_host, non_blocking=True)
+        if self._dyn is not None:  # graph mode: the kernel reads {lr, step} from device memory at execution time
+            if not self._dyn_external:  # eager step of a graph-mode optimizer: publish them from the host
+                self._dyn_host[0], self._dyn_host[1] = float(group["lr"]), float(self._step)
+                self._dyn.copy_(self._dyn_host, non_blocking=True)
             dyn = self._dyn
         wd = max(gr["weight_decay"] for gr in self.param_groups)
         norm = None

@@ -86,3 +86,48 @@ def test_graphed_step_dropout_varies_and_overflow_is_loud():
     step(full)
     with pytest.raises(_lib.MvptrError):
         step.check_overflow()
+
+
+def test_replays_enqueued_ahead_keep_their_own_lr_step_and_dropout_epoch():
+    """The host enqueues all replays WITHOUT synchronising (it runs far ahead of the device): replay n must
+    still see the learning rate / AdamW step of step n (mvptr_step_params reads a ring slot selected by a
+    device-side replay counter) -- the trajectory has to match eager steps taken one by one."""
+    from mvp_pytorch_b200.graphs import GraphedTrainStep
+    lrs = [2e-3, 1e-4, 3e-3, 5e-4, 2e-3, 1e-3, 4e-3, 2e-4]
+    m1, o1, batches, Lt = _setup()
+    eager = []
+    for i, lr in enumerate(lrs):
+        o1.param_groups[0]["lr"] = lr
+        torch.cuda.manual_seed(100 + i)
+        eager.append(_eager(m1, o1, batches[i % 4], Lt).cpu())
+    w_eager = m1.state_dict()["bert.txt_encoder.layer.0.attention.self.query.weight"].float().cpu()
+
+    m2, o2, batches, Lt = _setup()
+    sd0 = {k: v.clone() for k, v in m2.state_dict().items()}
+    step = GraphedTrainStep(m2, o2, batches[0], forward_kwargs=dict(max_tag_length=Lt), warmup=2)
+    m2.load_state_dict(sd0, strict=True)
+    o2._m.zero_(); o2._v.zero_(); o2._step = 0
+    torch.cuda.synchronize()
+    got = []
+    for i, lr in enumerate(lrs):  # no host-device synchronisation inside this loop
+        o2.param_groups[0]["lr"] = lr
+        torch.cuda.manual_seed(100 + i)
+        got.append(step(batches[i % 4]).clone())
+    torch.cuda.synchronize()
+    assert int(step.counter) == step.n == 2 + len(lrs)
+    for i, (e, g) in enumerate(zip(eager, got)):
+        P.close(g.cpu(), e, 1e-2, 1e-2 * (i + 1), f"step {i} losses (graph, host running ahead, vs eager)")
+    w_graph = m2.state_dict()["bert.txt_encoder.layer.0.attention.self.query.weight"].float().cpu()
+    # the weights integrate every step's lr: a replay that read a neighbour's lr would show up here
+    w0 = sd0["bert.txt_encoder.layer.0.attention.self.query.weight"].float().cpu()
+    assert (w_graph - w_eager).abs().mean() < 0.1 * (w_eager - w0).abs().mean()
+
+    # dropout epochs: two replays enqueued back to back (no sync) must draw different masks
+    m3, o3, batches, Lt = _setup(dropout=0.1)
+    o3.param_groups[0]["lr"] = 0.0
+    step3 = GraphedTrainStep(m3, o3, batches[0], forward_kwargs=dict(max_tag_length=Lt), warmup=1)
+    a = step3(batches[0]).clone()
+    b = step3(batches[0]).clone()
+    c = step3(batches[0]).clone()
+    torch.cuda.synchronize()
+    assert float((a[3] - b[3]).abs()) > 0 and float((b[3] - c[3]).abs()) > 0
