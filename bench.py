@@ -429,16 +429,6 @@ def run_b200(args):
         graphed.check_overflow()
     launches_per_step = launches / args.steps
 
-    if args.quick:  # A/B runs: the resident step only
-        if rank == 0:
-            print(json.dumps({"quick": True, "n_gpus": world, "ms_per_step": ms / args.steps,
-                              "pairs_per_s": B * world * args.steps / (ms / 1e3)}), flush=True)
-        if graphed is not None:
-            torch.cuda.synchronize()
-            graphed.release()
-        _shutdown(world)
-        return
-
     # ---- (2) end to end: pinned host inputs copied every step (prefetched on a copy stream), six
     #          losses read back every step into pinned memory
     copy_stream = torch.cuda.Stream()
@@ -446,9 +436,13 @@ def run_b200(args):
     staged = [None, None]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     freed = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_mode = set(filter(None, (args.e2e_debug or "").split(",")))  # A/B only: "noh2d", "nod2h"
 
     def stage(i):
         slot = i & 1
+        if "noh2d" in e2e_mode:
+            staged[slot] = resident[i % n_batches]
+            return
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(freed[slot])
             staged[slot] = {k: v.to(dev, non_blocking=True) for k, v in host[i % n_batches].items()}
@@ -460,11 +454,31 @@ def run_b200(args):
             stage(0)
         if i + 1 < args.steps:
             stage(i + 1)
-        torch.cuda.current_stream().wait_event(ready[slot])
+        if "noh2d" not in e2e_mode:
+            torch.cuda.current_stream().wait_event(ready[slot])
         out = train_step(staged[slot])
-        loss_host[i].copy_(out if torch.is_tensor(out) else torch.stack([x.detach().float() for x in out]),
-                           non_blocking=True)
+        if "nod2h" not in e2e_mode:
+            loss_host[i].copy_(out if torch.is_tensor(out) else torch.stack([x.detach().float() for x in out]),
+                               non_blocking=True)
         freed[slot].record()
+
+    if args.quick:  # A/B runs: the resident step only (plus the end-to-end loop when --e2e-debug is given)
+        res = {"quick": True, "n_gpus": world, "ms_per_step": ms / args.steps,
+               "pairs_per_s": B * world * args.steps / (ms / 1e3)}
+        if args.e2e_debug is not None:
+            for f in freed:
+                f.record()
+            ms_q, _ = timed(e2e_step, args.steps)
+            res["e2e_ms_per_step"], res["e2e_debug"] = ms_q / args.steps, args.e2e_debug
+            ms_r, _ = timed(lambda i: train_step(resident[i % n_batches]), args.steps)
+            res["resident_again_ms_per_step"] = ms_r / args.steps
+        if rank == 0:
+            print(json.dumps(res), flush=True)
+        if graphed is not None:
+            torch.cuda.synchronize()
+            graphed.release()
+        _shutdown(world)
+        return
 
     for f in freed:
         f.record()
@@ -594,6 +608,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="pairs per GPU (default: the 256 of BASELINE.json)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="time the resident step only (A/B experiments)")
+    ap.add_argument("--e2e-debug", default=None,
+                    help="with --quick: also time the end-to-end loop; comma list of noh2d / nod2h ('' = the real loop)")
     ap.add_argument("--p-drop", type=float, default=None, help="override dropout (only with --quick; the bench line uses 0.1)")
     ap.add_argument("--no-graph", action="store_true", help="run the eager step instead of the CUDA-graph step")
     ap.add_argument("--profile-step", action="store_true",
