@@ -56,9 +56,9 @@ int mvptr_profile_collect(const char** names_host, double* work_host, float* ms_
  *
  * Epilogue, applied per element in this order (null pointer = skipped):
  *   v = alpha*acc;  v += bias[n] (fp32 or bf16 per bias_is_bf16);
- *   pre_act[m,n] = bf16(v)                       (saved for backward)
+ *   pre_act[m,n] = bf16(v)                       (saved for backward; bf16(gelu'(v)) with aux_is_gelu_grad)
  *   v = act(v)            act: 0 none, 1 erf-GELU, 2 tanh
- *   v *= gelu'(gelu_grad_of[m,n])                (backward of act=1)
+ *   v *= gelu'(gelu_grad_of[m,n])                (backward of act=1; v *= gelu_grad_of[m,n] with aux_is_gelu_grad)
  *   colsum[n] += sum_m bf16(v)                   (fp32 atomics; only with gelu_grad_of: the bias gradient of
  *                                                 the GELU layer, i.e. the column sums of exactly what is stored)
  *   v = keep(seed, m*N+n) ? v/keep_prob : 0      (dropout, p_drop > 0)
@@ -89,6 +89,10 @@ typedef struct {
   int block_n;  /* 0 = auto, else 128 or 256 */
   int cta_pair; /* 0 = auto, 1 = single-CTA tiles (128 x block_n), 2 = CTA-pair tiles (256 x 256, cta_group::2) */
   float* colsum; /* fp32 [N] (+=), nullable; requires gelu_grad_of and the lean GELU' epilogue (see mvptr_gemm) */
+  int aux_is_gelu_grad; /* 1: the auxiliary tensor carries gelu'(pre-activation) instead of the pre-activation:
+                           pre_act[m,n] = bf16(gelu'(v)) in a forward call (act = 1), and a backward call multiplies
+                           by gelu_grad_of[m,n] itself.  Moves the erf of GELU' out of the dgrad epilogue (it shares
+                           the forward's erf evaluation); the [M,N] auxiliary tensor keeps its size. */
 } mvptr_gemm_args;
 
 int mvptr_gemm(const mvptr_gemm_args* args, void* stream);

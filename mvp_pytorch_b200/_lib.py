@@ -30,7 +30,7 @@ class GemmArgs(ctypes.Structure):
         ("pre_act", ctypes.c_void_p), ("act", ctypes.c_int),
         ("gelu_grad_of", ctypes.c_void_p), ("residual", ctypes.c_void_p), ("ld_aux", ctypes.c_int),
         ("p_drop", ctypes.c_float), ("seed", ctypes.c_uint32), ("block_n", ctypes.c_int), ("cta_pair", ctypes.c_int),
-        ("colsum", ctypes.c_void_p),
+        ("colsum", ctypes.c_void_p), ("aux_is_gelu_grad", ctypes.c_int),
     ]
 
 
@@ -243,7 +243,7 @@ ACT = {None: 0, "none": 0, "gelu": 1, "tanh": 2}
 
 def gemm(A, B, D, M, N, K, *, lda, ldb, ldd, a_mn=False, b_mn=False, accumulate=False, split_k=1, alpha=1.0,
          bias=None, pre_act=None, act=None, gelu_grad_of=None, residual=None, ld_aux=0, p_drop=0.0, seed=0,
-         block_n=0, cta_pair=0, colsum=None):
+         block_n=0, cta_pair=0, colsum=None, aux_is_gelu_grad=False):
     """D[M,N] (+)= epilogue(alpha * A . B^T); see include/mvptr_b200.h."""
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
     assert D.dtype in (torch.bfloat16, torch.float32)
@@ -264,6 +264,7 @@ def gemm(A, B, D, M, N, K, *, lda, ldb, ldd, a_mn=False, b_mn=False, accumulate=
     g.act = ACT[act]
     g.ld_aux, g.p_drop, g.seed, g.block_n = ld_aux, float(p_drop), int(seed) & 0xFFFFFFFF, block_n
     g.cta_pair = cta_pair
+    g.aux_is_gelu_grad = int(aux_is_gelu_grad)
     if colsum is not None:
         assert colsum.dtype == torch.float32
         g.colsum = colsum.data_ptr()

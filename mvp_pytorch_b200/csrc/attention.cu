@@ -115,8 +115,12 @@ struct FwdParams {
 };
 
 // NT = number of 8-key tiles covered (keys padded to NT*8, NT even)
+// Register caps: the kernel is latency bound (ncu: 17 % warps active at 126 registers = 2 CTAs of 6 warps per
+// SM for L = 90), so the two hot shapes trade a few registers for a third / fourth resident CTA; ptxas reports
+// no spills at these caps.
 template <int NT>
-__global__ void __launch_bounds__(256) attn_fwd_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(256)
+__maxnreg__(NT == 12 ? 112 : (NT == 10 ? 96 : (NT == 6 ? 80 : (NT <= 16 ? 128 : 255)))) attn_fwd_kernel(const FwdParams p) {
   constexpr int LP = NT * 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   bf16* Qs = reinterpret_cast<bf16*>(smem_attn);

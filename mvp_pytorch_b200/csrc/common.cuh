@@ -113,6 +113,14 @@ __device__ __forceinline__ float gelu_erf(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, e, hx);
 }
+// gelu(x) and gelu'(x) from ONE erf / gaussian evaluation (the forward epilogue that saves gelu' for backward)
+__device__ __forceinline__ void gelu_erf_both(float x, float& act, float& grad) {
+  float e, g;
+  erf_gauss(x, e, g);
+  const float hx = 0.5f * x;
+  act = fmaf(hx, e, hx);
+  grad = fmaf(x * 0.39894228040143268f, g, fmaf(0.5f, e, 0.5f));
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   float e, g;
   erf_gauss(x, e, g);

@@ -44,6 +44,7 @@ struct Params {
   uint32_t keep_thr;
   uint32_t seed;
   int use_dropout;
+  int aux_is_grad;  // the auxiliary tensor (pre_act / gelu_grad_of) carries gelu'(pre-activation), see the header
   int debug;  // MVPTR_GEMM_DEBUG bit 0: skip the slab-reuse wait (timing experiment only, results may be wrong)
 };
 
@@ -217,17 +218,20 @@ struct SmemLayout {
 // pre-activation backward needs), tmD receives gelu(acc + bias): BertIntermediate (modeling_bert.py:394-397)
 // in ONE pass over the accumulator, no separate GELU kernel and no re-read of the pre-activation.
 // EPI selects the epilogue: 0 = generic (run-time flags: alpha, bias, residual, dropout, GELU', ...),
-// 1 = lean bias + GELU, 2 = lean bias + GELU with DUAL stores.  The lean variants carry none of the
+// 1 = lean bias + GELU, 2 = lean bias + GELU with DUAL stores, 3 = acc * gelu'(P), 4 = as 2 but the second
+// store carries gelu'(acc + bias) (one shared erf evaluation), 5 = as 3 with P already holding gelu'
+// (acc * P: no transcendental left in the dgrad epilogue, which ran as long as its K=768 mainloop).  The lean variants carry none of the
 // generic branches: the generic body with GELU inlined 32x per chunk no longer fits the instruction
 // cache (ncu: stall_no_inst), and its bias loads sat behind the TMEM wait.
 template <int BN, bool A_MN, bool B_MN, bool F32OUT, int CTAS, int EPI = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmP, const Params p) {
-  constexpr bool DUAL = EPI == 2;  // two store slabs per epilogue warp
-  constexpr bool LEAN = EPI == 1 || EPI == 2;
-  constexpr bool GGRAD = EPI == 3;  // D = bf16(acc * gelu'(P)), colsum += column sums; P arrives by TMA through tmP
-  using L = SmemLayout<BN, CTAS, GGRAD ? 4 : DUAL ? 2 : 1>;
+  constexpr bool DUAL = EPI == 2 || EPI == 4;  // two store slabs per epilogue warp
+  constexpr bool LEAN = EPI == 1 || EPI == 2 || EPI == 4;
+  constexpr bool GGRAD = EPI == 3 || EPI == 5;  // D = bf16(acc * gelu'(P)), colsum += column sums; P arrives by TMA through tmP
+  constexpr bool AUXG = EPI == 4 || EPI == 5;   // P holds gelu'(pre-activation), not the pre-activation
+  using L = SmemLayout<BN, CTAS, GGRAD ? 4 : DUAL ? 2 : 1>;  // (EPI 4 / 5 share the layouts of 2 / 3)
   constexpr bool kPair = CTAS == 2;
   const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
@@ -441,7 +445,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             float x[8], o[8];
             unpack8(*unit, x);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(rbuf[c & 1][u * 8 + j]) * gelu_erf_grad(x[j]);
+            for (int j = 0; j < 8; ++j)
+              o[j] = __uint_as_float(rbuf[c & 1][u * 8 + j]) * (AUXG ? x[j] : gelu_erf_grad(x[j]));
             *unit = pack8(o);
           }
           if (h == 1) {
@@ -518,18 +523,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             __syncwarp();
             store_pending = false;
           }
-          if constexpr (DUAL) {
+          uint8_t* row = slab + lane * 128;
+          if constexpr (AUXG) {
+            // activation and gelu' from one erf evaluation, 8 columns at a time (keeps the live set small)
             uint8_t* prow = slab_pre + lane * 128;
 #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float a8[8], g8[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) gelu_erf_both(v[u * 8 + j], a8[j], g8[j]);
+              *reinterpret_cast<bf16x8*>(prow + (((h * 4 + u) ^ (lane & 7)) << 4)) = pack8(g8);
+              *reinterpret_cast<bf16x8*>(row + (((h * 4 + u) ^ (lane & 7)) << 4)) = pack8(a8);
+            }
+          } else {
+            if constexpr (DUAL) {
+              uint8_t* prow = slab_pre + lane * 128;
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                *reinterpret_cast<bf16x8*>(prow + (((h * 4 + u) ^ (lane & 7)) << 4)) = pack8(v + u * 8);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+#pragma unroll
             for (int u = 0; u < 4; ++u)
-              *reinterpret_cast<bf16x8*>(prow + (((h * 4 + u) ^ (lane & 7)) << 4)) = pack8(v + u * 8);
+              *reinterpret_cast<bf16x8*>(row + (((h * 4 + u) ^ (lane & 7)) << 4)) = pack8(v + u * 8);
           }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-          uint8_t* row = slab + lane * 128;
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            *reinterpret_cast<bf16x8*>(row + (((h * 4 + u) ^ (lane & 7)) << 4)) = pack8(v + u * 8);
           if (h == 1) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
@@ -593,7 +611,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (p.pre_act != nullptr && row_ok) {
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            if (n0 + u * 8 + 8 <= p.N) *reinterpret_cast<bf16x8*>(p.pre_act + aux_off + u * 8) = pack8(v + u * 8);
+            if (n0 + u * 8 + 8 <= p.N) {
+              if (p.aux_is_grad) {
+                float g8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) g8[j] = gelu_erf_grad(v[u * 8 + j]);
+                *reinterpret_cast<bf16x8*>(p.pre_act + aux_off + u * 8) = pack8(g8);
+              } else {
+                *reinterpret_cast<bf16x8*>(p.pre_act + aux_off + u * 8) = pack8(v + u * 8);
+              }
+            }
         }
         if (p.act == 1) {
 #pragma unroll
@@ -609,7 +636,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               float x[8];
               unpack8(*reinterpret_cast<const bf16x8*>(p.gelu_grad_of + aux_off + u * 8), x);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[u * 8 + j] *= gelu_erf_grad(x[j]);
+              for (int j = 0; j < 8; ++j) v[u * 8 + j] *= p.aux_is_grad ? x[j] : gelu_erf_grad(x[j]);
             }
         }
         if (p.use_dropout) {
@@ -722,7 +749,7 @@ template <int BN, bool A_MN, bool B_MN, bool F32OUT, int CTAS, int EPI = 0>
 static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d, const Params& p,
                   cudaStream_t stream, const CUtensorMap* pre = nullptr) {
   auto kern = gemm_kernel<BN, A_MN, B_MN, F32OUT, CTAS, EPI>;
-  constexpr int smem = SmemLayout<BN, CTAS, EPI == 3 ? 4 : EPI == 2 ? 2 : 1>::kTotal;
+  constexpr int smem = SmemLayout<BN, CTAS, (EPI == 3 || EPI == 5) ? 4 : (EPI == 2 || EPI == 4) ? 2 : 1>::kTotal;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool configured = false;  // per template instantiation
   if (!configured) {
@@ -836,6 +863,9 @@ extern "C" int mvptr_gemm(const mvptr_gemm_args* g, void* stream_) {
   p.inv_keep = p.use_dropout ? 1.0f / (1.0f - g->p_drop) : 1.0f;
   p.keep_thr = keep_threshold(g->p_drop);
   p.seed = g->seed;
+  p.aux_is_grad = g->aux_is_gelu_grad != 0;
+  if (p.aux_is_grad && g->pre_act && g->act != 1)
+    MVPTR_FAIL(MVPTR_ERR_ARG, "gemm: aux_is_gelu_grad with pre_act needs act = 1 (erf-GELU)");
   static const int debug_flags = getenv("MVPTR_GEMM_DEBUG") ? atoi(getenv("MVPTR_GEMM_DEBUG")) : 0;
   p.debug = debug_flags;
 
@@ -875,8 +905,15 @@ extern "C" int mvptr_gemm(const mvptr_gemm_args* g, void* stream_) {
   }
   static const char* kNames[4] = {"gemm[k,k]", "gemm[k,mn]", "gemm[mn,k]", "gemm[mn,mn]"};
   MVPTR_PROF(kNames[(g->a_mn ? 2 : 0) | (g->b_mn ? 1 : 0)], 2.0 * g->M * g->N * g->K, stream);
-  if (ggrad) return launch<256, false, true, false, 2, 3>(ta, tb, td, p, stream, &tp);
+  if (ggrad) {
+    if (p.aux_is_grad) return launch<256, false, true, false, 2, 5>(ta, tb, td, p, stream, &tp);
+    return launch<256, false, true, false, 2, 3>(ta, tb, td, p, stream, &tp);
+  }
   if (dual) {
+    if (p.aux_is_grad) {
+      if (ctas == 2) return launch<256, false, false, false, 2, 4>(ta, tb, td, p, stream, &tp);
+      return launch<256, false, false, false, 1, 4>(ta, tb, td, p, stream, &tp);
+    }
     if (ctas == 2) return launch<256, false, false, false, 2, 2>(ta, tb, td, p, stream, &tp);
     return launch<256, false, false, false, 1, 2>(ta, tb, td, p, stream, &tp);
   }

@@ -41,6 +41,16 @@ static int wgrad(const void* dY, int ld_dy, const void* X, int ld_x, int n_out, 
   return mvptr_gemm(&g, s);
 }
 
+static bool env_on(const char* name) { return !(getenv(name) && atoi(getenv(name)) == 0); }
+// pre_g carries gelu'(pre-activation) instead of the pre-activation when BOTH fused paths run (GELU in the
+// FFN1 epilogue, GELU' in the FFN2-dgrad epilogue): the forward epilogue gets gelu' from the erf it evaluates
+// anyway and the dgrad epilogue shrinks to one multiply.  Forward and backward must agree, hence one predicate.
+// MVPTR_GELU_GRAD_FACTOR=0 keeps the pre-activation (A/B runs).
+static bool pre_g_is_gelu_grad(int M, int I) {
+  static const bool on = env_on("MVPTR_GELU_GRAD_FACTOR") && env_on("MVPTR_FFN1_FUSED") && env_on("MVPTR_GELU_BWD_FUSED");
+  return on && (I % 64) == 0 && M > 128;
+}
+
 extern "C" int mvptr_layer_fwd(const mvptr_layer_args* a, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const int M = a->B * a->L, H = a->H, I = a->I;
@@ -64,14 +74,15 @@ extern "C" int mvptr_layer_fwd(const mvptr_layer_args* a, void* stream) {
   TRY(mvptr_add_ln_fwd(a->tmp, a->x, a->p_hidden, a->seed1, save ? a->pre1 : nullptr, a->ln1_g, a->ln1_b, a->a1, save ? a->st1 : nullptr,
                        save ? a->st1 + M : nullptr, M, H, a->eps, s));
   {  // BertIntermediate: gelu(dense(a1)), modeling_bert.py:394-397.  GELU runs in the GEMM epilogue (MUFU-cheap
-     // erf, common.cuh); in training the tile is stored twice -- pre-activation (for GELU') and activation --
-     // through the DUAL TMA-store slabs, so the [M, I] pre-activation is never read back in forward.
+     // erf, common.cuh); in training the tile is stored twice -- gelu'(pre-activation) (what backward needs; the
+     // pre-activation itself in the A/B fallbacks) and the activation -- through the DUAL TMA-store slabs, so
+     // the [M, I] pre-activation is never read back in forward.
     static const bool fused = !(getenv("MVPTR_FFN1_FUSED") && atoi(getenv("MVPTR_FFN1_FUSED")) == 0);
     if (fused) {
       mvptr_gemm_args g = gemm_base(a->a1, H, a->w_i, H, a->inter, I, M, I, H);
       g.bias = a->b_i;
       g.act = 1;
-      if (save) { g.pre_act = a->pre_g; g.ld_aux = I; }
+      if (save) { g.pre_act = a->pre_g; g.ld_aux = I; g.aux_is_gelu_grad = pre_g_is_gelu_grad(M, I); }
       TRY(mvptr_gemm(&g, s));
     } else {
       mvptr_gemm_args g = gemm_base(a->a1, H, a->w_i, H, a->pre_g, I, M, I, H);
@@ -109,6 +120,7 @@ extern "C" int mvptr_layer_bwd(const mvptr_layer_args* a, void* stream) {
       g.gelu_grad_of = a->pre_g;
       g.ld_aux = I;
       g.colsum = a->g_b_i;
+      g.aux_is_gelu_grad = pre_g_is_gelu_grad(M, I);
       TRY(mvptr_gemm(&g, s));
     } else {
       TRY(mvptr_gemm(&g, s));

@@ -258,18 +258,22 @@ small_head_bwd_dx_kernel(const float* __restrict__ dlogits, const bf16* __restri
 __global__ void __launch_bounds__(128)
 small_head_bwd_dw_kernel(const float* __restrict__ dlogits, const bf16* __restrict__ x, int ldx, float* __restrict__ dW,
                          float* __restrict__ db, int n, int H, int C) {
-  // grid (ceil(H/128), C)
+  // grid (ceil(H/128), C, row slices): every CTA reduces one slice of the rows and adds it atomically (a single
+  // CTA per column block walking all n rows serially took 0.13 ms for the 512 x 768 ITM head)
   const int c = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = (n + gridDim.z - 1) / gridDim.z;
+  const int r0 = blockIdx.z * per, r1 = min(n, r0 + per);
   if (i < H) {
     float s = 0.f;
-    for (int r = 0; r < n; ++r) s += dlogits[(size_t)r * C + c] * __bfloat162float(x[(size_t)r * ldx + i]);
+    for (int r = r0; r < r1; ++r) s += dlogits[(size_t)r * C + c] * __bfloat162float(x[(size_t)r * ldx + i]);
     atomicAdd(dW + (size_t)c * H + i, s);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && db) {
+  if (blockIdx.x == 0 && threadIdx.x < 32 && db) {
     float s = 0.f;
-    for (int r = 0; r < n; ++r) s += dlogits[(size_t)r * C + c];
-    atomicAdd(db + c, s);
+    for (int r = r0 + threadIdx.x; r < r1; r += 32) s += dlogits[(size_t)r * C + c];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) atomicAdd(db + c, s);
   }
 }
 // CE over tiny logits [n, C] fp32 with int64 labels -> loss (mean) and dlogits (already /n)
@@ -428,8 +432,9 @@ extern "C" int mvptr_small_head_bwd(const float* dlogits, const void* x, int ldx
     MVPTR_CHECK_LAUNCH("small_head_bwd_dx");
   }
   if (dW) {
-    small_head_bwd_dw_kernel<<<dim3((H + 127) / 128, C), 128, 0, (cudaStream_t)stream>>>(dlogits, (const bf16*)x, ldx,
-                                                                                          dW, db, n, H, C);
+    const int slices = n >= 512 ? 32 : (n + 15) / 16;
+    small_head_bwd_dw_kernel<<<dim3((H + 127) / 128, C, slices), 128, 0, (cudaStream_t)stream>>>(dlogits, (const bf16*)x,
+                                                                                                  ldx, dW, db, n, H, C);
     MVPTR_CHECK_LAUNCH("small_head_bwd_dw");
   }
   return 0;

@@ -462,6 +462,34 @@ __global__ void pad_cast_kernel(const T* __restrict__ src, long long ld_src, bf1
   if (c < K) v = (float)src[(size_t)r * ld_src + c];
   dst[(size_t)r * ld_dst + c] = __float2bfloat16(v);
 }
+// Same, 8 output columns per thread: one 16-byte store fed by four PAIR loads (a 2054-element row is only
+// 4-byte (bf16) / 8-byte (fp32) aligned, so pairs are the widest aligned source access).  Needs even K and
+// ld_src, ld_dst % 8 == 0 and a pair-aligned source.
+template <typename T>
+__global__ void __launch_bounds__(256)
+pad_cast8_kernel(const T* __restrict__ src, long long ld_src, bf16* __restrict__ dst, int ld_dst, int rows, int K) {
+  const int r = blockIdx.x;
+  const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
+  if (c0 >= ld_dst) return;
+  const T* s = src + (size_t)r * ld_src + c0;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    v[j] = v[j + 1] = 0.f;
+    if (c0 + j < K) {  // K even: a pair is either fully inside or fully outside
+      if constexpr (sizeof(T) == 4) {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(s + j));
+        v[j] = t.x;
+        v[j + 1] = t.y;
+      } else {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(s + j));
+        v[j] = __uint_as_float(w << 16);
+        v[j + 1] = __uint_as_float(w & 0xffff0000u);
+      }
+    }
+  }
+  *reinterpret_cast<bf16x8*>(dst + (size_t)r * ld_dst + c0) = pack8(v);
+}
 
 // additive attention mask: (1 - mask) * -10000   (modeling_vlbert.py:430-460), with an
 // optional per-row source remap and column window so the joint / hard-negative masks
@@ -720,6 +748,18 @@ extern "C" int mvptr_pad_cast(const void* src, int src_is_f32, long long ld_src,
                               void* stream) {
   MVPTR_PROF("pad_cast", 0, stream);
   if (rows <= 0) return 0;
+  const size_t pair_bytes = src_is_f32 ? 8 : 4;
+  const bool wide = (K % 2 == 0) && (ld_src % 2 == 0) && (ld_dst % 8 == 0) &&
+                    (reinterpret_cast<uintptr_t>(src) % pair_bytes == 0) && (reinterpret_cast<uintptr_t>(dst) % 16 == 0);
+  if (wide) {
+    dim3 grid(rows, (ld_dst / 8 + 255) / 256);
+    if (src_is_f32)
+      pad_cast8_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src, ld_src, (bf16*)dst, ld_dst, rows, K);
+    else
+      pad_cast8_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, ld_src, (bf16*)dst, ld_dst, rows, K);
+    MVPTR_CHECK_LAUNCH("pad_cast");
+    return 0;
+  }
   dim3 grid(rows, (ld_dst + 255) / 256);
   if (src_is_f32)
     pad_cast_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src, ld_src, (bf16*)dst, ld_dst, rows, K);

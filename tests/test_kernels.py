@@ -404,3 +404,69 @@ def test_adamw_matches_reference_trajectory(lib, golden_dir):
     O.adamw_step(a, gr.cpu()[: n // 2] * scale, mr[: n // 2], vr[: n // 2], 1, 0.01, weight_decay=0.1)
     O.adamw_step(b2, gr.cpu()[n // 2:] * scale, mr[n // 2:], vr[n // 2:], 1, 0.01, weight_decay=0.0)
     assert_close(p.cpu(), pr, 1e-4, 1e-5, "adamw clip + decay boundary")
+
+
+@pytest.mark.parametrize("K,f32", [(2054, False), (2054, True), (70, False), (71, False), (71, True)])
+def test_pad_cast_is_bit_exact(lib, K, f32):
+    """Region features [rows, K] -> bf16 [rows, pad8(K)] (modeling_vlbert.py:498-506 input staging): the 8-wide
+    pair-load kernel (even K) and the scalar fallback (odd K) both reproduce torch's cast bit for bit and zero
+    the padding columns."""
+    rows, Kp = 517, (K + 7) // 8 * 8
+    g = torch.Generator(device="cuda").manual_seed(K)
+    src = torch.randn(rows, K, device="cuda", generator=g)
+    src = src if f32 else src.to(BF16)
+    dst = torch.full((rows, Kp), 7.0, device="cuda", dtype=BF16)
+    lib.call("mvptr_pad_cast", src, int(f32), K, dst, Kp, rows, K)
+    assert torch.equal(dst[:, :K], src.to(BF16))
+    assert (dst[:, K:] == 0).all()
+
+
+def test_small_head_dw_row_slices(lib):
+    """ITM head weight gradient at the pre-training size (2B = 512 rows): the row-sliced reduction."""
+    n, H, C = 512, 768, 2
+    x, dl = rnd(n, H, seed=4), torch.randn(n, C, device="cuda") / n
+    W = rnd(C, H, scale=0.05, seed=5)
+    dx = torch.empty(n, H, device="cuda", dtype=BF16); dW = torch.zeros(C, H, device="cuda"); db = torch.zeros(C, device="cuda")
+    lib.call("mvptr_small_head_bwd", dl, x, H, W, dx, H, dW, db, n, H, C)
+    assert_close(dW, dl.t() @ x.float(), 1e-4, 1e-5, "small dW (512 rows)")
+    assert_close(db, dl.sum(0), 1e-4, 1e-6, "small db (512 rows)")
+    assert_close(dx, dl @ W.float(), 1e-2, 1e-5, "small dx (512 rows)")
+
+
+@pytest.mark.parametrize("M,N", [(515, 3072), (1000, 320)])
+def test_gemm_gelu_grad_factor_epilogues(lib, M, N):
+    """aux_is_gelu_grad: the FFN1 epilogue saves gelu'(pre-activation) (shared erf evaluation) and the FFN2-dgrad
+    epilogue multiplies by the saved factor -- lean tcgen05 epilogues (EPI 4 / 5) and the generic fallback."""
+    K = 768
+    A, B, bias = rnd(M, K, scale=0.5, seed=1), rnd(N, K, scale=0.05, seed=2), rnd(N, seed=3)
+    z = (A.float() @ B.float().t() + bias.float()).requires_grad_(True)
+    F.gelu(z).sum().backward()
+    gref = z.grad
+    out = torch.empty(M, N, device="cuda", dtype=BF16)
+    lib.gemm(A, B, out, M, N, K, lda=K, ldb=K, ldd=N, bias=bias, act="gelu")
+    auxs = []
+    for kw in (dict(cta_pair=1), dict(cta_pair=2), dict(block_n=128)):  # lean single / lean pair / generic epilogue
+        out2 = torch.zeros(M, N, device="cuda", dtype=BF16); aux = torch.zeros_like(out2)
+        lib.gemm(A, B, out2, M, N, K, lda=K, ldb=K, ldd=N, bias=bias, act="gelu", pre_act=aux, ld_aux=N,
+                 aux_is_gelu_grad=True, **kw)
+        assert_close(aux, gref, 1e-2, 1e-2, f"saved gelu' ({kw})")
+        if "cta_pair" in kw:
+            assert torch.equal(out2, out), "the activation must not depend on what the second store carries"
+        else:
+            assert_close(out2, F.gelu(z.detach()), 1e-2, 2e-2, "generic gelu")
+        auxs.append(aux)
+    assert torch.equal(auxs[0], auxs[1])
+    K2 = 256
+    dY, W = rnd(M, K2, scale=0.5, seed=5), rnd(K2, N, scale=0.05, seed=6)
+    aux = auxs[0]
+    ref = (dY.float() @ W.float()) * aux.float()
+    dx = torch.zeros(M, N, device="cuda", dtype=BF16)
+    cs = torch.full((N,), 0.25, device="cuda", dtype=F32)
+    lib.gemm(dY, W, dx, M, N, K2, lda=K2, ldb=N, ldd=N, b_mn=True, gelu_grad_of=aux, ld_aux=N, colsum=cs,
+             aux_is_gelu_grad=True)
+    assert_close(dx, ref, 1e-2, 1e-2, "acc * saved factor (lean)")
+    assert_close(cs, 0.25 + dx.float().sum(0), 1e-3, 2e-2, "fused bias-gradient column sums (factor mode)")
+    dx2 = torch.zeros(M, N, device="cuda", dtype=BF16)
+    lib.gemm(dY, W, dx2, M, N, K2, lda=K2, ldb=N, ldd=N, b_mn=True, gelu_grad_of=aux, ld_aux=N,
+             aux_is_gelu_grad=True, cta_pair=1)  # single-CTA tiles -> generic epilogue
+    assert_close(dx2, ref, 1e-2, 1e-2, "acc * saved factor (generic)")
