@@ -46,3 +46,12 @@ for a, bb in zip(evs, evs[1:]):
 print("largest gap totals (us/step) by preceding kernel:")
 for n, g in gaps.most_common(8):
     print(f"  {g/N:8.1f}  {n}")
+# the largest individual gaps with their neighbours (what the device was waiting for)
+big = []
+for a, bb in zip(evs, evs[1:]):
+    g = bb.time_range.start - a.time_range.end
+    if g > 15:
+        big.append((g, a.name.split("(")[0][-60:], bb.name.split("(")[0][-60:]))
+print(f"{len(big)} gaps > 15 us over {N} replays:")
+for g, a, bb in sorted(big, reverse=True)[:12]:
+    print(f"  {g:8.1f} us   after [{a}]   before [{bb}]")
