@@ -45,7 +45,7 @@ struct Params {
   uint32_t seed;
   int use_dropout;
   int aux_is_grad;  // the auxiliary tensor (pre_act / gelu_grad_of) carries gelu'(pre-activation), see the header
-  int debug;  // MVPTR_GEMM_DEBUG bit 0: skip the slab-reuse wait (timing experiment only, results may be wrong)
+  int debug;  // MVPTR_GEMM_DEBUG (timing experiments only, results wrong): bit 0 skips the slab-reuse wait, bit 1 the whole epilogue
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -494,6 +494,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       mbar_wait(tfull_bar + 8 * as, aph);
       tc_fence_after();
+      if (p.debug & 2) {  // timing experiment only (MVPTR_GEMM_DEBUG bit 1): no epilogue at all -> mainloop-only rate
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (kPair && !leader) mbar_arrive_remote(tempty_bar + 8 * as, 0);
+          else mbar_arrive(tempty_bar + 8 * as);
+        }
+        continue;
+      }
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + hf * kHalf;
 
       uint32_t rbuf[2][32];

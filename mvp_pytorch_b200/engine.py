@@ -486,6 +486,16 @@ def decoder_backward(rt, t, dlogits, wname, n_out, bias_name):
     # bias slot in the arena is padded to 8 elements, so the padded columns (zeros) are harmless
     rt.call("mvptr_colsum", dlogits, pitch, a.g_span(bias_name, pitch), n, pitch)
     wgrad(rt, dlogits, pitch, t, H, n_out, H, n, a.g(wname))
+    # dt[n, H] = dlogits[n, n_out] . W[n_out, H]: a few thousand rows x 768 columns is only ~54 output tiles
+    # for a 30 522-deep contraction (18-36 CTAs busy for 155 us in the ncu launch list) -> split K over the
+    # idle SMs, fp32 TMA reduce-add, one cast
+    split = split_k_for(n, H, n_out)
+    if split > 1:
+        dt32 = torch.zeros(n, H, device=t.device, dtype=F32)
+        dgrad(rt, dlogits, pitch, a.w(wname), H, n, n_out, H, dt32, accumulate=True, split_k=split)
+        dt = torch.empty(n, H, device=t.device, dtype=BF16)
+        rt.call("mvptr_cast_f32_bf16", dt32, dt, n * H)
+        return dt
     dt = torch.empty(n, H, device=t.device, dtype=BF16)
     dgrad(rt, dlogits, pitch, a.w(wname), H, n, n_out, H, dt)
     return dt
