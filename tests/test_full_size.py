@@ -79,7 +79,10 @@ def test_c4_vqa_batch_512_logits_match_small_batch_and_oracle_and_backward_scale
     loss2.backward()
     torch.cuda.synchronize()
     rel = float((arena.grad - 2.0 * g1).norm() / (2.0 * g1).norm())
-    assert rel < 1e-5, f"backward is not linear in the incoming gradient: rel {rel:.2e}"
+    # (the answer-decoder dgrad is a split-K fp32 reduce-add followed by ONE cast to bf16: an unordered sum that
+    # lands on the other side of a bf16 rounding boundary moves that element by one bf16 ulp -> ~5e-5 overall;
+    # a real scaling bug would show up at >= 1e-2)
+    assert rel < 2e-4, f"backward is not linear in the incoming gradient: rel {rel:.2e}"
     # rows of the full batch == the same rows run alone == the oracle
     # (same mode as the big step: with activations saved for backward, LayerNorm normalises the bf16
     # rounding of its input -- the value backward will see -- so no_grad outputs differ by an ulp)
