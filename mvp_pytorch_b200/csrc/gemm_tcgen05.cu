@@ -45,7 +45,7 @@ struct Params {
   uint32_t seed;
   int use_dropout;
   int aux_is_grad;  // the auxiliary tensor (pre_act / gelu_grad_of) carries gelu'(pre-activation), see the header
-  int debug;  // MVPTR_GEMM_DEBUG (timing experiments only, results wrong): bit 0 skips the slab-reuse wait, bit 1 the whole epilogue
+  int debug;  // MVPTR_GEMM_DEBUG (timing experiments only, results wrong): bit 0 skips the slab-reuse wait, bit 1 the whole epilogue, bit 2 everything after the TMEM reads, bit 3 the TMA stores
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -571,6 +571,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         tc_wait_ld();
         if (c + 1 < kChunks && n0 + 32 < p.N) tc_ld32(t_row + (c + 1) * 32, rbuf[(c + 1) & 1]);
+        if (p.debug & 4) continue;  // timing experiment: TMEM reads only (no conversion, no slab, no store)
         float v[32];
         if (p.alpha != 1.0f) {
 #pragma unroll
@@ -679,7 +680,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (last_in_box) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && !(p.debug & 8)) {  // bit 3: slab written, TMA store skipped
             const int ng0 = n0 - h * 32;
             if (p.accumulate)
               tma_reduce_add_2d(&tmD, smem_u32(slab), ng0, m_base + q * 32);
