@@ -429,46 +429,47 @@ def run_b200(args):
         graphed.check_overflow()
     launches_per_step = launches / args.steps
 
-    # ---- (2) end to end: pinned host inputs copied every step (prefetched on a copy stream), six
-    #          losses read back every step into pinned memory
-    copy_stream = torch.cuda.Stream()
+    # ---- (2) end to end through the public API: pinned host batches -> data.PinnedPrefetcher (H2D on a copy
+    #          stream, double buffered) -> the training step -> six losses read back into pinned memory, every step
+    from mvp_pytorch_b200.data import PinnedPrefetcher
     loss_host = torch.zeros(args.steps, 6, dtype=torch.float32).pin_memory()
-    staged = [None, None]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    freed = [torch.cuda.Event(), torch.cuda.Event()]
     e2e_mode = set(filter(None, (args.e2e_debug or "").split(",")))  # A/B only: "noh2d", "nod2h"
 
-    def stage(i):
-        slot = i & 1
+    def run_e2e(steps):
+        """Enqueues `steps` end-to-end steps; returns the host->device bytes copied."""
         if "noh2d" in e2e_mode:
-            staged[slot] = resident[i % n_batches]
-            return
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(freed[slot])
-            staged[slot] = {k: v.to(dev, non_blocking=True) for k, v in host[i % n_batches].items()}
-            ready[slot].record(copy_stream)
+            feed, pf = (resident[i % n_batches] for i in range(steps)), None
+        else:
+            pf = PinnedPrefetcher((host[i % n_batches] for i in range(steps)), dev, depth=2)
+            feed = pf
+        for i, batch in enumerate(feed):
+            out = train_step(batch)
+            if "nod2h" not in e2e_mode:
+                loss_host[i].copy_(out if torch.is_tensor(out) else torch.stack([x.detach().float() for x in out]),
+                                   non_blocking=True)
+        return pf.h2d_bytes if pf is not None else 0
 
-    def e2e_step(i):
-        slot = i & 1
-        if i == 0:
-            stage(0)
-        if i + 1 < args.steps:
-            stage(i + 1)
-        if "noh2d" not in e2e_mode:
-            torch.cuda.current_stream().wait_event(ready[slot])
-        out = train_step(staged[slot])
-        if "nod2h" not in e2e_mode:
-            loss_host[i].copy_(out if torch.is_tensor(out) else torch.stack([x.detach().float() for x in out]),
-                               non_blocking=True)
-        freed[slot].record()
+    def timed_e2e(steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        nbytes = run_e2e(steps)
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, nbytes
 
     if args.quick:  # A/B runs: the resident step only (plus the end-to-end loop when --e2e-debug is given)
         res = {"quick": True, "n_gpus": world, "ms_per_step": ms / args.steps,
                "pairs_per_s": B * world * args.steps / (ms / 1e3)}
         if args.e2e_debug is not None:
-            for f in freed:
-                f.record()
-            ms_q, _ = timed(e2e_step, args.steps)
+            ms_q, _ = timed_e2e(args.steps)
             res["e2e_ms_per_step"], res["e2e_debug"] = ms_q / args.steps, args.e2e_debug
             ms_r, _ = timed(lambda i: train_step(resident[i % n_batches]), args.steps)
             res["resident_again_ms_per_step"] = ms_r / args.steps
@@ -480,10 +481,9 @@ def run_b200(args):
         _shutdown(world)
         return
 
-    for f in freed:
-        f.record()
-    ms_e2e, _ = timed(e2e_step, args.steps)
+    ms_e2e, e2e_bytes = timed_e2e(args.steps)
     assert torch.isfinite(loss_host).all(), "non-finite loss in the end-to-end run"
+    assert e2e_bytes == h2d_bytes * args.steps, (e2e_bytes, h2d_bytes)  # every step's inputs crossed PCIe
 
     # The captured graph holds NCCL work: release it before anything tears the communicator down
     # (destroying a communicator under a live graph hangs).
