@@ -116,11 +116,6 @@ class AdamW(Optimizer):
         self._dyn_host = torch.zeros(2, dtype=torch.float32).pin_memory()
         self._dyn = torch.zeros(2, device=a.device, dtype=torch.float32)
 
-    def before_replay(self):
-        """Host side of one graph replay: advance the step, publish {lr, step} in the pinned source."""
-        self._step += 1
-        self._dyn_host[0], self._dyn_host[1] = float(self.param_groups[0]["lr"]), float(self._step)
-
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
