@@ -44,7 +44,6 @@ struct Params {
   uint32_t keep_thr;
   uint32_t seed;
   int use_dropout;
-  int wide_store;   // generic bf16 epilogue: the 4 warps of a column half share ONE 128-row TMA store (map in tmP)
   int aux_is_grad;  // the auxiliary tensor (pre_act / gelu_grad_of) carries gelu'(pre-activation), see the header
   int debug;  // MVPTR_GEMM_DEBUG (timing experiments only, results wrong): bit 0 skips the slab-reuse wait, bit 1 the whole epilogue, bit 2 everything after the TMEM reads, bit 3 the TMA stores
 };
@@ -614,14 +613,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         const int h = c % kChunksPerStore;  // position of this chunk inside the store box
         if (h == 0 && store_pending) {
-          if (p.wide_store) {
-            // the warp that issued the 128-row store waits for its shared-memory reads, then releases the other three
-            if (q == 0 && lane == 0) tma_wait_read<0>();
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + hf) : "memory");
-          } else {
-            if (lane == 0 && !(p.debug & 1)) tma_wait_read<0>();  // previous box(es) have been read out of the slab(s)
-            __syncwarp();
-          }
+          if (lane == 0 && !(p.debug & 1)) tma_wait_read<0>();  // previous box(es) have been read out of the slab(s)
+          __syncwarp();
           store_pending = false;
         }
         const size_t aux_off = (size_t)m * p.ld_aux + n0;
@@ -684,17 +677,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             *reinterpret_cast<bf16x8*>(row + (((h * 4 + u) ^ (lane & 7)) << 4)) = pack8(v + u * 8);
         }
         const bool last_in_box = (h == kChunksPerStore - 1) || (n0 + 32 >= p.N) || (c == kChunks - 1);
-        if (last_in_box && p.wide_store) {
-          // The slabs of warps q = 0..3 of a column half are contiguous: together a [128 rows][64 columns] box in the
-          // same 128B-swizzled layout.  One TMA store per 16 KB instead of four per 4 KB: 4 stores per tile, not 16.
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + hf) : "memory");  // all four row quarters are in shared memory
-          if (q == 0 && lane == 0) {
-            tma_store_2d(&tmP, smem_u32(slab), n0 - h * 32, m_base);  // q == 0: this warp's slab starts the 16 KB box
-            tma_commit();
-          }
-          store_pending = true;
-        } else if (last_in_box) {
+        if (last_in_box) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0 && !(p.debug & 8)) {  // bit 3: slab written, TMA store skipped
@@ -811,16 +794,16 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap&
 
 template <int BN, int CTAS>
 static int dispatch(const mvptr_gemm_args* g, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& d,
-                    const Params& p, cudaStream_t s, const CUtensorMap* wide = nullptr) {
+                    const Params& p, cudaStream_t s) {
   const int key = (g->a_mn ? 4 : 0) | (g->b_mn ? 2 : 0) | (g->d_is_f32 ? 1 : 0);
   switch (key) {
-    case 0: return launch<BN, false, false, false, CTAS>(a, b, d, p, s, wide);
+    case 0: return launch<BN, false, false, false, CTAS>(a, b, d, p, s);
     case 1: return launch<BN, false, false, true, CTAS>(a, b, d, p, s);
-    case 2: return launch<BN, false, true, false, CTAS>(a, b, d, p, s, wide);
+    case 2: return launch<BN, false, true, false, CTAS>(a, b, d, p, s);
     case 3: return launch<BN, false, true, true, CTAS>(a, b, d, p, s);
-    case 4: return launch<BN, true, false, false, CTAS>(a, b, d, p, s, wide);
+    case 4: return launch<BN, true, false, false, CTAS>(a, b, d, p, s);
     case 5: return launch<BN, true, false, true, CTAS>(a, b, d, p, s);
-    case 6: return launch<BN, true, true, false, CTAS>(a, b, d, p, s, wide);
+    case 6: return launch<BN, true, true, false, CTAS>(a, b, d, p, s);
     default: return launch<BN, true, true, true, CTAS>(a, b, d, p, s);
   }
 }
@@ -891,7 +874,6 @@ extern "C" int mvptr_gemm(const mvptr_gemm_args* g, void* stream_) {
   p.keep_thr = keep_threshold(g->p_drop);
   p.seed = g->seed;
   p.aux_is_grad = g->aux_is_gelu_grad != 0;
-  p.wide_store = 0;
   if (p.aux_is_grad && g->pre_act && g->act != 1)
     MVPTR_FAIL(MVPTR_ERR_ARG, "gemm: aux_is_gelu_grad with pre_act needs act = 1 (erf-GELU)");
   static const int debug_flags = getenv("MVPTR_GEMM_DEBUG") ? atoi(getenv("MVPTR_GEMM_DEBUG")) : 0;
@@ -948,15 +930,6 @@ extern "C" int mvptr_gemm(const mvptr_gemm_args* g, void* stream_) {
   if (lean) {
     if (ctas == 2) return launch<256, false, false, false, 2, 1>(ta, tb, td, p, stream);
     return launch<256, false, false, false, 1, 1>(ta, tb, td, p, stream);
-  }
-  // generic epilogue, bf16 output, plain stores: 128-row store boxes (MVPTR_GEMM_WIDE_STORE=0 keeps 32-row boxes)
-  static const bool wide_ok = !(getenv("MVPTR_GEMM_WIDE_STORE") && atoi(getenv("MVPTR_GEMM_WIDE_STORE")) == 0);
-  if (wide_ok && !g->d_is_f32 && !g->accumulate && split == 1 && !debug_flags) {
-    rc = make_map(&tp, g->D, false, g->N, g->M, (uint64_t)g->ldd * 2, 64, BM);
-    if (rc) return rc;
-    p.wide_store = 1;
-    if (ctas == 2) return dispatch<256, 2>(g, ta, tb, td, p, stream, &tp);
-    return bn == 256 ? dispatch<256, 1>(g, ta, tb, td, p, stream, &tp) : dispatch<128, 1>(g, ta, tb, td, p, stream, &tp);
   }
   if (ctas == 2) return dispatch<256, 2>(g, ta, tb, td, p, stream);
   return bn == 256 ? dispatch<256, 1>(g, ta, tb, td, p, stream) : dispatch<128, 1>(g, ta, tb, td, p, stream);
