@@ -1,0 +1,70 @@
+"""Golden vectors of BASELINE.json configs[0] from the REAL reference.  TEST INFRASTRUCTURE ONLY.
+
+    python -B oracle/make_golden_base.py        (authoring container: needs /root/reference)
+
+"MVP base cross-modal encoder forward, random-init, synthetic batch 8 x (35 text+phrase tokens, 50 regions x
+2054-d) on CPU fp32": the unmodified reference ``BiImageBertRep`` (oscar/modeling/modeling_vlbert.py:2509-2557)
+at the base shape (hidden 768, 12 heads, 6+6+6 layers, vocabulary 86 051) on the seeded synthetic batch with
+ragged masks.  Asserts that ``oracle/mvptr_oracle.py`` reproduces it to <= 2e-5 and stores a compact sample of
+the outputs (the pooled vectors in full, ROWS valid positions per sequence of the three token outputs, and
+whole-tensor checksums) in ``tests/golden/rep_base.pt``.  Weights / inputs are regenerated from seeds.
+"""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import mvptr_oracle as O  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+from oracle.make_golden import checksum, close  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden", "rep_base.pt")
+ROWS = 6
+DIMS = (8, 35, 20, 50)  # B, La, Lt, R of configs[0]
+WSEED, BSEED = 0, 1
+
+
+def sample_rows(mask):
+    """ROWS evenly spread VALID positions per sequence -> [B, ROWS] int64 (deterministic)."""
+    out = []
+    for m in mask:
+        idx = torch.nonzero(m > 0).reshape(-1)
+        pick = torch.linspace(0, idx.numel() - 1, ROWS).round().long()
+        out.append(idx[pick])
+    return torch.stack(out)
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    mv = ref_shim.load()
+    cfg = O.Cfg()
+    B, La, Lt, R = DIMS
+    sd = O.random_state_dict(cfg, "rep", seed=WSEED)
+    batch = O.synthetic_batch(cfg, B, La, Lt, R, seed=BSEED, ragged=True)
+    model = mv.BiImageBertRep(ref_shim.make_config(mv, cfg)).eval()
+    model.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        seq, pooled, (txt, vis) = model(max_tag_length=Lt, **batch)
+        o_seq, o_pooled, (o_txt, o_vis) = O.rep_forward(sd, cfg, max_tag_length=Lt, **batch)
+    jm = torch.cat([batch["attention_mask_a"], batch["attention_mask_b"][:, Lt:]], 1)
+    for a, b, m, n in ((o_seq, seq, jm, "seq"), (o_txt, txt, batch["attention_mask_a"], "txt"),
+                       (o_vis, vis, batch["attention_mask_b"], "vis")):
+        print("base", n, close(a[m.bool()], b[m.bool()], what=n))
+    print("base pooled", close(o_pooled, pooled, what="pooled"))
+    rows = {"seq": sample_rows(jm), "txt": sample_rows(batch["attention_mask_a"]), "vis": sample_rows(batch["attention_mask_b"])}
+    take = lambda t, r: torch.gather(t, 1, r[:, :, None].expand(-1, -1, t.shape[2])).clone()
+    torch.save(dict(head="rep", wseed=WSEED, bseed=BSEED, dims=DIMS, wsum=checksum(sd.values()),
+                    bsum=checksum([batch["img_feats"], batch["input_ids_a"]]), pooled=pooled.clone(),
+                    rows=rows, seq_rows=take(seq, rows["seq"]), txt_rows=take(txt, rows["txt"]),
+                    vis_rows=take(vis, rows["vis"]),
+                    valid_abs_sum=dict(seq=float(seq[jm.bool()].double().abs().sum()),
+                                       txt=float(txt[batch["attention_mask_a"].bool()].double().abs().sum()),
+                                       vis=float(vis[batch["attention_mask_b"].bool()].double().abs().sum()))), OUT)
+    print("wrote", OUT, os.path.getsize(OUT), "bytes")
+
+
+if __name__ == "__main__":
+    main()

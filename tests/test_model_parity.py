@@ -199,3 +199,23 @@ def test_base_shape_forward_matches_oracle():
         seq2, pooled2, _ = model(max_tag_length=Lt, **P.to_cuda(b2))
     assert torch.equal(pooled2, pooled)
     assert torch.equal(seq2[joint_mask.bool().cuda()], seq[joint_mask.bool().cuda()])
+
+
+def test_base_shape_matches_reference_golden(golden_dir):
+    """BASELINE.json configs[0] against the REAL reference's outputs at the base shape (tests/golden/rep_base.pt,
+    oracle/make_golden_base.py): pooled vectors and sampled valid rows of all three token outputs."""
+    g = _golden(golden_dir, "rep_base.pt")
+    cfg = O.Cfg()
+    sd = O.random_state_dict(cfg, g["head"], seed=g["wseed"])
+    B, La, Lt, R = g["dims"]
+    b = O.synthetic_batch(cfg, B, La, Lt, R, seed=g["bseed"], ragged=True)
+    model = P.build("BiImageBertRep", cfg, sd)
+    with torch.no_grad():
+        seq, pooled, (txt, vis) = model(max_tag_length=Lt, **P.to_cuda(b))
+    take = lambda t, r: torch.gather(t.float().cpu(), 1, r[:, :, None].expand(-1, -1, t.shape[2]))
+    P.close(pooled, g["pooled"], 2e-2, 3e-2, "pooled vs reference")
+    for name, t, tol in (("txt", txt, 3e-2), ("vis", vis, 3e-2), ("seq", seq, 4e-2)):
+        got, ref = take(t, g["rows"][name]), g[name + "_rows"]
+        err = (got - ref).abs()
+        frac = (err > tol + 2e-2 * ref.abs()).float().mean().item()
+        assert frac < 2e-3, f"{name}: {frac:.4%} of the sampled elements beyond tolerance, max err {err.max():.4f}"

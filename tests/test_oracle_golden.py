@@ -124,3 +124,29 @@ def test_adamw_known_answers(golden_dir):
         grad = (w - torch.tensor([0.4, 0.2, -0.5, 0.1])) * 2
         O.adamw_step(w, grad, m, v, it + 1, used[it], weight_decay=0.01)
         _close(w, g["traj"][it], tol=1e-6)
+
+
+def test_rep_base_shape_matches_reference(golden_dir):
+    """BASELINE.json configs[0] at the REAL base shape (hidden 768, 12 heads, 18 layers, 2054-d regions, batch 8 x
+    35 tokens + 50 regions): the oracle against what the unmodified reference produced
+    (oracle/make_golden_base.py: pooled vectors in full, sampled valid rows, whole-tensor checksums)."""
+    g = _load(golden_dir, "rep_base.pt")
+    cfg = O.Cfg()
+    sd = O.random_state_dict(cfg, g["head"], seed=g["wseed"])
+    assert abs(_sum(sd.values()) - g["wsum"]) < 1e-6 * g["wsum"], "weight generator drifted"
+    B, La, Lt, R = g["dims"]
+    batch = O.synthetic_batch(cfg, B, La, Lt, R, seed=g["bseed"], ragged=True)
+    assert abs(_sum([batch["img_feats"], batch["input_ids_a"]]) - g["bsum"]) < 1e-6 * g["bsum"]
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        seq, pooled, (txt, vis) = O.rep_forward(sd, cfg, max_tag_length=Lt, **batch)
+    take = lambda t, r: torch.gather(t, 1, r[:, :, None].expand(-1, -1, t.shape[2]))
+    _close(pooled, g["pooled"])
+    _close(take(seq, g["rows"]["seq"]), g["seq_rows"])
+    _close(take(txt, g["rows"]["txt"]), g["txt_rows"])
+    _close(take(vis, g["rows"]["vis"]), g["vis_rows"])
+    jm = torch.cat([batch["attention_mask_a"], batch["attention_mask_b"][:, Lt:]], 1).bool()
+    for name, t, m in (("seq", seq, jm), ("txt", txt, batch["attention_mask_a"].bool()),
+                       ("vis", vis, batch["attention_mask_b"].bool())):
+        s = float(t[m].double().abs().sum())
+        assert abs(s - g["valid_abs_sum"][name]) < 1e-5 * g["valid_abs_sum"][name], name
