@@ -66,5 +66,56 @@ def main():
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 
 
+def pretrain_case():
+    """BASELINE.json configs[1] per-pair shape (40 text+phrase tokens, 20 tags, 50 regions) at the base model size,
+    batch 6, forward + backward of the unmodified reference BiBertImgForPreTraining (modeling_vlbert.py:1133-1311)
+    with its RNG draws replaced by recorded values -> tests/golden/pretrain_base.pt (six losses, every gradient
+    norm, a few small gradient tensors in full)."""
+    from oracle.make_golden import Inject
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    mv = ref_shim.load()
+    cfg = O.Cfg()
+    B, La, Lt, R = 6, 40, 20, 50
+    sd = O.random_state_dict(cfg, "pretrain", seed=7)
+    batch = O.synthetic_batch(cfg, B, La, Lt, R, seed=17, ragged=True, with_labels=True)
+    model = mv.BiBertImgForPreTraining(ref_shim.make_config(mv, cfg, max_text_seq_length=La)).train()
+    model.load_state_dict(sd, strict=True)
+    n_ph = (batch["phrase_index"][:, 1] - batch["phrase_index"][:, 0]).tolist()
+    randint_seq, choice_seq = [], []
+    for b in range(B):  # call order inside get_pos_neg_sims: pos randint, random.choice, neg randint
+        if n_ph[b] > 0:
+            randint_seq.append(batch["rand_pos"][b, : n_ph[b]])
+        choice_seq.append(int(batch["neg_img"][b]))
+        if n_ph[b] > 0:
+            randint_seq.append(batch["rand_neg"][b, : n_ph[b]])
+    kw = dict(input_ids_a=batch["input_ids_a"], token_type_ids_a=batch["token_type_ids_a"],
+              attention_mask_a=batch["attention_mask_a"], masked_lm_labels_a=batch["masked_lm_labels_a"],
+              input_ids_b=batch["input_ids_b"], token_type_ids_b=batch["token_type_ids_b"],
+              attention_mask_b=batch["attention_mask_b"], masked_lm_labels_b=batch["masked_lm_labels_b"],
+              img_feats=batch["img_feats"], max_tag_length=Lt, img_index=batch["img_index"],
+              phrase_index=batch["phrase_index"])
+    with Inject(mv, dice=batch["dice_index"], randint_seq=randint_seq, choice_seq=choice_seq):
+        losses = model(**kw)
+    losses[0].backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    with torch.no_grad():
+        o_losses = O.pretrain_forward(sd, cfg, dice_index=batch["dice_index"], neg_img=batch["neg_img"],
+                                      rand_pos=batch["rand_pos"], rand_neg=batch["rand_neg"], **kw)
+    for i, (a, b) in enumerate(zip(o_losses, losses)):
+        print("pretrain base loss", i, float(b), close(a.detach(), b.detach(), what=f"loss{i}"))
+    keep = [k for k in grads if grads[k].numel() <= 3072 and ("layer.0." in k or "layer.5." in k or "layer" not in k)]
+    out = os.path.join(os.path.dirname(OUT), "pretrain_base.pt")
+    torch.save(dict(head="pretrain", wseed=7, bseed=17, dims=(B, La, Lt, R), wsum=checksum(sd.values()),
+                    losses=[l.detach().clone() for l in losses],
+                    grad_norms={k: float(g.norm()) for k, g in grads.items()},
+                    grads={k: grads[k] for k in keep},
+                    no_grad=sorted(k for k in sd if k not in grads)), out)
+    print("wrote", out, os.path.getsize(out), "bytes;", len(keep), "gradient tensors in full,", len(grads), "norms")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) < 2 or sys.argv[1] == "rep":
+        main()
+    if len(sys.argv) < 2 or sys.argv[1] == "pretrain":
+        pretrain_case()

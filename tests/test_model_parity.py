@@ -219,3 +219,33 @@ def test_base_shape_matches_reference_golden(golden_dir):
         err = (got - ref).abs()
         frac = (err > tol + 2e-2 * ref.abs()).float().mean().item()
         assert frac < 2e-3, f"{name}: {frac:.4%} of the sampled elements beyond tolerance, max err {err.max():.4f}"
+
+
+def test_pretrain_base_shape_losses_and_grads_match_reference_golden(golden_dir):
+    """The pre-training step at the base model size (BASELINE configs[1] per-pair shape, batch 6) against the REAL
+    reference (tests/golden/pretrain_base.pt): six losses, every gradient norm, 76 small gradient tensors."""
+    g = _golden(golden_dir, "pretrain_base.pt")
+    cfg = O.Cfg()
+    sd = O.random_state_dict(cfg, "pretrain", seed=g["wseed"])
+    B, La, Lt, R = g["dims"]
+    b = O.synthetic_batch(cfg, B, La, Lt, R, seed=g["bseed"], ragged=True, with_labels=True)
+    torch.set_num_threads(os.cpu_count() or 8)
+    model, losses = _run_pretrain(cfg, sd, b, Lt)
+    names = ["total", "vis_mlm", "vsc", "mlm", "itm", "wra"]
+    for n, a, r in zip(names, losses, g["losses"]):
+        P.close(a.detach(), r, 1.5e-2, 1e-2, n)
+    params = dict(model.named_parameters())
+    bad = []
+    for k, gr in g["grads"].items():
+        rel = P.rel_l2(params[k].grad, gr)
+        if rel >= 5e-2:
+            bad.append((k, rel))
+    assert not bad, f"gradients beyond 5e-2 relative L2: {bad[:6]}"
+    off = []
+    for k, n in g["grad_norms"].items():
+        got = float(params[k].grad.float().norm())
+        if abs(got - n) > 0.06 * n + 1e-4:
+            off.append((k, got, n))
+    assert not off, f"gradient norms off by more than 6 %: {off[:6]}"
+    for k in g["no_grad"]:
+        assert float(params[k].grad.abs().max()) == 0.0

@@ -150,3 +150,25 @@ def test_rep_base_shape_matches_reference(golden_dir):
                        ("vis", vis, batch["attention_mask_b"].bool())):
         s = float(t[m].double().abs().sum())
         assert abs(s - g["valid_abs_sum"][name]) < 1e-5 * g["valid_abs_sum"][name], name
+
+
+def test_pretrain_base_shape_losses_match_reference(golden_dir):
+    """BASELINE.json configs[1] per-pair shape at the base model size (batch 6): the six pre-training losses of the
+    oracle against the unmodified reference's (oracle/make_golden_base.py pretrain)."""
+    g = _load(golden_dir, "pretrain_base.pt")
+    cfg = O.Cfg()
+    sd = O.random_state_dict(cfg, g["head"], seed=g["wseed"])
+    assert abs(_sum(sd.values()) - g["wsum"]) < 1e-6 * g["wsum"], "weight generator drifted"
+    B, La, Lt, R = g["dims"]
+    b = O.synthetic_batch(cfg, B, La, Lt, R, seed=g["bseed"], ragged=True, with_labels=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        losses = O.pretrain_forward(sd, cfg, b["input_ids_a"], b["token_type_ids_a"], b["attention_mask_a"],
+                                    b["masked_lm_labels_a"], b["input_ids_b"], b["token_type_ids_b"],
+                                    b["attention_mask_b"], b["masked_lm_labels_b"], b["img_feats"], max_tag_length=Lt,
+                                    img_index=b["img_index"], phrase_index=b["phrase_index"],
+                                    dice_index=b["dice_index"], neg_img=b["neg_img"], rand_pos=b["rand_pos"],
+                                    rand_neg=b["rand_neg"])
+    assert len(losses) == len(g["losses"]) == 6
+    for a, r in zip(losses, g["losses"]):
+        _close(a, r)
