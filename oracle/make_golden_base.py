@@ -114,8 +114,45 @@ def pretrain_case():
     print("wrote", out, os.path.getsize(out), "bytes;", len(keep), "gradient tensors in full,", len(grads), "norms")
 
 
+def vqa_case():
+    """BASELINE.json configs[3] shape (max_seq 128 + 5 phrase slots, 20 tags, 50 regions, 3129 answers, BCE loss) at
+    the base model size, batch 4: forward + backward of the unmodified reference BiImageBertForVQA
+    (modeling_vlbert.py:1801-1870) -> tests/golden/vqa_base.pt (loss, logits, all gradient norms)."""
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    mv = ref_shim.load()
+    cfg = O.Cfg(num_labels=3129, loss_type="bce", qa_answer_size=3129)
+    B, La, Lt, R = 4, 133, 20, 50
+    sd = O.random_state_dict(cfg, "vqa", seed=8)
+    batch = O.synthetic_batch(cfg, B, La, Lt, R, seed=18, ragged=True)
+    g = torch.Generator().manual_seed(48)
+    labels = torch.zeros(B, 3129)
+    for b in range(B):  # sparse soft scores as in VQA v2 (SURVEY 8d C4)
+        idx = torch.randperm(3129, generator=g)[:4]
+        labels[b, idx] = torch.tensor([0.3, 0.6, 0.9, 1.0])
+    model = mv.BiImageBertForVQA(ref_shim.make_config(mv, cfg)).train()
+    model.load_state_dict(sd, strict=True)
+    loss, logits = model(labels=labels, max_tag_length=Lt, **batch)[:2]
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    with torch.no_grad():
+        o_loss, o_logits = O.vqa_forward(sd, cfg, batch["input_ids_a"], batch["token_type_ids_a"],
+                                         batch["attention_mask_a"], labels, batch["input_ids_b"],
+                                         batch["token_type_ids_b"], batch["attention_mask_b"], batch["img_feats"],
+                                         max_tag_length=Lt)
+    print("vqa base loss", float(loss), close(o_loss, loss.detach(), what="loss"), "logits",
+          close(o_logits, logits.detach(), what="logits"))
+    out = os.path.join(os.path.dirname(OUT), "vqa_base.pt")
+    torch.save(dict(head="vqa", wseed=8, bseed=18, dims=(B, La, Lt, R), labels=labels, wsum=checksum(sd.values()),
+                    loss=loss.detach().clone(), logits=logits.detach().clone(),
+                    grad_norms={k: float(v.norm()) for k, v in grads.items()}), out)
+    print("wrote", out, os.path.getsize(out), "bytes")
+
+
 if __name__ == "__main__":
     if len(sys.argv) < 2 or sys.argv[1] == "rep":
         main()
+    if len(sys.argv) < 2 or sys.argv[1] == "vqa":
+        vqa_case()
     if len(sys.argv) < 2 or sys.argv[1] == "pretrain":
         pretrain_case()

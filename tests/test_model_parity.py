@@ -262,3 +262,28 @@ def test_pretrain_base_shape_losses_and_grads_match_reference_golden(golden_dir)
     assert not off, f"gradient norms off by more than 8 %: {off[:6]}"
     for k in g["no_grad"]:
         assert float(params[k].grad.abs().max()) == 0.0
+
+
+def test_vqa_base_shape_matches_reference_golden(golden_dir):
+    """VQA fine-tune step at the base model size (BASELINE configs[3] shape, batch 4) against the REAL reference
+    (tests/golden/vqa_base.pt): BCE loss, the 3129-way logits and every gradient norm."""
+    g = _golden(golden_dir, "vqa_base.pt")
+    cfg = O.Cfg(num_labels=3129, loss_type="bce", qa_answer_size=3129)
+    sd = O.random_state_dict(cfg, "vqa", seed=g["wseed"])
+    B, La, Lt, R = g["dims"]
+    b = P.to_cuda(O.synthetic_batch(cfg, B, La, Lt, R, seed=g["bseed"], ragged=True))
+    model = P.build("BiImageBertForVQA", cfg, sd, train=True)
+    out = model(labels=g["labels"].cuda(), max_tag_length=Lt, **b)
+    loss, logits = out[0], out[1]
+    model.zero_grad()
+    loss.backward()
+    torch.cuda.synchronize()
+    P.close(loss.detach(), g["loss"], 1.5e-2, 1e-2, "vqa loss (base shape)")
+    P.close(logits.detach(), g["logits"], 2e-2, 4e-2, "vqa logits (base shape)")
+    params = dict(model.named_parameters())
+    off = []
+    for k, n in g["grad_norms"].items():
+        got = float(params[k].grad.float().norm())
+        if abs(got - n) > 0.1 * n + 2e-3:
+            off.append((k, got, n))
+    assert not off, f"gradient norms off by more than 10 %: {off[:6]}"

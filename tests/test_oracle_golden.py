@@ -172,3 +172,20 @@ def test_pretrain_base_shape_losses_match_reference(golden_dir):
     assert len(losses) == len(g["losses"]) == 6
     for a, r in zip(losses, g["losses"]):
         _close(a, r)
+
+
+def test_vqa_base_shape_matches_reference(golden_dir):
+    """BASELINE.json configs[3] shape (133 text tokens, 20 tags, 50 regions, 3129 answers, BCE) at the base model
+    size, batch 4: oracle loss / logits against the unmodified reference's (oracle/make_golden_base.py vqa)."""
+    g = _load(golden_dir, "vqa_base.pt")
+    cfg = O.Cfg(num_labels=3129, loss_type="bce", qa_answer_size=3129)
+    sd = O.random_state_dict(cfg, g["head"], seed=g["wseed"])
+    assert abs(_sum(sd.values()) - g["wsum"]) < 1e-6 * g["wsum"], "weight generator drifted"
+    B, La, Lt, R = g["dims"]
+    b = O.synthetic_batch(cfg, B, La, Lt, R, seed=g["bseed"], ragged=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        loss, logits = O.vqa_forward(sd, cfg, b["input_ids_a"], b["token_type_ids_a"], b["attention_mask_a"], g["labels"],
+                                     b["input_ids_b"], b["token_type_ids_b"], b["attention_mask_b"], b["img_feats"],
+                                     max_tag_length=Lt)
+    _close(loss, g["loss"]); _close(logits, g["logits"])
