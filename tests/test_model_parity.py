@@ -288,6 +288,6 @@ def test_vqa_base_shape_matches_reference_golden(golden_dir):
     off = []
     for k, n in g["grad_norms"].items():
         got = float(params[k].grad.float().norm())
-        if abs(got - n) > 0.1 * n + 1e-3 * scale:
+        if abs(got - n) > 0.1 * n + 1e-5 * scale:
             off.append((k, got, n))
-    assert not off, f"gradient norms off by more than 10 % (+ floor {1e-3 * scale:.2e}): {off[:6]}"
+    assert not off, f"gradient norms off by more than 10 % (+ floor {1e-5 * scale:.2e}): {off[:6]}"
