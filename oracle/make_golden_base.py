@@ -149,9 +149,72 @@ def vqa_case():
     print("wrote", out, os.path.getsize(out), "bytes")
 
 
+def rep_long_case():
+    """BASELINE.json configs[4] per-sequence shape (70 text+phrase tokens, 20 tags, 100 regions -> 170 joint tokens) at the
+    base model size, batch 4, inference: the unmodified reference BiImageBertRep -> tests/golden/rep_long_base.pt."""
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    mv = ref_shim.load()
+    cfg = O.Cfg()
+    B, La, Lt, R = 4, 70, 20, 100
+    sd = O.random_state_dict(cfg, "rep", seed=9)
+    batch = O.synthetic_batch(cfg, B, La, Lt, R, seed=19, ragged=True)
+    model = mv.BiImageBertRep(ref_shim.make_config(mv, cfg)).eval()
+    model.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        seq, pooled, (txt, vis) = model(max_tag_length=Lt, **batch)
+        o_seq, o_pooled, (o_txt, o_vis) = O.rep_forward(sd, cfg, max_tag_length=Lt, **batch)
+    jm = torch.cat([batch["attention_mask_a"], batch["attention_mask_b"][:, Lt:]], 1)
+    for a, b, m, n in ((o_seq, seq, jm, "seq"), (o_txt, txt, batch["attention_mask_a"], "txt"),
+                       (o_vis, vis, batch["attention_mask_b"], "vis")):
+        print("long", n, close(a[m.bool()], b[m.bool()], what=n))
+    print("long pooled", close(o_pooled, pooled, what="pooled"))
+    rows = {"seq": sample_rows(jm), "txt": sample_rows(batch["attention_mask_a"]), "vis": sample_rows(batch["attention_mask_b"])}
+    take = lambda t, r: torch.gather(t, 1, r[:, :, None].expand(-1, -1, t.shape[2])).clone()
+    out = os.path.join(os.path.dirname(OUT), "rep_long_base.pt")
+    torch.save(dict(head="rep", wseed=9, bseed=19, dims=(B, La, Lt, R), wsum=checksum(sd.values()),
+                    pooled=pooled.clone(), rows=rows, seq_rows=take(seq, rows["seq"]), txt_rows=take(txt, rows["txt"]),
+                    vis_rows=take(vis, rows["vis"])), out)
+    print("wrote", out, os.path.getsize(out), "bytes")
+
+
+def retrieval_case():
+    """BASELINE.json configs[2] per-pair shape (55 caption tokens, 20 tags, 50 regions) at the base model size, 6 pairs:
+    the unmodified reference BiImageBertForRetrieval in its 'coarse' (uni-modal embeddings) and 'fine' (ITM logits)
+    modes (modeling_vlbert.py:1643-1712) -> tests/golden/retrieval_base.pt."""
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    mv = ref_shim.load()
+    cfg = O.Cfg()
+    B, La, Lt, R = 6, 55, 20, 50
+    sd = O.random_state_dict(cfg, "retrieval", seed=10)
+    batch = O.synthetic_batch(cfg, B, La, Lt, R, seed=20, ragged=True)
+    model = mv.BiImageBertForRetrieval(ref_shim.make_config(mv, cfg)).eval()
+    model.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        model.forward_mod = "coarse"
+        gt, gi = model(max_tag_length=Lt, **batch)
+        model.forward_mod = "fine"
+        fine = model(max_tag_length=Lt, **batch)
+        o_gt, o_gi = O.forward_single(sd, cfg, **batch)
+        o_fine = O.retrieval_fine_forward(sd, cfg, batch["input_ids_a"], batch["token_type_ids_a"],
+                                          batch["attention_mask_a"], max_tag_length=Lt,
+                                          input_ids_b=batch["input_ids_b"], token_type_ids_b=batch["token_type_ids_b"],
+                                          attention_mask_b=batch["attention_mask_b"], img_feats=batch["img_feats"])
+    print("retrieval base gt", close(o_gt, gt), "gi", close(o_gi, gi), "fine", close(o_fine, fine))
+    out = os.path.join(os.path.dirname(OUT), "retrieval_base.pt")
+    torch.save(dict(head="retrieval", wseed=10, bseed=20, dims=(B, La, Lt, R), wsum=checksum(sd.values()),
+                    global_txt=gt.clone(), global_img=gi.clone(), fine_logits=fine.clone()), out)
+    print("wrote", out, os.path.getsize(out), "bytes")
+
+
 if __name__ == "__main__":
     if len(sys.argv) < 2 or sys.argv[1] == "rep":
         main()
+    if len(sys.argv) < 2 or sys.argv[1] == "long":
+        rep_long_case()
+    if len(sys.argv) < 2 or sys.argv[1] == "retrieval":
+        retrieval_case()
     if len(sys.argv) < 2 or sys.argv[1] == "vqa":
         vqa_case()
     if len(sys.argv) < 2 or sys.argv[1] == "pretrain":

@@ -291,3 +291,46 @@ def test_vqa_base_shape_matches_reference_golden(golden_dir):
         if abs(got - n) > 0.1 * n + 1e-5 * scale:
             off.append((k, got, n))
     assert not off, f"gradient norms off by more than 10 % (+ floor {1e-5 * scale:.2e}): {off[:6]}"
+
+
+def test_long_sequence_base_shape_matches_reference_golden(golden_dir):
+    """configs[4] per-sequence shape (170 joint tokens: the L > 128 attention kernels) at the base model size against
+    the REAL reference (tests/golden/rep_long_base.pt)."""
+    g = _golden(golden_dir, "rep_long_base.pt")
+    cfg = O.Cfg()
+    sd = O.random_state_dict(cfg, "rep", seed=g["wseed"])
+    B, La, Lt, R = g["dims"]
+    b = O.synthetic_batch(cfg, B, La, Lt, R, seed=g["bseed"], ragged=True)
+    model = P.build("BiImageBertRep", cfg, sd)
+    with torch.no_grad():
+        seq, pooled, (txt, vis) = model(max_tag_length=Lt, **P.to_cuda(b))
+    take = lambda t, r: torch.gather(t.float().cpu(), 1, r[:, :, None].expand(-1, -1, t.shape[2]))
+    P.close(pooled, g["pooled"], 2e-2, 3e-2, "pooled vs reference (long)")
+    for name, t, tol in (("txt", txt, 3e-2), ("vis", vis, 3e-2), ("seq", seq, 4e-2)):
+        got, ref = take(t, g["rows"][name]), g[name + "_rows"]
+        err = (got - ref).abs()
+        frac = (err > tol + 2e-2 * ref.abs()).float().mean().item()
+        assert frac < 2e-3, f"{name}: {frac:.4%} of the sampled elements beyond tolerance, max err {err.max():.4f}"
+
+
+def test_retrieval_base_shape_matches_reference_golden(golden_dir):
+    """configs[2] per-pair shape at the base model size against the REAL reference (tests/golden/retrieval_base.pt):
+    the uni-modal embeddings of the coarse stage and the ITM logits of the fine stage."""
+    g = _golden(golden_dir, "retrieval_base.pt")
+    cfg = O.Cfg()
+    sd = O.random_state_dict(cfg, "retrieval", seed=g["wseed"])
+    B, La, Lt, R = g["dims"]
+    b = P.to_cuda(O.synthetic_batch(cfg, B, La, Lt, R, seed=g["bseed"], ragged=True))
+    model = P.build("BiImageBertForRetrieval", cfg, sd)
+    with torch.no_grad():
+        model.forward_mod = "coarse"
+        gt, gi = model(max_tag_length=Lt, **b)
+        model.forward_mod = "fine"
+        fine = model(max_tag_length=Lt, **b)
+    P.close(gt, g["global_txt"], 2e-2, 1e-2, "global_txt (unit-norm embedding)")
+    P.close(gi, g["global_img"], 2e-2, 1e-2, "global_img (unit-norm embedding)")
+    P.close(fine, g["fine_logits"], 2e-2, 3e-2, "ITM logits")
+    # the ranking the scorer derives from them: same order as the reference's similarities (fp32 given the embeddings)
+    sim_ref = g["global_img"] @ g["global_txt"].t()
+    sim = (gi.float() @ gt.float().t()).cpu()
+    assert (sim - sim_ref).abs().max() < 2e-2

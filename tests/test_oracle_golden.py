@@ -189,3 +189,35 @@ def test_vqa_base_shape_matches_reference(golden_dir):
                                      b["input_ids_b"], b["token_type_ids_b"], b["attention_mask_b"], b["img_feats"],
                                      max_tag_length=Lt)
     _close(loss, g["loss"]); _close(logits, g["logits"])
+
+
+def test_long_sequence_and_retrieval_base_shapes_match_reference(golden_dir):
+    """configs[4] per-sequence shape (70 + 20 + 100 -> 170 joint tokens, batch 4) and configs[2] per-pair shape
+    (55 caption tokens, 6 pairs) at the base model size: oracle against the unmodified reference
+    (oracle/make_golden_base.py long / retrieval)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    take = lambda t, r: torch.gather(t, 1, r[:, :, None].expand(-1, -1, t.shape[2]))
+    g = _load(golden_dir, "rep_long_base.pt")
+    cfg = O.Cfg()
+    sd = O.random_state_dict(cfg, "rep", seed=g["wseed"])
+    assert abs(_sum(sd.values()) - g["wsum"]) < 1e-6 * g["wsum"]
+    B, La, Lt, R = g["dims"]
+    b = O.synthetic_batch(cfg, B, La, Lt, R, seed=g["bseed"], ragged=True)
+    with torch.no_grad():
+        seq, pooled, (txt, vis) = O.rep_forward(sd, cfg, max_tag_length=Lt, **b)
+    _close(pooled, g["pooled"])
+    _close(take(seq, g["rows"]["seq"]), g["seq_rows"])
+    _close(take(txt, g["rows"]["txt"]), g["txt_rows"])
+    _close(take(vis, g["rows"]["vis"]), g["vis_rows"])
+    g = _load(golden_dir, "retrieval_base.pt")
+    sd = O.random_state_dict(cfg, "retrieval", seed=g["wseed"])
+    assert abs(_sum(sd.values()) - g["wsum"]) < 1e-6 * g["wsum"]
+    B, La, Lt, R = g["dims"]
+    b = O.synthetic_batch(cfg, B, La, Lt, R, seed=g["bseed"], ragged=True)
+    with torch.no_grad():
+        gt, gi = O.forward_single(sd, cfg, **b)
+        fine = O.retrieval_fine_forward(sd, cfg, b["input_ids_a"], b["token_type_ids_a"], b["attention_mask_a"],
+                                        max_tag_length=Lt, input_ids_b=b["input_ids_b"],
+                                        token_type_ids_b=b["token_type_ids_b"], attention_mask_b=b["attention_mask_b"],
+                                        img_feats=b["img_feats"])
+    _close(gt, g["global_txt"]); _close(gi, g["global_img"]); _close(fine, g["fine_logits"])
