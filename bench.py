@@ -19,7 +19,6 @@ import json
 import math
 import os
 import statistics
-import subprocess
 import sys
 import tempfile
 import time

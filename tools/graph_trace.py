@@ -1,6 +1,6 @@
 """Per-kernel durations INSIDE CUDA-graph replays of the pre-training step (torch.profiler / CUPTI):
 busy time vs step time (= launch gaps), per-kernel totals, GEMM durations by launch order."""
-import sys, os, collections, json
+import sys, os, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from torch.profiler import profile, ProfilerActivity
