@@ -195,7 +195,10 @@ int mvptr_small_head_fwd(const void* x, int ldx, const void* W, const void* bias
                          void* stream);
 int mvptr_small_head_bwd(const float* dlogits, const void* x, int ldx, const void* W, void* dx, int ld_dx, float* dW,
                          float* db, int n, int H, int C, void* stream);
-int mvptr_small_ce(const float* logits, const int64_t* labels, int n, int C, float* loss, float* dlogits,
+/* acc = float[2] {sum of row losses, valid rows}: accumulated by the forward call (dlogits == NULL, acc pre-zeroed),
+ * read by the backward call (dlogits != NULL).  Labels outside [0, C) (e.g. ignore_index -1 of the QA loss,
+ * modeling_vlbert.py:1262-1264) are ignored: no loss, zero gradient, mean over the valid rows. */
+int mvptr_small_ce(const float* logits, const int64_t* labels, int n, int C, float* acc, float* dlogits,
                    const float* gscale, void* stream);
 
 /* ---- optimizer ------------------------------------------------------------------------

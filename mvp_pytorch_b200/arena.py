@@ -60,6 +60,11 @@ class ParamArena:
             p.data = view
         self.shadow = self.master if dt == torch.bfloat16 else torch.empty(off, device=dev, dtype=torch.bfloat16)
         self.grad = None
+        # names whose gradient some backward has written at least once (sticky, like a torch 1.7 .grad that
+        # stays a tensor after zero_grad()): the fused AdamW skips everything else, as the reference skips
+        # parameters whose grad is None (optimization.py:140-142)
+        self.touched = set()
+        self.dirty = False  # set by PreTrainedModel.mark_weights_changed(): p.data writes do not bump versions
         self.params = dict(named)
         self._sentinels = [(p, p.data_ptr()) for _, p in (order[0], order[-1])]
         self._shadow_version = -1
@@ -74,9 +79,10 @@ class ParamArena:
         if self.shadow is self.master:
             return
         v = self.master._version
-        if force or v != self._shadow_version:
+        if force or self.dirty or v != self._shadow_version:
             _lib.call("mvptr_cast_f32_bf16", self.master, self.shadow, self.numel)
             self._shadow_version = v
+            self.dirty = False
 
     def mark_shadow_fresh(self):
         self._shadow_version = self.master._version
@@ -114,10 +120,12 @@ class ParamArena:
 
     def g(self, name):
         o, k, shp = self.offsets[name]
+        self.touched.add(name)
         return self.ensure_grad()[o:o + k].view(shp)
 
     def g_span(self, first, rows, cols=None):
         o, k, shp = self.offsets[first]
+        self.touched.add(first)
         if cols is None:
             return self.ensure_grad()[o:o + rows]
         return self.ensure_grad()[o:o + rows * cols].view(rows, cols)

@@ -276,23 +276,33 @@ small_head_bwd_dw_kernel(const float* __restrict__ dlogits, const bf16* __restri
     if (threadIdx.x == 0) atomicAdd(db + c, s);
   }
 }
-// CE over tiny logits [n, C] fp32 with int64 labels -> loss (mean) and dlogits (already /n)
+// CE over tiny logits [n, C] fp32 with int64 labels (CrossEntropyLoss(ignore_index), modeling_vlbert.py:1251,
+// :1262-1264, :1682).  Rows whose label is ignore_index -- or outside [0, C) -- contribute neither loss nor
+// gradient and the mean runs over the valid rows only, as torch does.
+// Forward (dlogits == null): acc[0] += sum of row losses, acc[1] += valid rows.  Backward (dlogits != null):
+// dlogits = (softmax - onehot) * gscale / acc[1] with acc[1] left by the forward; acc is not touched.
 __global__ void small_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int n, int C,
-                                float* __restrict__ loss, float* __restrict__ dlogits, const float* __restrict__ gscale) {
+                                float* __restrict__ acc, float* __restrict__ dlogits, const float* __restrict__ gscale) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
+  const int64_t lab64 = labels[r];
+  const bool valid = lab64 >= 0 && lab64 < C;
+  const int lab = valid ? (int)lab64 : 0;
   float mx = -INFINITY;
   for (int c = 0; c < C; ++c) mx = fmaxf(mx, logits[(size_t)r * C + c]);
   float s = 0.f;
   for (int c = 0; c < C; ++c) s += __expf(logits[(size_t)r * C + c] - mx);
   const float lse = mx + logf(s);
-  const int lab = (int)labels[r];
-  atomicAdd(loss, (lse - logits[(size_t)r * C + lab]) / n);
-  if (dlogits) {
-    const float g = (gscale ? *gscale : 1.f) / n;
-    for (int c = 0; c < C; ++c)
-      dlogits[(size_t)r * C + c] = (__expf(logits[(size_t)r * C + c] - lse) - (c == lab ? 1.f : 0.f)) * g;
+  if (!dlogits) {
+    if (valid) {
+      atomicAdd(acc, lse - logits[(size_t)r * C + lab]);
+      atomicAdd(acc + 1, 1.f);
+    }
+    return;
   }
+  const float g = valid ? (gscale ? *gscale : 1.f) / fmaxf(acc[1], 1.f) : 0.f;
+  for (int c = 0; c < C; ++c)
+    dlogits[(size_t)r * C + c] = (__expf(logits[(size_t)r * C + c] - lse) - (c == lab ? 1.f : 0.f)) * g;
 }
 
 // ---------------------------------------------------------------------------------
@@ -439,10 +449,11 @@ extern "C" int mvptr_small_head_bwd(const float* dlogits, const void* x, int ldx
   }
   return 0;
 }
-extern "C" int mvptr_small_ce(const float* logits, const int64_t* labels, int n, int C, float* loss, float* dlogits,
+extern "C" int mvptr_small_ce(const float* logits, const int64_t* labels, int n, int C, float* acc, float* dlogits,
                               const float* gscale, void* stream) {
   if (n <= 0) return 0;
-  small_ce_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(logits, labels, n, C, loss, dlogits, gscale);
+  if (!acc) MVPTR_FAIL(MVPTR_ERR_ARG, "small_ce: acc (float[2]: loss sum, valid rows) is required");
+  small_ce_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(logits, labels, n, C, acc, dlogits, gscale);
   MVPTR_CHECK_LAUNCH("small_ce");
   return 0;
 }

@@ -140,6 +140,7 @@ def _layer_proto(rt, pf, with_grads):
             g = a.ensure_grad().data_ptr()
             for f, n in _W_FIELDS:
                 setattr(proto, "g_" + f, g + 4 * offs[pf + n][0])
+            a.touched.update(k for k in offs if k.startswith(pf))
         rt.layer_protos[key] = proto
     return _lib.LayerArgs.from_buffer_copy(proto)
 
@@ -222,15 +223,18 @@ class EncoderFn(Function):
             la.datt = s0 + 2 * M * 5 * H
             la.dqkv = s0 + 2 * M * 6 * H
             la.dpre_g = s0 + 2 * M * 9 * H
-            _lib.layer_call("mvptr_layer_bwd", la, 12)
             sync = getattr(rt, "grad_sync", None)
-            if sync is not None and sync.enabled:  # this layer's gradients are final: reduce them now
+            if sync is not None and sync.enabled:
                 offs = rt.arena.offsets
                 w0 = offs[pf + "attention.self.query.weight"][0]
                 w1 = offs[pf + "output.dense.weight"]
-                sync.layer_done(w0, w1[0] + w1[1])
                 b0 = offs[pf + "attention.self.query.bias"][0]
                 b1 = offs[pf + "output.LayerNorm.bias"]
+                sync.will_write(w0, w1[0] + w1[1])
+                sync.will_write(b0, b1[0] + b1[1])
+            _lib.layer_call("mvptr_layer_bwd", la, 12)
+            if sync is not None and sync.enabled:  # this layer's gradients are final: reduce them now
+                sync.layer_done(w0, w1[0] + w1[1])
                 sync.layer_done(b0, b1[0] + b1[1])
             dy = dx
         ctx.saved = None
@@ -680,25 +684,25 @@ class SmallHeadFn(Function):
 
 
 class SmallCEFn(Function):
-    """CrossEntropyLoss over [n, C] fp32 logits, C small (modeling_vlbert.py:1251, :1682)."""
+    """CrossEntropyLoss(ignore_index=-1) over [n, C] fp32 logits, C small (modeling_vlbert.py:1251, :1262-1264,
+    :1682): labels outside [0, C) are ignored, the mean runs over the valid rows."""
 
     @staticmethod
     def forward(ctx, logits, labels, rt):
         n, C = logits.shape
         logits = logits.contiguous()
-        loss = torch.zeros(1, device=logits.device, dtype=F32)
-        rt.call("mvptr_small_ce", logits, labels, n, C, loss, None, None)
-        ctx.rt, ctx.s = rt, (logits, labels)
-        return loss[0]
+        acc = torch.zeros(2, device=logits.device, dtype=F32)  # {sum of row losses, valid rows}
+        rt.call("mvptr_small_ce", logits, labels, n, C, acc, None, None)
+        ctx.rt, ctx.s = rt, (logits, labels, acc)
+        return acc[0] / acc[1]
 
     @staticmethod
     def backward(ctx, g):
         rt = ctx.rt
-        logits, labels = ctx.s
+        logits, labels, acc = ctx.s
         n, C = logits.shape
         dl = torch.empty_like(logits)
-        scratch = torch.zeros(1, device=logits.device, dtype=F32)
-        rt.call("mvptr_small_ce", logits, labels, n, C, scratch, dl, g.reshape(1).to(F32).contiguous())
+        rt.call("mvptr_small_ce", logits, labels, n, C, acc, dl, g.reshape(1).to(F32).contiguous())
         return dl, None, None
 
 

@@ -16,6 +16,15 @@ from torch import nn
 
 logger = logging.getLogger(__name__)
 
+import weakref
+
+_LIVE_MODELS = weakref.WeakSet()  # every PreTrainedModel alive: lets AdamW(params) find the model that owns them
+
+
+def live_models():
+    return list(_LIVE_MODELS)
+
+
 CONFIG_NAME = "config.json"
 WEIGHTS_NAME = "pytorch_model.bin"
 
@@ -122,6 +131,7 @@ class PreTrainedModel(nn.Module):
         self.config = config
         self._rt = None          # engine.Runtime, built lazily on the first forward
         self._rt_prefix = ""     # name prefix of this module inside the runtime's root model
+        _LIVE_MODELS.add(self)
 
     # ---- B200 runtime ----------------------------------------------------------------
     def runtime(self):
@@ -141,6 +151,16 @@ class PreTrainedModel(nn.Module):
     def _adopt(self, child, prefix):
         child._rt = self._rt
         child._rt_prefix = self._rt_prefix + prefix
+
+    def mark_weights_changed(self):
+        """Call after writing parameters through ``p.data`` / ``copy_`` outside an optimizer step (re-initialised
+        heads, EMA, manual surgery): such writes do not bump version counters, and once the fused AdamW manages
+        the bf16 compute copy nothing else would notice them.  The next forward re-derives the copy."""
+        for m in self.modules():
+            rt = getattr(m, "_rt", None)
+            if rt is not None:
+                rt.arena.dirty = True
+                rt._img_w_version = -1
 
     def zero_grad(self, set_to_none=False):
         """Gradients live in the flat arena: zero it in place and keep the views bound."""

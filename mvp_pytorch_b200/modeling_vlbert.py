@@ -438,10 +438,10 @@ class BiBertImgForPreTraining(BertPreTrainedModel):
         total_loss = vis_mlm_loss + retrieval_loss + masked_lm_loss + next_sentence_loss
         outputs = (vis_mlm_loss, retrieval_loss, masked_lm_loss, next_sentence_loss)
         if qa_ans is not None:
-            qa_logits = E.DecoderFn.apply(pooled_output, rt, "qa_head.weight", self.config.qa_answer_size,
-                                          "qa_head.bias", anchor)
-            qa_loss = E.SmallCEFn.apply(qa_logits.contiguous(), qa_ans.to(torch.int64), rt) \
-                if self.config.qa_answer_size <= 64 else nn.functional.cross_entropy(qa_logits, qa_ans, ignore_index=-1)
+            # qa_head + CrossEntropyLoss(ignore_index=-1) (:1224, :1262-1264): the same fused decoder + CE kernels
+            # as the MLM heads, for any answer count
+            qa_loss = E.VocabCEFn.apply(pooled_output, qa_ans.to(torch.int64).contiguous(), rt, "qa_head.weight",
+                                        self.config.qa_answer_size, "qa_head.bias", anchor)
             total_loss = total_loss + qa_loss
             outputs = outputs + (qa_loss,)
 
@@ -597,6 +597,7 @@ class BiImageBertForSequenceClassificationPlus(BertPreTrainedModel):
 
     def reinit_cls_head(self):
         self.classifier.apply(self.init_weights)
+        self.mark_weights_changed()
 
     def freeze_backbone(self):
         for param in self.bert.parameters():
@@ -700,6 +701,7 @@ class BiImageBertForRE(BertPreTrainedModel):
 
     def reinit_cls_head(self):
         self.classifier.apply(self.init_weights)
+        self.mark_weights_changed()
 
     def forward(self, input_ids_a, token_type_ids_a=None, attention_mask_a=None, labels=None, phrase_layer=None,
                 input_ids_b=None, token_type_ids_b=None, attention_mask_b=None, max_tag_length=20, mod=1,

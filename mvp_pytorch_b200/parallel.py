@@ -82,6 +82,15 @@ class GradientSync:
             self.stream.wait_event(ev)
             dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
 
+    def will_write(self, lo, hi):
+        """Called before backward kernels accumulate into arena range [lo, hi).  If that range was already
+        handed to the communication stream since the last finish() (a second backward before the optimizer
+        step: gradient accumulation, or the same layers run twice in one forward), the compute stream first
+        waits for that collective -- writing under an in-flight all-reduce would race.  The result stays
+        right by linearity: avg(avg(g1) + g2) = avg(g1) + avg(g2)."""
+        if self.enabled and self.stream is not None and any(l < hi and lo < h for l, h in self.done):
+            torch.cuda.current_stream().wait_stream(self.stream)
+
     def layer_done(self, lo, hi):
         if not self.enabled or hi <= lo:
             return

@@ -307,11 +307,15 @@ def test_small_head_l2norm_colsum(lib):
     lib.call("mvptr_small_head_fwd", x, H, W, b, logits, n, H, C)
     assert_close(logits, x.float() @ W.float().t() + b.float(), 1e-4, 1e-3, "small head")
     labels = torch.randint(0, C, (n,)).cuda()
-    loss = torch.zeros(1, device="cuda"); dl = torch.empty_like(logits)
-    lib.call("mvptr_small_ce", logits, labels, n, C, loss, dl, None)
+    labels[::5] = -1  # ignore_index rows (QA loss, modeling_vlbert.py:1262-1264): no loss, no gradient
+    acc = torch.zeros(2, device="cuda"); dl = torch.empty_like(logits)
+    lib.call("mvptr_small_ce", logits, labels, n, C, acc, None, None)
+    lib.call("mvptr_small_ce", logits, labels, n, C, acc, dl, None)
     lg = logits.clone().requires_grad_(True)
-    ref = F.cross_entropy(lg, labels); ref.backward()
-    assert_close(loss[0], ref, 1e-5, 1e-5, "small ce"); assert_close(dl, lg.grad, 1e-4, 1e-6, "small ce grad")
+    ref = F.cross_entropy(lg, labels, ignore_index=-1); ref.backward()
+    assert float(acc[1]) == float((labels >= 0).sum())
+    assert_close(acc[0] / acc[1], ref, 1e-5, 1e-5, "small ce"); assert_close(dl, lg.grad, 1e-4, 1e-6, "small ce grad")
+    assert float(dl[::5].abs().max()) == 0.0
     dx = torch.empty(n, H, device="cuda", dtype=BF16); dW = torch.zeros(C, H, device="cuda"); db = torch.zeros(C, device="cuda")
     lib.call("mvptr_small_head_bwd", dl, x, H, W, dx, H, dW, db, n, H, C)
     assert_close(dx, dl @ W.float(), 1e-2, 1e-4, "small dx"); assert_close(dW, dl.t() @ x.float(), 1e-4, 1e-4, "small dW")
