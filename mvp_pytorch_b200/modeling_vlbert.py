@@ -460,7 +460,29 @@ class BiBertImgForPreTraining(BertPreTrainedModel):
                 total_loss = total_loss + wra_loss
                 outputs = (total_loss,) + outputs + (wra_loss,)
             elif phrase_mod == 'hard':
-                raise NotImplementedError("phrase_mod='hard' (:1271-1283) is not used by run_pretrain_ml.py")
+                # :1270-1283 -- positives from the matched sequences, negatives from the hard-negative sequences
+                # (phrases of text hard_txt_index[i] against the regions of image hard_img_index[i]); both are the
+                # "own image" half of the batched WRA kernel (negative image = the row itself, its output unused)
+                maxp = E._lib.lib().mvptr_wra_max_phrases()
+                if wra_choices is None:
+                    wra_choices = _draw_wra_choices(B, maxp, sequence_output.device)
+                _, rand_pos, rand_neg = wra_choices
+                hard_txt_index, hard_img_index = hard_indexes
+                pidx = phrase_index.to(torch.int64).contiguous()
+                iidx = img_index.to(torch.int64).contiguous()
+                hard_phrase_index = torch.index_select(pidx, 0, hard_txt_index).contiguous()
+                hard_object_index = torch.index_select(iidx, 0, hard_img_index).contiguous()
+                own = torch.arange(B, device=sequence_output.device)
+                pos_sims, _ = E.WRAFn.apply(sequence_output, pidx, iidx, own, rand_pos.contiguous(),
+                                            rand_pos.contiguous(), rt)
+                neg_sims, _ = E.WRAFn.apply(hard_sequence_output, hard_phrase_index, hard_object_index, own,
+                                            rand_neg.contiguous(), rand_neg.contiguous(), rt)
+                hinge = torch.clamp(neg_sims + 0.2 - pos_sims, min=0)
+                valid = (((pidx[:, 1] - pidx[:, 0]) > 0)
+                         & ((hard_phrase_index[:, 1] - hard_phrase_index[:, 0]) > 0)).to(hinge.dtype)
+                wra_loss = (hinge * valid).sum() / valid.sum()
+                total_loss = total_loss + wra_loss
+                outputs = (total_loss,) + outputs + (wra_loss,)
             else:
                 raise NotImplementedError
         else:
@@ -479,11 +501,12 @@ class BiImageBertForRetrieval(BertPreTrainedModel):
         self.dropout = nn.Dropout(config.hidden_dropout_prob)
         self.logit_scale = nn.Parameter(torch.ones([]) * np.log(1 / 0.07))
         self.forward_mod = 'train'
-        if hasattr(config, 'classifier') and config.classifier == 'mlp':
-            raise NotImplementedError("classifier='mlp' (:1616-1621) is not on the CUDA path; use the reference "
-                                      "default linear classifier")
-        self.classifier = _Linear(config.hidden_size, self.num_labels)
+        self.classifier = _make_classifier(config, config.hidden_size, config.num_labels)  # linear | mlp (:1615-1629)
         self.apply(self.init_weights)
+
+    def reinit_cls_head(self):
+        self.classifier.apply(self.init_weights)
+        self.mark_weights_changed()
 
     def forward(self, input_ids_a, token_type_ids_a=None, attention_mask_a=None, input_ids_b=None,
                 token_type_ids_b=None, attention_mask_b=None, max_tag_length=20, position_ids_a=None,
@@ -516,7 +539,7 @@ class BiImageBertForRetrieval(BertPreTrainedModel):
         pooled_all = torch.cat([pooled_output, hard_pooled_output], dim=0)
         if self.training and self.config.hidden_dropout_prob > 0:
             pooled_all = nn.functional.dropout(pooled_all, self.config.hidden_dropout_prob, True)  # :1680
-        logits = E.SmallHeadFn.apply(pooled_all, rt, "classifier.weight", "classifier.bias", anchor)
+        logits = _apply_classifier(self, rt, pooled_all, anchor)
         B = pooled_output.shape[0]
         labels = torch.cat([torch.ones(B, dtype=torch.int64, device=logits.device),
                             torch.zeros(hard_pooled_output.shape[0], dtype=torch.int64, device=logits.device)])
@@ -532,7 +555,7 @@ class BiImageBertForRetrieval(BertPreTrainedModel):
     def forward_fine(self, **kw):
         rt = self._prep()
         outputs, _, _ = self.bert(encode_hn=False, **kw)
-        return E.SmallHeadFn.apply(outputs[1], rt, "classifier.weight", "classifier.bias", rt.anchor(self.logit_scale))
+        return _apply_classifier(self, rt, outputs[1], rt.anchor(self.logit_scale))
 
 
 def _cls_loss(self, logits, labels, soft_label, num_labels):
@@ -852,9 +875,12 @@ class BiBertImgForMLM(BertPreTrainedModel):
         pick = torch.zeros(B, Ltot, dtype=torch.bool, device=input_ids_a.device)
         pick[:, :La] = input_ids_a == 103
         idx = torch.nonzero(pick.reshape(-1)).reshape(-1)
-        rows = E.GatherRowsFn.apply(sequence_output.reshape(-1, H), idx, rt)
-        t = E.HeadTransformFn.apply(rows, rt, "cls.predictions.transform", anchor)
-        scores = E.DecoderFn.apply(t, rt, "cls.predictions.decoder.weight", self.only_vocab_size,
-                                   "cls.predictions.bias", anchor)
+        if idx.numel() == 0:  # no [MASK] in the batch: the reference's masked_select gives [0, V] scores
+            scores = torch.empty(0, self.only_vocab_size, device=input_ids_a.device, dtype=torch.float32)
+        else:
+            rows = E.GatherRowsFn.apply(sequence_output.reshape(-1, H), idx, rt)
+            t = E.HeadTransformFn.apply(rows, rt, "cls.predictions.transform", anchor)
+            scores = E.DecoderFn.apply(t, rt, "cls.predictions.decoder.weight", self.only_vocab_size,
+                                       "cls.predictions.bias", anchor)
         rel = E.SmallHeadFn.apply(pooled_output, rt, "cls.seq_relationship.weight", "cls.seq_relationship.bias", anchor)
         return scores, rel

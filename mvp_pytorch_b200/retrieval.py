@@ -18,6 +18,7 @@ import torch
 
 from . import _lib
 from . import engine as E
+from .modeling_vlbert import _apply_classifier
 from .parallel import all_gather_rows, shard_range, world
 
 
@@ -121,7 +122,7 @@ class RetrievalScorer:
             e = min(hi, s + self.pair_batch)
             ra, rb = cap_index[s:e].contiguous(), img_index[s:e].contiguous()
             _, pooled = m.bert.forward_stage2(self.txt, self.vis, self.txt_mask, self.vis_mask, self.max_tag_length, ra, rb)
-            logits = E.SmallHeadFn.apply(pooled, rt, "classifier.weight", "classifier.bias", m.logit_scale)
+            logits = _apply_classifier(m, rt, pooled, m.logit_scale)  # linear or mlp head (:1615-1629)
             _lib.call("mvptr_match_prob", logits.contiguous(), out[s - lo:e - lo], e - s)
         return all_gather_rows(out)
 

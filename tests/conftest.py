@@ -16,3 +16,24 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+# Observed parity errors: every GPU parity test reports its measured distances through
+# mvptr_parity_utils.report(); they are printed at the end of the session (also under -q) and written to
+# gpurun_out/parity_report.txt so the numbers behind each assert can be read, not just "passed".
+PARITY_LINES = []
+
+
+def pytest_terminal_summary(terminalreporter):
+    if not PARITY_LINES:
+        return
+    terminalreporter.write_sep("-", "observed parity errors (CUDA path vs oracle)")
+    for line in PARITY_LINES:
+        terminalreporter.write_line(line)
+    try:
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_report.txt"), "w") as f:
+            f.write("\n".join(PARITY_LINES) + "\n")
+    except OSError:
+        pass

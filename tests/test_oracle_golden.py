@@ -221,3 +221,91 @@ def test_long_sequence_and_retrieval_base_shapes_match_reference(golden_dir):
                                         token_type_ids_b=b["token_type_ids_b"], attention_mask_b=b["attention_mask_b"],
                                         img_feats=b["img_feats"])
     _close(gt, g["global_txt"]); _close(gi, g["global_img"]); _close(fine, g["fine_logits"])
+
+
+ENC = ("input_ids_a", "token_type_ids_a", "attention_mask_a", "input_ids_b", "token_type_ids_b", "attention_mask_b",
+       "img_feats")
+
+
+def test_round2_cases_match_reference(golden_dir):
+    """tests/golden/r2_tiny.pt (oracle/make_golden_r2.py): BiBertImgForMLM, the 'mlp' retrieval classifier, use_b=True
+    and phrase_mod='hard' + qa_ans with ignored labels -- the oracle reproduces the REAL reference's outputs."""
+    g = _load(golden_dir, "r2_tiny.pt")
+    B, La, Lt, R = g["dims"]
+    cfg = O.Cfg(**g["cfg"])
+    c = g["mlm"]
+    sd = O.random_state_dict(cfg, "mlm", seed=c["wseed"])
+    assert abs(_sum(sd.values()) - c["wsum"]) < 1e-6 * c["wsum"]
+    b = O.synthetic_batch(cfg, B, La, Lt, R, seed=c["bseed"], ragged=True)
+    b["input_ids_a"][c["mask_positions"]] = 103
+    with torch.no_grad():
+        scores, rel = O.mlm_forward(sd, cfg, *[b[k] for k in ENC], max_tag_length=Lt)
+    _close(scores, c["scores"]); _close(rel, c["rel"])
+
+    c = g["retrieval_mlp"]
+    sd = O.random_state_dict(cfg, "retrieval_mlp", seed=c["wseed"])
+    b = O.synthetic_batch(cfg, B, La, Lt, R, seed=c["bseed"], ragged=True)
+    with torch.no_grad():
+        fine = O.retrieval_fine_forward(sd, cfg, b["input_ids_a"], b["token_type_ids_a"], b["attention_mask_a"],
+                                        max_tag_length=Lt, **{k: b[k] for k in ENC[3:]})
+        total, logits, _, _, labels = O.retrieval_train_forward(sd, cfg, *[b[k] for k in ENC], max_tag_length=Lt,
+                                                                dice_index=c["dice"])
+    _close(fine, c["fine_logits"]); _close(total, c["train_total"]); _close(logits, c["train_logits"])
+    assert torch.equal(labels, c["train_labels"])
+
+    c = g["use_b"]
+    cfg3 = O.Cfg(**dict(g["cfg"], num_labels=3, loss_type="xe"))
+    sd = {k: v.requires_grad_(True) for k, v in O.random_state_dict(cfg3, "cls_linear", seed=c["wseed"]).items()}
+    b = O.synthetic_batch(cfg3, B, La, Lt, R, seed=c["bseed"], ragged=True)
+    loss, logits = O.seqcls_forward(sd, cfg3, b["input_ids_a"], b["token_type_ids_a"], b["attention_mask_a"], c["labels"],
+                                    b["input_ids_b"], b["token_type_ids_b"], b["attention_mask_b"], b["img_feats"],
+                                    max_tag_length=Lt, use_b=True)
+    loss.backward()
+    _close(loss.detach(), c["loss"]); _close(logits.detach(), c["logits"])
+    for k, gr in c["grads"].items():
+        _close(sd[k].grad, gr, 5e-5)
+
+    c = g["pretrain_hard"]
+    sd = {k: v.requires_grad_(True) for k, v in O.random_state_dict(cfg, "pretrain", seed=c["wseed"]).items()}
+    b = O.synthetic_batch(cfg, B, La, Lt, R, seed=c["bseed"], ragged=True, with_labels=True)
+    losses = O.pretrain_forward(sd, cfg, b["input_ids_a"], b["token_type_ids_a"], b["attention_mask_a"],
+                                b["masked_lm_labels_a"], b["input_ids_b"], b["token_type_ids_b"], b["attention_mask_b"],
+                                b["masked_lm_labels_b"], b["img_feats"], max_tag_length=Lt, img_index=b["img_index"],
+                                phrase_index=b["phrase_index"], dice_index=b["dice_index"], rand_pos=b["rand_pos"],
+                                rand_neg=b["rand_neg"], phrase_mod="hard", qa_ans=c["qa_ans"])
+    assert len(losses) == 7
+    losses[0].backward()
+    for a, r in zip(losses, c["losses"]):
+        _close(a.detach(), r)
+    for k, gr in c["grads"].items():
+        _close(sd[k].grad, gr, 5e-5)
+    for k, n in c["grad_norms"].items():
+        assert abs(float(sd[k].grad.norm()) - n) <= 1e-4 * n + 1e-7, k
+
+
+def test_bf16_storage_distance_to_fp32_reference(golden_dir, capsys):
+    """What bf16 STORAGE alone costs against the fp32 reference -- no kernel involved: the oracle with its
+    activations rounded to bf16 at the CUDA path's store points (O.bf16_stores()) against the reference goldens of
+    the pre-training step.  This is the part of the CUDA-vs-fp32 distance that no kernel can remove (the fp32
+    verification tier does); the GPU suite asserts the kernels against the bf16-store oracle at rtol 1e-2 and only
+    bounds this distance."""
+    g = _load(golden_dir, "pretrain_tiny.pt")
+    cfg = O.Cfg(**g["cfg"])
+    B, La, Lt, R = g["dims"]
+    b = O.synthetic_batch(cfg, B, La, Lt, R, seed=g["bseed"], ragged=True, with_labels=True)
+    sd = {k: v.requires_grad_(True) for k, v in O.random_state_dict(cfg, "pretrain", seed=g["wseed"]).items()}
+    with O.bf16_stores():
+        losses = O.pretrain_forward(sd, cfg, b["input_ids_a"], b["token_type_ids_a"], b["attention_mask_a"],
+                                    b["masked_lm_labels_a"], b["input_ids_b"], b["token_type_ids_b"],
+                                    b["attention_mask_b"], b["masked_lm_labels_b"], b["img_feats"], max_tag_length=Lt,
+                                    img_index=b["img_index"], phrase_index=b["phrase_index"], dice_index=b["dice_index"],
+                                    neg_img=b["neg_img"], rand_pos=b["rand_pos"], rand_neg=b["rand_neg"])
+        losses[0].backward()
+    loss_rel = max(abs(float(a.detach()) - float(r)) / abs(float(r)) for a, r in zip(losses, g["losses"]))
+    rels = {k: float((sd[k].grad - gr).norm() / gr.norm()) for k, gr in g["grads"].items() if float(gr.norm()) > 1e-6}
+    norm_rel = {k: abs(float(sd[k].grad.norm()) - n) / n for k, n in g["grad_norms"].items() if n > 1e-6}
+    with capsys.disabled():
+        print(f"\n[bf16 storage vs fp32 reference, tiny pre-training step] losses: max rel {loss_rel:.2e}; gradient "
+              f"tensors: max relative L2 {max(rels.values()):.2e}; gradient norms: max rel {max(norm_rel.values()):.2e}")
+    assert loss_rel < 1e-2                    # losses survive bf16 storage at rtol 1e-2 ...
+    assert 3e-3 < max(rels.values()) < 6e-2   # ... individual gradient tensors do not (1e-2 is NOT reachable in bf16)
