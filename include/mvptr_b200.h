@@ -141,9 +141,11 @@ int mvptr_ln_bwd(const void* dy, int dy_rows_per_batch, long long dy_batch_strid
 /* out[n] += sum_m x[m,n]  (bias gradient of a dense layer) */
 int mvptr_colsum(const void* x, int ldx, float* out, int M, int N, void* stream);
 
-/* region features [rows,K] fp32|bf16 (any pitch) -> bf16 [rows, ld_dst] zero padded so that the
- * K=2054 projection (modeling_vlbert.py:498) has a 16-byte aligned pitch for TMA. */
-int mvptr_pad_cast(const void* src, int src_is_f32, long long ld_src, void* dst, int ld_dst, int rows, int K,
+/* region features [rows,K] bf16|fp32|fp16 (src_kind 0|1|2; any pitch) -> bf16 [rows, ld_dst] zero padded so that the
+ * K=2054 projection (modeling_vlbert.py:498) has a 16-byte aligned pitch for TMA.  fp16 is what the reference's
+ * --half_evaluation (run_retrieval.py:1047-1048 + prepare_inputs) and DeepSpeed fp16 loaders (run_pretrain_ml.py:504)
+ * deliver. */
+int mvptr_pad_cast(const void* src, int src_kind, long long ld_src, void* dst, int ld_dst, int rows, int K,
                    void* stream);
 /* additive mask (1-mask)*-10000 of modeling_vlbert.py:430-460 for the sequence
  * [a(row_a[r], 0..La) | b(row_b[r], b_col0..Lb)] -- also assembles the joint and

@@ -1,6 +1,8 @@
 // HBM-bound row kernels: embedding gather + LayerNorm, LayerNorm fwd/bwd, column sums,
 // embedding scatter-add, region-feature pad/cast, mask preparation, row gathers.
 // One warp per row, 16-byte vector accesses, warp-shuffle reductions.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace mvptr {
@@ -451,7 +453,12 @@ embed_pos_type_bwd_kernel(const bf16* __restrict__ dpre, const int64_t* __restri
   }
 }
 
-// fp32/bf16 [rows, K] (any pitch) -> bf16 [rows, Kp] zero padded  (region features, K=2054)
+template <typename T>
+constexpr bool kIsHalf = false;
+template <>
+constexpr bool kIsHalf<__half> = true;
+
+// fp32/bf16/fp16 [rows, K] (any pitch) -> bf16 [rows, Kp] zero padded  (region features, K=2054)
 template <typename T>
 __global__ void pad_cast_kernel(const T* __restrict__ src, long long ld_src, bf16* __restrict__ dst, int ld_dst,
                                 int rows, int K) {
@@ -481,10 +488,15 @@ pad_cast8_kernel(const T* __restrict__ src, long long ld_src, bf16* __restrict__
         const float2 t = __ldg(reinterpret_cast<const float2*>(s + j));
         v[j] = t.x;
         v[j + 1] = t.y;
-      } else {
+      } else if constexpr (sizeof(T) == 2 && !kIsHalf<T>) {
         const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(s + j));
         v[j] = __uint_as_float(w << 16);
         v[j + 1] = __uint_as_float(w & 0xffff0000u);
+      } else {  // fp16 features (the reference's --half_evaluation / DeepSpeed fp16 loaders)
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(s + j));
+        const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w));
+        v[j] = t.x;
+        v[j + 1] = t.y;
       }
     }
   }
@@ -744,10 +756,13 @@ extern "C" int mvptr_embed_bwd(const void* dpre, const int64_t* ids, const int64
   return 0;
 }
 
-extern "C" int mvptr_pad_cast(const void* src, int src_is_f32, long long ld_src, void* dst, int ld_dst, int rows, int K,
+// src_kind: 0 = bf16, 1 = fp32, 2 = fp16
+extern "C" int mvptr_pad_cast(const void* src, int src_kind, long long ld_src, void* dst, int ld_dst, int rows, int K,
                               void* stream) {
   MVPTR_PROF("pad_cast", 0, stream);
   if (rows <= 0) return 0;
+  if (src_kind < 0 || src_kind > 2) MVPTR_FAIL(MVPTR_ERR_ARG, "pad_cast: src_kind %d (0 bf16, 1 fp32, 2 fp16)", src_kind);
+  const bool src_is_f32 = src_kind == 1;
   const size_t pair_bytes = src_is_f32 ? 8 : 4;
   const bool wide = (K % 2 == 0) && (ld_src % 2 == 0) && (ld_dst % 8 == 0) &&
                     (reinterpret_cast<uintptr_t>(src) % pair_bytes == 0) && (reinterpret_cast<uintptr_t>(dst) % 16 == 0);
@@ -755,6 +770,8 @@ extern "C" int mvptr_pad_cast(const void* src, int src_is_f32, long long ld_src,
     dim3 grid(rows, (ld_dst / 8 + 255) / 256);
     if (src_is_f32)
       pad_cast8_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src, ld_src, (bf16*)dst, ld_dst, rows, K);
+    else if (src_kind == 2)
+      pad_cast8_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)src, ld_src, (bf16*)dst, ld_dst, rows, K);
     else
       pad_cast8_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, ld_src, (bf16*)dst, ld_dst, rows, K);
     MVPTR_CHECK_LAUNCH("pad_cast");
@@ -763,6 +780,8 @@ extern "C" int mvptr_pad_cast(const void* src, int src_is_f32, long long ld_src,
   dim3 grid(rows, (ld_dst + 255) / 256);
   if (src_is_f32)
     pad_cast_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src, ld_src, (bf16*)dst, ld_dst, rows, K);
+  else if (src_kind == 2)
+    pad_cast_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)src, ld_src, (bf16*)dst, ld_dst, rows, K);
   else
     pad_cast_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, ld_src, (bf16*)dst, ld_dst, rows, K);
   MVPTR_CHECK_LAUNCH("pad_cast");

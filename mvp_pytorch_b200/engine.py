@@ -318,11 +318,12 @@ class VisInputFn(Function):
                 cfg.max_position_embeddings, cfg.type_vocab_size, p, s_tag)
         # region features -> bf16 with a 16-byte aligned pitch, then the K=2054 projection
         Kp = _pad8(Kimg)
-        if img_feats.dtype not in (F32, BF16):
-            raise _lib.MvptrError(f"img_feats dtype {img_feats.dtype} unsupported (float32 or bfloat16)")
+        kind = {BF16: 0, F32: 1, torch.float16: 2}.get(img_feats.dtype)
+        if kind is None:
+            raise _lib.MvptrError(f"img_feats dtype {img_feats.dtype} unsupported (float32, bfloat16 or float16)")
         feats = img_feats if img_feats.is_contiguous() else img_feats.contiguous()
         x16 = torch.empty(B * R, Kp, device=dev, dtype=BF16)
-        rt.call("mvptr_pad_cast", feats, int(feats.dtype == F32), Kimg, x16, Kp, B * R, Kimg)
+        rt.call("mvptr_pad_cast", feats, kind, Kimg, x16, Kp, B * R, Kimg)
         w16 = rt.img_weight(bert + "img_embedding.weight")
         pre_i = torch.empty(B * R, H, device=dev, dtype=BF16)
         rt.gemm(x16, w16, pre_i, B * R, H, Kimg, lda=Kp, ldb=Kp, ldd=H, bias=a.w(bert + "img_embedding.bias"))
