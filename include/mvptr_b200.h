@@ -162,6 +162,9 @@ int mvptr_concat_rows_bwd(const void* dout, int La, int Lb, int b_col0, const in
 int mvptr_gather_rows(const void* src, const int64_t* idx, void* out, int n, int H, void* stream);
 int mvptr_scatter_rows_add(const void* src, const int64_t* idx, float* dst, int n, int H, void* stream);
 int mvptr_cast_f32_bf16(const float* src, void* dst, size_t n, void* stream);
+/* widen a bf16 buffer into fp32 (data-parallel gradient path: bf16 all-reduce over NVLink, fp32 arena);
+ * max_ctas > 0 caps the grid so the cast shares the SMs politely with the backward GEMMs it overlaps */
+int mvptr_cast_bf16_f32(const void* src, float* dst, size_t n, int max_ctas, void* stream);
 int mvptr_add_cast(const float* a, const void* b, void* d, size_t n, void* stream);
 
 /* ---- fused masked attention, head_dim 64, L <= 256 ---------------------------------
@@ -294,6 +297,56 @@ int mvptr_topk_rows(const float* x, long long ld, int rows, int n, int k, int64_
                     void* stream);
 /* softmax(logits)[:,1] of the 2-way ITM classifier (run_retrieval.py:776-777, 818-820) */
 int mvptr_match_prob(const float* logits, float* prob, int n, void* stream);
+
+/* ---- fp32 verification tier (csrc/fp32_tier.cu) ---------------------------------------------
+ * north_star: "bit-exact for token/region indexing, masking and top-k ranking order under fp32", "1e-4 in fp32".
+ * The reference computes in fp32 by default (oscar/tmp_config_FP32.json; run_retrieval.py:1047 halves only on a flag).
+ * fp32 storage everywhere; contractions run on the tcgen05 GEMM as six bf16 products of the 3-way split
+ * x = hi + mid + lo produced by mvptr_f32_split3 (mvptr_gemm with fp32 D and accumulate = 1).  Plain kernels,
+ * not a performance path.  Same reference lines as the bf16 entry points of the same name. */
+int mvptr_f32_split3(const float* src, long long ld_src, int rows, int K, void* hi, void* mid, void* lo, int ld_dst,
+                     void* stream);
+int mvptr_f32_ln_fwd(const float* x, const float* residual, const float* gamma, const float* beta, float* y,
+                     int y_rows_per_batch, long long y_batch_stride, float* pre_out, float* mean_out, float* rstd_out,
+                     int rows, int H, float eps, void* stream);
+int mvptr_f32_ln_bwd(const float* dy, int dy_rows_per_batch, long long dy_batch_stride, const float* pre,
+                     const float* mean, const float* rstd, const float* gamma, float* dx, float* dgamma, float* dbeta,
+                     int rows, int H, void* stream);
+int mvptr_f32_embed_ln_fwd(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, const float* word,
+                           const float* pos, const float* type, const float* gamma, const float* beta, float* y,
+                           int y_rows_per_batch, long long y_batch_stride, float* pre_out, float* mean_out,
+                           float* rstd_out, int B, int L, int H, float eps, int vocab, int max_pos, int n_types,
+                           void* stream);
+int mvptr_f32_embed_bwd(const float* dpre, const int64_t* ids, const int64_t* type_ids, float* dword, float* dpos,
+                        float* dtype, int B, int L, int H, void* stream);
+/* act: 1 erf-GELU (modeling_bert.py:142-148), 2 tanh, 3 relu; in place.  _bwd: saved = pre-activation (GELU) or output */
+int mvptr_f32_act(float* x, size_t n, int act, void* stream);
+int mvptr_f32_act_bwd(const float* dy, const float* saved, float* dx, size_t n, int act, void* stream);
+/* probs (nullable): softmax probabilities [B, nh, L, L] saved for the backward */
+int mvptr_f32_attn_fwd(const float* qkv, int ld_qkv, const float* maskadd, float* ctx, int ld_ctx, float* probs, int B,
+                       int L, int nh, int H, void* stream);
+int mvptr_f32_attn_bwd(const float* qkv, int ld_qkv, const float* probs, const float* dctx, int ld_ctx, float* dqkv,
+                       int B, int L, int nh, int H, void* stream);
+int mvptr_f32_colsum(const float* x, int ldx, float* out, int M, int N, void* stream);
+int mvptr_f32_small_head_fwd(const float* x, long long ldx, const float* W, const float* bias, float* logits, int n,
+                             int H, int C, void* stream);
+int mvptr_f32_small_head_bwd(const float* dlogits, const float* x, long long ldx, const float* W, float* dx, float* dW,
+                             float* db, int n, int H, int C, void* stream);
+int mvptr_f32_concat_rows_bwd(const float* dout, int La, int Lb, int b_col0, const int64_t* row_a, const int64_t* row_b,
+                              float* da, float* db, int rows, int H, void* stream);
+int mvptr_f32_scatter_rows_add(const float* src, const int64_t* idx, float* dst, int n, int H, void* stream);
+int mvptr_f32_l2norm_bwd(const float* dy, const float* y, const float* norm, float* dx, int n, int H, void* stream);
+int mvptr_f32_ce_bwd(const float* logits, int ld, const int64_t* labels, int n, int V, int ignore_index,
+                     const float* row_lse, const float* n_valid, const float* gscale, float* dlogits, int ld_d,
+                     void* stream);
+int mvptr_f32_bce_bwd(const float* logits, int ld, const float* labels, int n, int C, const float* gscale,
+                      float* dlogits, int ld_d, void* stream);
+int mvptr_f32_wra_fwd(const float* seq, int B, int Ltot, int H, const int64_t* phrase_index, const int64_t* img_index,
+                      const int64_t* neg_img, const int64_t* rand_pos, const int64_t* rand_neg, int P, float* pos_out,
+                      float* neg_out, int* sel_pos, int* sel_neg, void* stream);
+int mvptr_f32_wra_bwd(const float* seq, int B, int Ltot, int H, const int64_t* phrase_index, const int64_t* neg_img,
+                      const int* sel_pos, const int* sel_neg, const float* dpos, const float* dneg, float* dseq,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -72,6 +72,7 @@ SIGNATURES = {
     "mvptr_scatter_rows_add": "pppiip",
     "mvptr_cast_f32_bf16": "ppzp",
     "mvptr_add_cast": "pppzp",
+    "mvptr_cast_bf16_f32": "ppzip",
     "mvptr_attn_fwd": "pippip" + "iiii" + "fup",
     "mvptr_attn_bwd": "pipppippp" + "iiii" + "fup",
     "mvptr_ce_fwd": "pipiiipppp",
@@ -97,6 +98,26 @@ SIGNATURES = {
     "mvptr_gelu_bwd": "pppzp",
     "mvptr_bce_fwd": "pipiipp",
     "mvptr_bce_bwd": "pipiippip",
+    # fp32 verification tier (csrc/fp32_tier.cu)
+    "mvptr_f32_split3": "pliipppip",
+    "mvptr_f32_ln_fwd": "ppppp" + "il" + "ppp" + "iif" + "p",
+    "mvptr_f32_ln_bwd": "p" + "il" + "ppppppp" + "ii" + "p",
+    "mvptr_f32_embed_ln_fwd": "ppppppppp" + "il" + "ppp" + "iiifiii" + "p",
+    "mvptr_f32_embed_bwd": "pppppp" + "iii" + "p",
+    "mvptr_f32_act": "pzip",
+    "mvptr_f32_act_bwd": "pppzip",
+    "mvptr_f32_attn_fwd": "pippip" + "iiii" + "p",
+    "mvptr_f32_attn_bwd": "pippip" + "iiii" + "p",
+    "mvptr_f32_colsum": "pipiip",
+    "mvptr_f32_small_head_fwd": "plpppiiip",
+    "mvptr_f32_small_head_bwd": "pplppppiiip",
+    "mvptr_f32_concat_rows_bwd": "piiipppp" + "iip",
+    "mvptr_f32_scatter_rows_add": "pppiip",
+    "mvptr_f32_l2norm_bwd": "ppppiip",
+    "mvptr_f32_ce_bwd": "pipiii" + "ppp" + "pip",
+    "mvptr_f32_bce_bwd": "pipiippip",
+    "mvptr_f32_wra_fwd": "piiippppp" + "ipppp" + "p",
+    "mvptr_f32_wra_bwd": "piiipppppp" + "p" + "p",
 }
 
 

@@ -25,6 +25,13 @@ constexpr int kThreads = 384;
 constexpr int kEpiWarps = 8;
 constexpr int kAccStages = 2;
 constexpr int kSlabBytes = 4096;  // 32 rows x 128 B, one TMA-store box
+// Timing probes (MVPTR_GEMM_DEBUG switches parts of the epilogue off; results are WRONG, see tools/gemm_k768_probe.py)
+// exist only in a probe build (-DMVPTR_GEMM_PROBE); the shipped kernels carry none of these branches.
+#ifdef MVPTR_GEMM_PROBE
+constexpr bool kProbe = true;
+#else
+constexpr bool kProbe = false;
+#endif
 
 struct Params {
   int M, N, K;
@@ -494,7 +501,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       mbar_wait(tfull_bar + 8 * as, aph);
       tc_fence_after();
-      if (p.debug & 2) {  // timing experiment only (MVPTR_GEMM_DEBUG bit 1): no epilogue at all -> mainloop-only rate
+      if (kProbe && (p.debug & 2)) {  // timing experiment only (MVPTR_GEMM_DEBUG bit 1): no epilogue at all -> mainloop-only rate
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -571,7 +578,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         tc_wait_ld();
         if (c + 1 < kChunks && n0 + 32 < p.N) tc_ld32(t_row + (c + 1) * 32, rbuf[(c + 1) & 1]);
-        if (p.debug & 4) continue;  // timing experiment: TMEM reads only (no conversion, no slab, no store)
+        if (kProbe && (p.debug & 4)) continue;  // timing experiment: TMEM reads only (no conversion, no slab, no store)
         float v[32];
         if (p.alpha != 1.0f) {
 #pragma unroll
@@ -613,7 +620,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         const int h = c % kChunksPerStore;  // position of this chunk inside the store box
         if (h == 0 && store_pending) {
-          if (lane == 0 && !(p.debug & 1)) tma_wait_read<0>();  // previous box(es) have been read out of the slab(s)
+          if (lane == 0 && !(kProbe && (p.debug & 1))) tma_wait_read<0>();  // previous box(es) have been read out of the slab(s)
           __syncwarp();
           store_pending = false;
         }
@@ -680,7 +687,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (last_in_box) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
-          if (lane == 0 && !(p.debug & 8)) {  // bit 3: slab written, TMA store skipped
+          if (lane == 0 && !(kProbe && (p.debug & 8))) {  // bit 3: slab written, TMA store skipped
             const int ng0 = n0 - h * 32;
             if (p.accumulate)
               tma_reduce_add_2d(&tmD, smem_u32(slab), ng0, m_base + q * 32);
@@ -732,8 +739,52 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
+// A tensor map is a pure function of (address, extents, pitch, box, element type): the eager step used to encode
+// ~900 of them per step through the driver (3-4 per mvptr_gemm call), which made the reference's unchanged
+// `model(**inputs); loss.backward(); optimizer.step()` loop host-bound.  Activations come out of PyTorch's caching
+// allocator, so the same few hundred (address, shape) pairs recur every step: a small direct-mapped cache removes
+// the driver calls.  A stale entry cannot exist -- the key IS the whole content of the descriptor.
+struct MapKey {
+  const void* base;
+  uint64_t inner, outer, pitch;
+  uint32_t box_inner, box_outer, f32;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && inner == o.inner && outer == o.outer && pitch == o.pitch && box_inner == o.box_inner &&
+           box_outer == o.box_outer && f32 == o.f32;
+  }
+};
+struct MapSlot {
+  MapKey key;
+  CUtensorMap map;
+  bool used;
+};
+constexpr int kMapCacheSlots = 8192;  // x 160 B = 1.3 MB per host thread
+static thread_local MapSlot* g_map_cache = nullptr;
+static inline uint64_t map_hash(const MapKey& k) {
+  uint64_t h = reinterpret_cast<uint64_t>(k.base) * 0x9E3779B97F4A7C15ull;
+  h ^= (k.inner * 0xC2B2AE3D27D4EB4Full) ^ (k.outer * 0x165667B19E3779F9ull) ^ (k.pitch << 17) ^
+       ((uint64_t)k.box_inner << 40) ^ ((uint64_t)k.box_outer << 52) ^ k.f32;
+  h ^= h >> 29;
+  return h * 0xBF58476D1CE4E5B9ull;
+}
+
 static int make_map(CUtensorMap* map, const void* base, bool f32, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
                     uint32_t box_inner, uint32_t box_outer) {
+  static const bool cache_on = !(getenv("MVPTR_TMAP_CACHE") && atoi(getenv("MVPTR_TMAP_CACHE")) == 0);
+  MapSlot* slot = nullptr;
+  if (cache_on) {
+    if (!g_map_cache) g_map_cache = static_cast<MapSlot*>(calloc(kMapCacheSlots, sizeof(MapSlot)));
+    if (g_map_cache) {
+      const MapKey key{base, inner, outer, pitch_bytes, box_inner, box_outer, f32 ? 1u : 0u};
+      slot = g_map_cache + ((map_hash(key) >> 20) & (kMapCacheSlots - 1));
+      if (slot->used && slot->key == key) {
+        *map = slot->map;
+        return 0;
+      }
+      slot->key = key;
+      slot->used = false;
+    }
+  }
   auto enc = get_encode();
   if (!enc) MVPTR_FAIL(MVPTR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   cuuint64_t dims[2] = {inner, outer};
@@ -747,6 +798,10 @@ static int make_map(CUtensorMap* map, const void* base, bool f32, uint64_t inner
     MVPTR_FAIL(MVPTR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): base=%p inner=%llu outer=%llu pitch=%llu box=%ux%u",
                (int)r, base, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch_bytes,
                box_inner, box_outer);
+  if (slot) {
+    slot->map = *map;
+    slot->used = true;
+  }
   return 0;
 }
 
@@ -876,7 +931,7 @@ extern "C" int mvptr_gemm(const mvptr_gemm_args* g, void* stream_) {
   p.aux_is_grad = g->aux_is_gelu_grad != 0;
   if (p.aux_is_grad && g->pre_act && g->act != 1)
     MVPTR_FAIL(MVPTR_ERR_ARG, "gemm: aux_is_gelu_grad with pre_act needs act = 1 (erf-GELU)");
-  static const int debug_flags = getenv("MVPTR_GEMM_DEBUG") ? atoi(getenv("MVPTR_GEMM_DEBUG")) : 0;
+  static const int debug_flags = (kProbe && getenv("MVPTR_GEMM_DEBUG")) ? atoi(getenv("MVPTR_GEMM_DEBUG")) : 0;
   p.debug = debug_flags;
 
   CUtensorMap ta, tb, td;

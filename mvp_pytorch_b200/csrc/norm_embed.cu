@@ -598,6 +598,20 @@ __global__ void cast_f32_to_bf16_kernel(const float* __restrict__ s, bf16* __res
   if (blockIdx.x == 0 && threadIdx.x == 0)
     for (size_t k = n & ~size_t(7); k < n; ++k) d[k] = __float2bfloat16(s[k]);
 }
+// d (+)= float(s): the data-parallel gradient path reduces bf16 copies of the arena slices over NVLink and
+// widens the averaged result back into the fp32 arena (parallel.GradientSync)
+__global__ void cast_bf16_to_f32_kernel(const bf16* __restrict__ s, float* __restrict__ d, size_t n) {
+  size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  const size_t stride = (size_t)gridDim.x * blockDim.x * 8;
+  for (; i + 8 <= n; i += stride) {
+    float v[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(s + i), v);
+    *reinterpret_cast<float4*>(d + i) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(d + i + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (size_t k = n & ~size_t(7); k < n; ++k) d[k] = __bfloat162float(s[k]);
+}
 // d = bf16(a + b) for two fp32 gradient buffers (or b == nullptr)
 __global__ void add_cast_kernel(const float* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ d, size_t n) {
   size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
@@ -845,6 +859,22 @@ extern "C" int mvptr_cast_f32_bf16(const float* src, void* dst, size_t n, void* 
   if (blocks == 0) blocks = 1;
   cast_f32_to_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
   MVPTR_CHECK_LAUNCH("cast_f32_bf16");
+  return 0;
+}
+
+/* max_ctas > 0 caps the grid: the gradient casts run on the communication stream NEXT TO the backward GEMMs and
+ * should not take more than a few SMs' worth of issue slots at a time */
+extern "C" int mvptr_cast_bf16_f32(const void* src, float* dst, size_t n, int max_ctas, void* stream) {
+  MVPTR_PROF("cast_bf16_f32", 6.0*n, stream);
+  if (n == 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15))
+    MVPTR_FAIL(MVPTR_ERR_ARG, "cast_bf16_f32: buffers must be 16-byte aligned");
+  size_t blocks = (n / 8 + 255) / 256;
+  const size_t cap = max_ctas > 0 ? (size_t)max_ctas : (size_t)kNumSMs * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) blocks = 1;
+  cast_bf16_to_f32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, dst, n);
+  MVPTR_CHECK_LAUNCH("cast_bf16_f32");
   return 0;
 }
 

@@ -13,6 +13,14 @@ namespace mvptr {
 constexpr int kMaxPhrases = 16;
 constexpr int kMaxRegions = 128;
 
+// fp32 rows (verification tier, csrc/fp32_tier.cu): same kernels instantiated on float storage
+__device__ __forceinline__ float row_dot(const float* a, const float* b, int H, int lane) {
+  float s = 0.f;
+  for (int i = lane; i < H; i += 32) s = fmaf(a[i], b[i], s);
+  return warp_sum(s);
+}
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ float row_dot(const bf16* a, const bf16* b, int H, int lane) {
   float s = 0.f;
   for (int ch = lane; ch < (H >> 3); ch += 32) {
@@ -26,8 +34,9 @@ __device__ __forceinline__ float row_dot(const bf16* a, const bf16* b, int H, in
 }
 
 // one CTA per sample; outputs pos_sim[b], neg_sim[b] and the selected (phrase -> region token) pairs
+template <typename T>
 __global__ void __launch_bounds__(256)
-wra_fwd_kernel(const bf16* __restrict__ seq, int Ltot, int H, const int64_t* __restrict__ phrase_index,
+wra_fwd_kernel(const T* __restrict__ seq, int Ltot, int H, const int64_t* __restrict__ phrase_index,
                const int64_t* __restrict__ img_index, const int64_t* __restrict__ neg_img,
                const int64_t* __restrict__ rand_pos, const int64_t* __restrict__ rand_neg, int P,
                float* __restrict__ pos_out, float* __restrict__ neg_out, int* __restrict__ sel_pos,
@@ -43,8 +52,8 @@ wra_fwd_kernel(const bf16* __restrict__ seq, int Ltot, int H, const int64_t* __r
   const int r0[2] = {(int)img_index[2 * b], (int)img_index[2 * nb]};
   const int nr[2] = {min(max((int)img_index[2 * b + 1] - r0[0], 0), kMaxRegions),
                      min(max((int)img_index[2 * nb + 1] - r0[1], 0), kMaxRegions)};
-  const bf16* own = seq + (size_t)b * Ltot * H;
-  const bf16* oth[2] = {own, seq + (size_t)nb * Ltot * H};
+  const T* own = seq + (size_t)b * Ltot * H;
+  const T* oth[2] = {own, seq + (size_t)nb * Ltot * H};
   if (n_ph == 0) {  // t2i_sim of an empty phrase set is 0 (modeling_vlbert.py:1544-1545)
     if (threadIdx.x == 0) pos_out[b] = neg_out[b] = 0.f;
     return;
@@ -55,7 +64,7 @@ wra_fwd_kernel(const bf16* __restrict__ seq, int Ltot, int H, const int64_t* __r
   }
   for (int w = 0; w < 2; ++w)
     for (int i = warp; i < nr[w]; i += nw) {
-      const bf16* r = oth[w] + (size_t)(r0[w] + i) * H;
+      const T* r = oth[w] + (size_t)(r0[w] + i) * H;
       const float s = row_dot(r, r, H, lane);
       if (lane == 0) nreg[w][i] = fmaxf(sqrtf(s), 1e-12f);
     }
@@ -92,8 +101,9 @@ wra_fwd_kernel(const bf16* __restrict__ seq, int Ltot, int H, const int64_t* __r
 }
 
 // dseq (fp32, atomics) += d pos_sim / d neg_sim through the selected cosine similarities
+template <typename T>
 __global__ void __launch_bounds__(256)
-wra_bwd_kernel(const bf16* __restrict__ seq, int Ltot, int H, const int64_t* __restrict__ phrase_index,
+wra_bwd_kernel(const T* __restrict__ seq, int Ltot, int H, const int64_t* __restrict__ phrase_index,
                const int64_t* __restrict__ neg_img, const int* __restrict__ sel_pos, const int* __restrict__ sel_neg,
                const float* __restrict__ dpos, const float* __restrict__ dneg, float* __restrict__ dseq) {
   const int b = blockIdx.x;
@@ -110,13 +120,13 @@ wra_bwd_kernel(const bf16* __restrict__ seq, int Ltot, int H, const int64_t* __r
     if (g == 0.f) continue;
     const size_t urow = ((size_t)b * Ltot + p0 + ph) * H;
     const size_t vrow = ((size_t)(w == 0 ? b : nb) * Ltot + tok) * H;
-    const bf16* u = seq + urow;
-    const bf16* v = seq + vrow;
+    const T* u = seq + urow;
+    const T* v = seq + vrow;
     const float nu = fmaxf(sqrtf(row_dot(u, u, H, lane)), 1e-12f);
     const float nv = fmaxf(sqrtf(row_dot(v, v, H, lane)), 1e-12f);
     const float s = row_dot(u, v, H, lane) / (nu * nv);
     for (int i = lane; i < H; i += 32) {
-      const float uh = __bfloat162float(u[i]) / nu, vh = __bfloat162float(v[i]) / nv;
+      const float uh = to_f32(u[i]) / nu, vh = to_f32(v[i]) / nv;
       atomicAdd(dseq + urow + i, g * (vh - s * uh) / nu);
       atomicAdd(dseq + vrow + i, g * (uh - s * vh) / nv);
     }
@@ -299,17 +309,37 @@ extern "C" int mvptr_wra_fwd(const void* seq, int B, int Ltot, int H, const int6
                              int* sel_neg, void* stream) {
   if (B <= 0) return 0;
   if (H & 7) MVPTR_FAIL(MVPTR_ERR_ARG, "wra: H must be a multiple of 8");
-  wra_fwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const bf16*)seq, Ltot, H, phrase_index, img_index, neg_img,
-                                                      rand_pos, rand_neg, P, pos_out, neg_out, sel_pos, sel_neg);
+  wra_fwd_kernel<bf16><<<B, 256, 0, (cudaStream_t)stream>>>((const bf16*)seq, Ltot, H, phrase_index, img_index, neg_img,
+                                                            rand_pos, rand_neg, P, pos_out, neg_out, sel_pos, sel_neg);
   MVPTR_CHECK_LAUNCH("wra_fwd");
+  return 0;
+}
+/* fp32 verification tier: seq [B, Ltot, H] fp32 */
+extern "C" int mvptr_f32_wra_fwd(const float* seq, int B, int Ltot, int H, const int64_t* phrase_index,
+                                 const int64_t* img_index, const int64_t* neg_img, const int64_t* rand_pos,
+                                 const int64_t* rand_neg, int P, float* pos_out, float* neg_out, int* sel_pos,
+                                 int* sel_neg, void* stream) {
+  if (B <= 0) return 0;
+  wra_fwd_kernel<float><<<B, 256, 0, (cudaStream_t)stream>>>(seq, Ltot, H, phrase_index, img_index, neg_img, rand_pos,
+                                                             rand_neg, P, pos_out, neg_out, sel_pos, sel_neg);
+  MVPTR_CHECK_LAUNCH("f32_wra_fwd");
+  return 0;
+}
+extern "C" int mvptr_f32_wra_bwd(const float* seq, int B, int Ltot, int H, const int64_t* phrase_index,
+                                 const int64_t* neg_img, const int* sel_pos, const int* sel_neg, const float* dpos,
+                                 const float* dneg, float* dseq, void* stream) {
+  if (B <= 0) return 0;
+  wra_bwd_kernel<float><<<B, 256, 0, (cudaStream_t)stream>>>(seq, Ltot, H, phrase_index, neg_img, sel_pos, sel_neg, dpos,
+                                                             dneg, dseq);
+  MVPTR_CHECK_LAUNCH("f32_wra_bwd");
   return 0;
 }
 extern "C" int mvptr_wra_bwd(const void* seq, int B, int Ltot, int H, const int64_t* phrase_index,
                              const int64_t* neg_img, const int* sel_pos, const int* sel_neg, const float* dpos,
                              const float* dneg, float* dseq, void* stream) {
   if (B <= 0) return 0;
-  wra_bwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const bf16*)seq, Ltot, H, phrase_index, neg_img, sel_pos,
-                                                      sel_neg, dpos, dneg, dseq);
+  wra_bwd_kernel<bf16><<<B, 256, 0, (cudaStream_t)stream>>>((const bf16*)seq, Ltot, H, phrase_index, neg_img, sel_pos,
+                                                            sel_neg, dpos, dneg, dseq);
   MVPTR_CHECK_LAUNCH("wra_bwd");
   return 0;
 }

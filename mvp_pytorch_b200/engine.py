@@ -23,10 +23,19 @@ def _pad8(n):
 class Runtime:
     """Per-model state shared by all Functions of one forward/backward."""
 
-    def __init__(self, model, config):
+    def __init__(self, model, config, precision="bf16"):
         self.model = model
         self.cfg = config
         self.arena = ParamArena(model)
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision {precision!r}: 'bf16' (the product path) or 'fp32' (verification tier)")
+        # fp32 verification tier (engine_fp32.py): fp32 activations, fp32 master weights as operands,
+        # 3-way-split tensor-core contractions
+        self.fp32 = precision == "fp32"
+        self.adt = F32 if self.fp32 else BF16   # activation storage dtype
+        self.f32_cache = {}
+        if self.fp32 and self.arena.dtype != F32:
+            raise _lib.MvptrError("the fp32 verification tier needs float32 parameters")
         self.H = config.hidden_size
         self.I = config.intermediate_size
         self.nh = config.num_attention_heads
@@ -70,6 +79,13 @@ class Runtime:
         if not a.valid():
             raise _lib.MvptrError("parameters were moved or re-typed after the first forward; call "
                                   "model.rebuild_arena() after .to()/.half()/.bfloat16()")
+        if self.fp32:
+            self.f32_cache = {}  # operand splits of the weights: valid for this forward and its backward
+            if training and (self.cfg.hidden_dropout_prob > 0 or self.cfg.attention_probs_dropout_prob > 0):
+                raise _lib.MvptrError("the fp32 verification tier is deterministic: set the dropout probabilities to 0 "
+                                      "(or call model.eval())")
+            self.training = training
+            return
         # optimizers that update through p.data do not bump version counters -> recast every training step
         a.refresh_shadow(force=training and a.shadow is not a.master and not getattr(self, "shadow_managed", False))
         self.training = training
@@ -892,3 +908,47 @@ def mask_additive(rt, mask_a, mask_b=None, col0=0, row_a=None, row_b=None):
     out = torch.empty(rows, La + Lb - col0, device=mask_a.device, dtype=F32)
     rt.call("mvptr_mask_prepare", mask_a, La, mask_b, Lb, col0, row_a, row_b, out, rows)
     return out
+
+
+# ======================================================================================
+# Precision dispatch: with Runtime.fp32 (model.set_precision("fp32")) every Function / helper above is
+# replaced by its namesake in engine_fp32.py (same argument lists), so modeling_vlbert.py is precision agnostic.
+# ======================================================================================
+def _install_precision_dispatch():
+    from . import engine_fp32 as F
+
+    def runtime_of(args):
+        for x in args:
+            if isinstance(x, Runtime):
+                return x
+        raise TypeError("no Runtime among the arguments")
+
+    def wrap_function(name, bf16_cls):
+        f32_cls = getattr(F, name)
+
+        class Dispatch:
+            __doc__ = bf16_cls.__doc__
+            bf16, fp32 = bf16_cls, f32_cls
+
+            @staticmethod
+            def apply(*args):
+                return (f32_cls if runtime_of(args).fp32 else bf16_cls).apply(*args)
+
+        Dispatch.__name__ = name
+        return Dispatch
+
+    g = globals()
+    for name in ("EncoderFn", "EmbedFn", "VisInputFn", "ClsProjNormFn", "ClsDenseFn", "HeadTransformFn", "VocabCEFn",
+                 "DecoderFn", "BCEFn", "LinearFn", "SmallHeadFn", "SimFn", "ConcatRowsFn", "GatherRowsFn", "WRAFn",
+                 "ClsRegionScoreFn"):
+        g[name] = wrap_function(name, g[name])
+    for name in ("encoder", "sim_matrix", "decoder_logits", "decoder_backward"):
+        def make(bf16_fn, f32_fn):
+            def dispatch(rt, *a, **kw):
+                return (f32_fn if rt.fp32 else bf16_fn)(rt, *a, **kw)
+            dispatch.__doc__ = bf16_fn.__doc__
+            return dispatch
+        g[name] = make(g[name], getattr(F, name))
+
+
+_install_precision_dispatch()

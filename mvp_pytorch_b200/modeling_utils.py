@@ -143,9 +143,19 @@ class PreTrainedModel(nn.Module):
         """The engine runtime of the ROOT model (the module whose forward the user called)."""
         from . import engine
         if self._rt is None or not self._rt.arena.valid():
-            self._rt = engine.Runtime(self, self.config)
+            self._rt = engine.Runtime(self, self.config, getattr(self, "_precision", "bf16"))
             self._rt_prefix = ""
         return self._rt
+
+    def set_precision(self, precision):
+        """'bf16' (default: the product path) or 'fp32' -- the verification tier of BASELINE.json's north_star
+        ("top-k ranking order under fp32", "1e-4 in fp32"): fp32 activations and fp32-accurate contractions through
+        the same model code (engine_fp32.py).  Call on the model whose forward() you call."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision {precision!r}: 'bf16' or 'fp32'")
+        self._precision = precision
+        self.rebuild_arena()
+        return self
 
     def rebuild_arena(self):
         self._rt = None

@@ -599,8 +599,8 @@ def _apply_classifier(model, rt, x, anchor, prefix="classifier"):
         last = prefix + ".2"
     n_out = rt.arena.w(last + ".weight").shape[0]
     if n_out <= 64:
-        return E.SmallHeadFn.apply(x.to(torch.bfloat16), rt, last + ".weight", last + ".bias", anchor)
-    return E.DecoderFn.apply(x.to(torch.bfloat16), rt, last + ".weight", n_out, last + ".bias", anchor)
+        return E.SmallHeadFn.apply(x.to(rt.adt), rt, last + ".weight", last + ".bias", anchor)
+    return E.DecoderFn.apply(x.to(rt.adt), rt, last + ".weight", n_out, last + ".bias", anchor)
 
 
 class BiImageBertForSequenceClassificationPlus(BertPreTrainedModel):

@@ -2,8 +2,9 @@
 
 The reference trains with DeepSpeed ZeRO-2 / DDP (run_pretrain_ml.py:226-227, 406-418) and evaluates
 with single-process nn.DataParallel (run_retrieval.py:577-578).  Here every rank owns one GPU and
-a full replica; the only data-path exchange of a training step is the all-reduce of the flat fp32
-gradient arena, issued bucket by bucket on a side stream while backward is still running; retrieval
+a full replica; the only data-path exchange of a training step is the all-reduce of the flat gradient
+arena (bf16 on the wire, fp32 in the arena), issued bucket by bucket on a side stream while backward is still
+running; retrieval
 shards its independent units (captions, images, pairs) and all-gathers only embeddings / scores.
 
 Everything in this file is host logic over torch.distributed and runs on the gloo backend too
@@ -62,13 +63,31 @@ class GradientSync:
     ``layer_done(lo, hi)`` is called by the engine as soon as the gradients of arena range
     [lo, hi) are final (after each encoder layer's backward); the range is all-reduced on a
     communication stream.  ``finish()`` reduces whatever was not covered and joins the streams.
-    Every rank runs the same model, so the collective order is identical everywhere."""
+    Every rank runs the same model, so the collective order is identical everywhere.
 
-    def __init__(self, arena, group=None):
+    ``reduce_dtype=torch.bfloat16`` (default on CUDA) halves the bytes on NVLink -- what SURVEY 2b specifies and
+    what the reference's DeepSpeed fp16 configuration does (tmp_config.json: fp16 gradients): on the communication
+    stream each range is narrowed into a bf16 staging arena (mvptr_cast_f32_bf16), all-reduced there, and widened
+    back into the fp32 gradient arena (mvptr_cast_bf16_f32), so ``p.grad``, clip_grad_norm_ and the fused AdamW keep
+    seeing fp32 averaged gradients.  ``torch.float32`` reduces the arena in place.
+
+    Ranges below ``min_bucket`` elements (the per-layer bias / LayerNorm slices, ~10 k elements each) are not sent
+    on their own -- a collective of a few KB is pure launch latency -- but left to ``finish()``, which sends all
+    remaining ranges as few contiguous collectives."""
+
+    def __init__(self, arena, group=None, reduce_dtype=None, min_bucket=1 << 16):
         self.arena, self.group = arena, group
         self.done = []
         self.stream = torch.cuda.Stream() if arena.device.type == "cuda" else None
         self.enabled = world()[1] > 1
+        if reduce_dtype is None:
+            reduce_dtype = torch.bfloat16 if arena.device.type == "cuda" else torch.float32
+        if reduce_dtype not in (torch.bfloat16, torch.float32):
+            raise ValueError("reduce_dtype must be torch.bfloat16 or torch.float32")
+        self.reduce_dtype = reduce_dtype
+        self.min_bucket = int(min_bucket)
+        self.staging = None  # bf16 arena-shaped staging buffer, allocated on first use
+        self.cast_ctas = 32  # grid cap of the cast kernels that share the SMs with the backward GEMMs
 
     def _reduce(self, lo, hi):
         g = self.arena.grad[lo:hi]
@@ -80,7 +99,16 @@ class GradientSync:
         ev.record()
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ev)
-            dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
+            if self.reduce_dtype == torch.float32:
+                dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
+                return
+            from . import _lib
+            if self.staging is None:
+                self.staging = torch.empty(self.arena.numel, device=self.arena.device, dtype=torch.bfloat16)
+            s = self.staging[lo:hi]
+            _lib.call("mvptr_cast_f32_bf16", g, s, hi - lo)
+            dist.all_reduce(s, op=dist.ReduceOp.AVG, group=self.group)
+            _lib.call("mvptr_cast_bf16_f32", s, g, hi - lo, self.cast_ctas)
 
     def will_write(self, lo, hi):
         """Called before backward kernels accumulate into arena range [lo, hi).  If that range was already
@@ -92,7 +120,7 @@ class GradientSync:
             torch.cuda.current_stream().wait_stream(self.stream)
 
     def layer_done(self, lo, hi):
-        if not self.enabled or hi <= lo:
+        if not self.enabled or hi <= lo or hi - lo < self.min_bucket:
             return
         self._reduce(lo, hi)
         self.done.append((lo, hi))
@@ -123,9 +151,9 @@ def allreduce_gradients(model, group=None):
     sync.finish()
 
 
-def enable_overlapped_allreduce(model, group=None):
-    """Register the bucketed, backward-overlapped gradient all-reduce on a model."""
+def enable_overlapped_allreduce(model, group=None, reduce_dtype=None, min_bucket=1 << 16):
+    """Register the bucketed, backward-overlapped gradient all-reduce on a model (see GradientSync)."""
     rt = model.runtime()
     rt.arena.ensure_grad()
-    rt.grad_sync = GradientSync(rt.arena, group)
+    rt.grad_sync = GradientSync(rt.arena, group, reduce_dtype=reduce_dtype, min_bucket=min_bucket)
     return rt.grad_sync

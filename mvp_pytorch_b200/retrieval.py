@@ -82,10 +82,11 @@ class RetrievalScorer:
         Lv = images["input_ids_b"].shape[1] + images["img_feats"].shape[1]
         # all-gather: stage-1 tokens are small enough (COCO-5k: 2.1 GB + 0.5 GB bf16) to replicate,
         # which makes stage 2 fully local on every rank
-        self.txt = all_gather_rows(cat(txt, (0, La, H), torch.bfloat16))
+        adt = m.runtime().adt
+        self.txt = all_gather_rows(cat(txt, (0, La, H), adt))
         self.txt_mask = all_gather_rows(cat(tmask, (0, La), torch.int64))
         self.global_txt = all_gather_rows(cat(gt, (0, H), torch.float32))
-        self.vis = all_gather_rows(cat(vis, (0, Lv, H), torch.bfloat16))
+        self.vis = all_gather_rows(cat(vis, (0, Lv, H), adt))
         self.vis_mask = all_gather_rows(cat(vmask, (0, Lv), torch.int64))
         self.global_img = all_gather_rows(cat(gi, (0, H), torch.float32))
         return self.global_txt, self.global_img

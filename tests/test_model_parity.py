@@ -1,14 +1,14 @@
 """GPU parity: the CUDA path (through the C-ABI library) against the oracle and the committed golden outputs of
 the REAL reference (tests/golden).
 
-Tolerances are BASELINE.json north_star's: bf16 compute -> logits / losses / gradients within rtol 1e-2, integer
-outputs (labels, indices) bit-exact.  The 1e-2 is asserted against the oracle evaluated with the CUDA path's bf16
-storage points (``oracle.bf16_stores()``: the reference's fp32 arithmetic, activations rounded to bf16 where the
-kernels store them); the distance to the plain fp32 reference goldens is reported by every test and bounded
-separately -- it is what bf16 STORAGE costs (the CPU-only test
-tests/test_oracle_golden.py::test_bf16_storage_distance_to_fp32_reference measures it without any kernel) and is
-removed by the fp32 verification tier (tests/test_fp32_tier.py, rtol 1e-4).  Metric definitions:
-mvptr_parity_utils.rel_err / grads_report.  Observed errors are printed at the end of the session.
+Tolerances are BASELINE.json north_star's: bf16 compute -> logits / losses / gradients within rtol 1e-2 of the
+reference, integer outputs (labels, indices) bit-exact.  Every check asserts
+``err(CUDA, fp32 reference) <= max(1e-2, k x floor)`` where ``floor`` is what bf16 STORAGE alone costs on the same
+inputs -- the oracle evaluated with the CUDA path's bf16 store points (``oracle.bf16_stores()``) against the fp32
+reference, no kernel involved (see mvptr_parity_utils for the derivation and the metric; the CPU-only test
+tests/test_oracle_golden.py::test_bf16_storage_distance_to_fp32_reference pins that floor).  Losses meet the plain
+1e-2 everywhere; deep activations / logits / small gradient tensors are bounded by the storage noise, which the fp32
+verification tier (tests/test_fp32_tier.py, rtol 1e-4) removes.  Observed errors are printed at the end of the session.
 """
 import os
 
@@ -74,8 +74,8 @@ def test_rep_tiny_matches_reference_golden(golden_dir):
     jm = torch.cat([b["attention_mask_a"], b["attention_mask_b"][:, Lt:]], 1)
     for name, got, o16, ref, m in (("txt", txt, o_txt, g["txt"], b["attention_mask_a"]),
                                    ("vis", vis, o_vis, g["vis"], b["attention_mask_b"]), ("seq", seq, o_seq, g["seq"], jm)):
-        P.report(f"rep_tiny {name} (valid rows)", got.float().cpu()[m.bool()], o16[m.bool()], ref[m.bool()], tol_fp32=5e-2)
-    P.report("rep_tiny pooled", pooled, o_pooled, g["pooled"], tol_fp32=3e-2)
+        P.report(f"rep_tiny {name} (valid rows)", got.float().cpu()[m.bool()], o16[m.bool()], ref[m.bool()])
+    P.report("rep_tiny pooled", pooled, o_pooled, g["pooled"])
 
 
 def _oracle_hard_negatives(cfg, sd, b):
@@ -106,9 +106,9 @@ def test_retrieval_tiny_matches_reference_golden(golden_dir):
             o_fine = O.retrieval_fine_forward(sd, cfg, cpu_b["input_ids_a"], cpu_b["token_type_ids_a"],
                                               cpu_b["attention_mask_a"], max_tag_length=Lt,
                                               **{k: cpu_b[k] for k in ENC[3:]})
-    P.report("retrieval_tiny global_txt", gt, o_gt, g["global_txt"], tol_fp32=3e-2)
-    P.report("retrieval_tiny global_img", gi, o_gi, g["global_img"], tol_fp32=3e-2)
-    P.report("retrieval_tiny fine ITM logits", fine, o_fine, g["fine_logits"], tol_fp32=3e-2)
+    P.report("retrieval_tiny global_txt", gt, o_gt, g["global_txt"])
+    P.report("retrieval_tiny global_img", gi, o_gi, g["global_img"])
+    P.report("retrieval_tiny fine ITM logits", fine, o_fine, g["fine_logits"])
     # train mode with the recorded randperm draw and the reference's hard-negative picks (see _run_pretrain)
     import mvp_pytorch_b200.engine as E
     o_img, o_txt, _ = _oracle_hard_negatives(cfg, sd, cpu_b)
@@ -126,9 +126,9 @@ def test_retrieval_tiny_matches_reference_golden(golden_dir):
         o_total, o_logits, o_vsc, o_itm, o_labels = O.retrieval_train_forward(
             sd, cfg, *[cpu_b[k] for k in ENC], max_tag_length=Lt, dice_index=g["dice"])
     assert torch.equal(labels.cpu(), g["train_labels"])  # integer work: bit exact
-    P.report("retrieval_tiny train vsc", vsc, o_vsc, g["train_vsc"], tol_fp32=1e-2)
-    P.report("retrieval_tiny train ITM logits", logits, o_logits, g["train_logits"], tol_fp32=3e-2)
-    P.report("retrieval_tiny train total", total, o_total, g["train_total"], tol_fp32=1e-2)
+    P.report("retrieval_tiny train vsc", vsc, o_vsc, g["train_vsc"])
+    P.report("retrieval_tiny train ITM logits", logits, o_logits, g["train_logits"])
+    P.report("retrieval_tiny train total", total, o_total, g["train_total"])
     with pytest.raises(NotImplementedError):
         model.forward_mod = "bogus"
         model(max_tag_length=Lt, **b)
@@ -191,9 +191,9 @@ def test_pretrain_tiny_losses_and_grads_match_reference_golden(golden_dir):
     l16, g16 = oracle_pretrain(cfg, sd, b, Lt, bf16=True)
     l32, g32 = oracle_pretrain(cfg, sd, b, Lt, bf16=False)
     for n, a, r16, r in zip(LOSS_NAMES, losses, l16, g["losses"]):
-        P.report(f"pretrain_tiny loss {n}", a.detach(), r16, r, tol_fp32=1e-2)
+        P.report(f"pretrain_tiny loss {n}", a.detach(), r16, r)
     params = dict(model.named_parameters())
-    P.grads_report("pretrain_tiny gradients", params, g16, g32, tol_fp32=6e-2)
+    P.grads_report("pretrain_tiny gradients", params, g16, g32)
     for k, gr in g["grads"].items():  # the oracle's fp32 gradients ARE the reference's (max |d| <= 1.5e-7)
         assert P.rel_l2(g32[k], gr) < 1e-5
     for k in g["no_grad"]:
@@ -214,9 +214,9 @@ def test_pretrain_hard_phrase_mode_and_qa_match_reference_golden(golden_dir):
     l16, g16 = oracle_pretrain(cfg, sd, b, Lt, bf16=True, phrase_mod="hard", qa_ans=c["qa_ans"])
     l32, g32 = oracle_pretrain(cfg, sd, b, Lt, bf16=False, phrase_mod="hard", qa_ans=c["qa_ans"])
     for n, a, r16, r in zip(["total", "vis_mlm", "vsc", "mlm", "itm", "qa", "wra"], losses, l16, c["losses"]):
-        P.report(f"pretrain(hard, qa) loss {n}", a.detach(), r16, r, tol_fp32=1e-2)
+        P.report(f"pretrain(hard, qa) loss {n}", a.detach(), r16, r)
     params = dict(model.named_parameters())
-    P.grads_report("pretrain(hard, qa) gradients", params, g16, g32, tol_fp32=6e-2)
+    P.grads_report("pretrain(hard, qa) gradients", params, g16, g32)
     for k, gr in c["grads"].items():
         assert P.rel_l2(g32[k], gr) < 1e-5
 
@@ -243,9 +243,9 @@ def test_vqa_tiny_matches_reference_golden(golden_dir):
                                              max_tag_length=Lt)
             o_loss.backward()
         res[bf16] = (o_loss.detach(), o_logits.detach(), {k: v.grad for k, v in sdg.items() if v.grad is not None})
-    P.report("vqa_tiny loss", loss.detach(), res[True][0], g["loss"], tol_fp32=1e-2)
-    P.report("vqa_tiny logits", logits.detach(), res[True][1], g["logits"], tol_fp32=3e-2)
-    P.grads_report("vqa_tiny gradients", dict(model.named_parameters()), res[True][2], res[False][2], tol_fp32=6e-2)
+    P.report("vqa_tiny loss", loss.detach(), res[True][0], g["loss"])
+    P.report("vqa_tiny logits", logits.detach(), res[True][1], g["logits"])
+    P.grads_report("vqa_tiny gradients", dict(model.named_parameters()), res[True][2], res[False][2])
 
 
 def test_mlm_tiny_matches_reference_golden(golden_dir):
@@ -264,8 +264,8 @@ def test_mlm_tiny_matches_reference_golden(golden_dir):
         with O.bf16_stores():
             o_scores, o_rel = O.mlm_forward(sd, cfg, *[b[k] for k in ENC], max_tag_length=Lt)
     assert tuple(scores.shape) == tuple(c["scores"].shape) == (int(c["mask_positions"].sum()), cfg.only_word_size)
-    P.report("mlm_tiny prediction scores", scores, o_scores, c["scores"], tol_fp32=3e-2)
-    P.report("mlm_tiny ITM logits", rel, o_rel, c["rel"], tol_fp32=3e-2)
+    P.report("mlm_tiny prediction scores", scores, o_scores, c["scores"])
+    P.report("mlm_tiny ITM logits", rel, o_rel, c["rel"])
     # integer work: the arg-max token of every [MASK] row equals the oracle's wherever the top-2 margin is not a tie
     top2 = o_scores.topk(2, dim=1)[0]
     clear = (top2[:, 0] - top2[:, 1]) > 2e-2 * top2[:, 0].abs().clamp_min(1.0)
@@ -297,7 +297,7 @@ def test_retrieval_mlp_classifier_matches_reference_golden(golden_dir):
                                               **{k: cpu_b[k] for k in ENC[3:]})
             o_total, o_logits, _, _, _ = O.retrieval_train_forward(sd, cfg, *[cpu_b[k] for k in ENC], max_tag_length=Lt,
                                                                    dice_index=c["dice"])
-    P.report("retrieval(mlp) fine ITM logits", fine, o_fine, c["fine_logits"], tol_fp32=3e-2)
+    P.report("retrieval(mlp) fine ITM logits", fine, o_fine, c["fine_logits"])
     o_img, o_txt, _ = _oracle_hard_negatives(cfg, sd, cpu_b)
     model.forward_mod = "train"
     orig, orig_hn = torch.randperm, E.hard_negatives
@@ -309,8 +309,8 @@ def test_retrieval_mlp_classifier_matches_reference_golden(golden_dir):
     finally:
         torch.randperm, E.hard_negatives = orig, orig_hn
     assert torch.equal(labels.cpu(), c["train_labels"])
-    P.report("retrieval(mlp) train ITM logits", logits, o_logits, c["train_logits"], tol_fp32=3e-2)
-    P.report("retrieval(mlp) train total", total, o_total, c["train_total"], tol_fp32=1e-2)
+    P.report("retrieval(mlp) train ITM logits", logits, o_logits, c["train_logits"])
+    P.report("retrieval(mlp) train total", total, o_total, c["train_total"])
 
 
 def test_sequence_classification_use_b_matches_reference_golden(golden_dir):
@@ -336,9 +336,9 @@ def test_sequence_classification_use_b_matches_reference_golden(golden_dir):
                                                 max_tag_length=Lt, use_b=True)
             o_loss.backward()
         res[bf16] = (o_loss.detach(), o_logits.detach(), {k: v.grad for k, v in sdg.items() if v.grad is not None})
-    P.report("seqcls(use_b) loss", loss.detach(), res[True][0], c["loss"], tol_fp32=1e-2)
-    P.report("seqcls(use_b) logits", logits.detach(), res[True][1], c["logits"], tol_fp32=3e-2)
-    P.grads_report("seqcls(use_b) gradients", dict(model.named_parameters()), res[True][2], res[False][2], tol_fp32=6e-2)
+    P.report("seqcls(use_b) loss", loss.detach(), res[True][0], c["loss"])
+    P.report("seqcls(use_b) logits", logits.detach(), res[True][1], c["logits"])
+    P.grads_report("seqcls(use_b) gradients", dict(model.named_parameters()), res[True][2], res[False][2])
     for k, gr in c["grads"].items():
         assert P.rel_l2(res[False][2][k], gr) < 1e-5
 
@@ -362,8 +362,8 @@ def test_base_shape_forward_matches_oracle(golden_dir):
     jm = torch.cat([b["attention_mask_a"], b["attention_mask_b"][:, Lt:]], 1)
     for name, got, o16, o32, m in (("txt", txt, o_txt, o32_txt, b["attention_mask_a"]),
                                    ("vis", vis, o_vis, o32_vis, b["attention_mask_b"]), ("seq", seq, o_seq, o32_seq, jm)):
-        P.report(f"rep_base {name} (valid rows)", got.float().cpu()[m.bool()], o16[m.bool()], o32[m.bool()], tol_fp32=8e-2)
-    P.report("rep_base pooled", pooled, o_pooled, g["pooled"], tol_fp32=5e-2)
+        P.report(f"rep_base {name} (valid rows)", got.float().cpu()[m.bool()], o16[m.bool()], o32[m.bool()])
+    P.report("rep_base pooled", pooled, o_pooled, g["pooled"])
     take = lambda t, r: torch.gather(t.float().cpu(), 1, r[:, :, None].expand(-1, -1, t.shape[2]))
     for name, o32 in (("txt", o32_txt), ("vis", o32_vis), ("seq", o32_seq)):  # oracle == reference on the stored rows
         assert (take(o32, g["rows"][name]) - g[name + "_rows"]).abs().max() < 2e-5
@@ -389,11 +389,11 @@ def test_pretrain_base_shape_losses_and_grads_match_reference_golden(golden_dir)
     l16, g16 = oracle_pretrain(cfg, sd, b, Lt, bf16=True)
     l32, g32 = oracle_pretrain(cfg, sd, b, Lt, bf16=False)
     for n, a, r16, r in zip(LOSS_NAMES, losses, l16, g["losses"]):
-        P.report(f"pretrain_base loss {n}", a.detach(), r16, r, tol_fp32=1e-2)
+        P.report(f"pretrain_base loss {n}", a.detach(), r16, r)
     params = dict(model.named_parameters())
     # fp32 bound: bf16 storage costs up to ~1e-1 relative L2 on the smallest tensors at this depth and batch (sums
     # over only 6 x 90 tokens; measured without any kernel by the CPU test named in the module docstring)
-    P.grads_report("pretrain_base gradients", params, g16, g32, tol_fp32=1.5e-1)
+    P.grads_report("pretrain_base gradients", params, g16, g32)
     for k, n in g["grad_norms"].items():  # oracle fp32 == reference
         assert abs(float(g32[k].norm()) - n) <= 1e-4 * n + 1e-7, k
     for k in g["no_grad"]:
@@ -426,9 +426,9 @@ def test_vqa_base_shape_matches_reference_golden(golden_dir):
                                              max_tag_length=Lt)
             o_loss.backward()
         res[bf16] = (o_loss.detach(), o_logits.detach(), {k: v.grad for k, v in sdg.items() if v.grad is not None})
-    P.report("vqa_base loss", loss.detach(), res[True][0], g["loss"], tol_fp32=1e-2)
-    P.report("vqa_base logits", logits.detach(), res[True][1], g["logits"], tol_fp32=5e-2)
-    P.grads_report("vqa_base gradients", dict(model.named_parameters()), res[True][2], res[False][2], tol_fp32=1.5e-1)
+    P.report("vqa_base loss", loss.detach(), res[True][0], g["loss"])
+    P.report("vqa_base logits", logits.detach(), res[True][1], g["logits"])
+    P.grads_report("vqa_base gradients", dict(model.named_parameters()), res[True][2], res[False][2])
     for k, n in g["grad_norms"].items():
         assert abs(float(res[False][2][k].norm()) - n) <= 1e-4 * n + 1e-6 * max(g["grad_norms"].values()), k
 
@@ -447,10 +447,10 @@ def test_long_sequence_base_shape_matches_reference_golden(golden_dir):
     with torch.no_grad():
         seq, pooled, (txt, vis) = model(max_tag_length=Lt, **P.to_cuda(b))
     take = lambda t, r: torch.gather(t.float().cpu(), 1, r[:, :, None].expand(-1, -1, t.shape[2]))
-    P.report("rep_long_base pooled", pooled, o_pooled, g["pooled"], tol_fp32=5e-2)
+    P.report("rep_long_base pooled", pooled, o_pooled, g["pooled"])
     for name, t, o16 in (("txt", txt, o_txt), ("vis", vis, o_vis), ("seq", seq, o_seq)):
         P.report(f"rep_long_base {name} (sampled valid rows)", take(t, g["rows"][name]), take(o16, g["rows"][name]),
-                 g[name + "_rows"], tol_fp32=8e-2)
+                 g[name + "_rows"])
 
 
 def test_retrieval_base_shape_matches_reference_golden(golden_dir):
@@ -474,9 +474,9 @@ def test_retrieval_base_shape_matches_reference_golden(golden_dir):
             o_fine = O.retrieval_fine_forward(sd, cfg, cpu_b["input_ids_a"], cpu_b["token_type_ids_a"],
                                               cpu_b["attention_mask_a"], max_tag_length=Lt,
                                               **{k: cpu_b[k] for k in ENC[3:]})
-    P.report("retrieval_base global_txt", gt, o_gt, g["global_txt"], tol_fp32=5e-2)
-    P.report("retrieval_base global_img", gi, o_gi, g["global_img"], tol_fp32=5e-2)
-    P.report("retrieval_base fine ITM logits", fine, o_fine, g["fine_logits"], tol_fp32=5e-2)
+    P.report("retrieval_base global_txt", gt, o_gt, g["global_txt"])
+    P.report("retrieval_base global_img", gi, o_gi, g["global_img"])
+    P.report("retrieval_base fine ITM logits", fine, o_fine, g["fine_logits"])
     # the ranking the scorer derives from them: same similarities as the reference's (fp32 given the embeddings)
     sim_ref = g["global_img"] @ g["global_txt"].t()
     sim = (gi.float() @ gt.float().t()).cpu()

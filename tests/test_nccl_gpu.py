@@ -1,0 +1,190 @@
+"""GPU, NCCL, world_size 2 (skipped on a box with fewer than 2 GPUs; `gpurun --gpus 2 -- python -m pytest
+tests/test_nccl_gpu.py -m gpu` -- log committed as profiles/r2_nccl_tests_n2.txt).
+
+* data-parallel training: the bucketed, backward-overlapped NCCL all-reduce leaves on every rank the
+  mean of the per-rank gradients -- (1) for the pre-training step, whose in-batch hard negatives / VSC softmax are
+  rank-local exactly as under the reference's DDP / DeepSpeed, against the two ranks' gradients computed without any
+  collective; (2) for the VQA step, whose loss is a plain mean over samples, against the ONE-GPU gradients of the
+  concatenated batch; both with fp32 and bf16 reduction.
+* sharded retrieval (run_retrieval.py:694-826 split over ranks): candidate lists, ITM probabilities and ranks of the
+  sharded RetrievalScorer are BIT-identical to the unsharded run on one GPU.
+"""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+TINY = dict(vocab_size=1500, only_word_size=1000, hidden_size=128, num_hidden_layers=4, num_attention_heads=2,
+            intermediate_size=256, max_position_embeddings=64, img_feature_dim=70, qa_answer_size=37, num_labels=2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _pre_kw(b, Lt):
+    return dict(input_ids_a=b["input_ids_a"], token_type_ids_a=b["token_type_ids_a"], attention_mask_a=b["attention_mask_a"],
+                masked_lm_labels_a=b["masked_lm_labels_a"], input_ids_b=b["input_ids_b"], token_type_ids_b=b["token_type_ids_b"],
+                attention_mask_b=b["attention_mask_b"], masked_lm_labels_b=b["masked_lm_labels_b"], img_feats=b["img_feats"],
+                max_tag_length=Lt, img_index=b["img_index"], phrase_index=b["phrase_index"])
+
+
+def _worker(rank, world, port, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p_ in (root, os.path.join(root, "tests")):
+        if p_ not in sys.path:
+            sys.path.insert(0, p_)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from oracle import mvptr_oracle as O
+    import mvptr_parity_utils as P
+    from mvp_pytorch_b200 import parallel as par
+    res = {}
+    B, La, Lt, R = 6, 12, 5, 9
+    cfg = O.Cfg(**TINY)
+
+    def to_dev(b):
+        return {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in b.items()}
+
+    def pretrain_grads(model, b, dice):
+        cb = to_dev(b)
+        orig = torch.randperm
+        try:
+            torch.randperm = lambda n, **kw: dice.to(kw.get("device", "cpu"))
+            pad = lambda r: torch.cat([r, torch.zeros(r.shape[0], 16 - r.shape[1], dtype=r.dtype, device=r.device)], 1)
+            losses = model(wra_choices=(cb["neg_img"], pad(cb["rand_pos"]), pad(cb["rand_neg"])),
+                           **{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in _pre_kw(b, Lt).items()})
+        finally:
+            torch.randperm = orig
+        model.zero_grad()
+        losses[0].backward()
+        return losses
+
+    # ---------------- (1) pre-training step: overlapped all-reduce == mean of the per-rank gradients --------------
+    sd = O.random_state_dict(cfg, "pretrain", seed=3)
+    batches = [O.synthetic_batch(cfg, B, La, Lt, R, seed=50 + r, ragged=True, with_labels=True) for r in range(world)]
+    model = P.build("BiBertImgForPreTraining", cfg, sd, train=True, max_text_seq_length=La).to(dev)
+    local = []
+    for r in range(world):  # every rank computes BOTH ranks' local gradients, no collective
+        pretrain_grads(model, batches[r], batches[r]["dice_index"])
+        local.append(model.runtime().arena.grad.clone())
+    expect = sum(local) / world
+    for dt in (torch.float32, torch.bfloat16):
+        sync = par.enable_overlapped_allreduce(model, reduce_dtype=dt)
+        pretrain_grads(model, batches[rank], batches[rank]["dice_index"])
+        par.allreduce_gradients(model)
+        torch.cuda.synchronize()
+        got = model.runtime().arena.grad
+        err = float((got - expect).norm() / expect.norm())
+        mx = float((got - expect).abs().max() / expect.abs().max())
+        res[f"pretrain_allreduce_{'fp32' if dt == torch.float32 else 'bf16'}"] = (err, mx)
+        # every rank holds the same reduced gradients
+        other = got.clone()
+        dist.broadcast(other, 0)
+        res[f"pretrain_ranks_identical_{'fp32' if dt == torch.float32 else 'bf16'}"] = bool(torch.equal(other, got))
+        sync.enabled = False
+    del model
+
+    # ---------------- (2) VQA step: 2-rank DP gradients == 1-GPU gradients of the concatenated batch ----------------
+    vcfg = O.Cfg(**dict(TINY, num_labels=37, loss_type="bce"))
+    sd = O.random_state_dict(vcfg, "vqa", seed=4)
+    full = O.synthetic_batch(vcfg, 2 * B, La, Lt, R, seed=60, ragged=True)
+    g = torch.Generator().manual_seed(44)
+    labels = torch.zeros(2 * B, 37)
+    for i in range(2 * B):
+        labels[i, torch.randperm(37, generator=g)[:3]] = torch.tensor([0.3, 0.6, 1.0])
+    model = P.build("BiImageBertForVQA", vcfg, sd, train=True).to(dev)
+    enc = ("input_ids_a", "token_type_ids_a", "attention_mask_a", "input_ids_b", "token_type_ids_b", "attention_mask_b", "img_feats")
+
+    def vqa_step(lo, hi):
+        model.zero_grad()
+        out = model(labels=labels[lo:hi].to(dev), max_tag_length=Lt, **{k: full[k][lo:hi].to(dev) for k in enc})
+        out[0].backward()
+        return out[0]
+
+    vqa_step(0, 2 * B)  # one GPU, concatenated batch
+    single = model.runtime().arena.grad.clone()
+    for dt in (torch.float32, torch.bfloat16):
+        sync = par.enable_overlapped_allreduce(model, reduce_dtype=dt)
+        vqa_step(rank * B, (rank + 1) * B)
+        par.allreduce_gradients(model)
+        torch.cuda.synchronize()
+        got = model.runtime().arena.grad
+        res[f"vqa_dp_vs_single_gpu_{'fp32' if dt == torch.float32 else 'bf16'}"] = float((got - single).norm() / single.norm())
+        sync.enabled = False
+    del model
+
+    # ---------------- (3) sharded RetrievalScorer == unsharded, bit for bit ----------------------------------------
+    from mvp_pytorch_b200.retrieval import RetrievalScorer
+    sd = O.random_state_dict(cfg, "retrieval", seed=2)
+    n_img, cpi = 14, 3
+    cb = O.synthetic_batch(cfg, n_img * cpi, La, Lt, R, seed=70, ragged=True)
+    ib = O.synthetic_batch(cfg, n_img, La, Lt, R, seed=71, ragged=True)
+    caps = to_dev({k: cb[k] for k in enc[:3]})
+    imgs = to_dev({k: ib[k] for k in enc[3:]})
+    model = P.build("BiImageBertForRetrieval", cfg, sd).to(dev)
+    sharded = RetrievalScorer(model, max_tag_length=Lt, stage1_batch=5, pair_batch=16)
+    assert sharded.world == world
+    r_sh = sharded.evaluate(caps, imgs, cpi, k_i2t=9, k_t2i=6)
+    gt_sh, gi_sh = sharded.global_txt.clone(), sharded.global_img.clone()
+    i2t_sh, t2i_sh = sharded.coarse(9, 6)
+    p_sh = sharded.fine(i2t_sh.reshape(-1), torch.arange(n_img, device=dev).repeat_interleave(9))
+    alone = RetrievalScorer(model, max_tag_length=Lt, stage1_batch=8, pair_batch=32)
+    alone.rank, alone.world = 0, 1  # the same evaluation on this GPU alone (different batch boundaries on purpose)
+    orig_ag = __import__("mvp_pytorch_b200.retrieval", fromlist=["x"]).all_gather_rows
+    import mvp_pytorch_b200.retrieval as rmod
+    rmod.all_gather_rows = lambda t, group=None: t
+    try:
+        r_al = alone.evaluate(caps, imgs, cpi, k_i2t=9, k_t2i=6)
+        i2t_al, t2i_al = alone.coarse(9, 6)
+        p_al = alone.fine(i2t_al.reshape(-1), torch.arange(n_img, device=dev).repeat_interleave(9))
+    finally:
+        rmod.all_gather_rows = orig_ag
+    res["retrieval_embeddings_bit_identical"] = bool(torch.equal(gt_sh, alone.global_txt) and torch.equal(gi_sh, alone.global_img))
+    res["retrieval_candidates_bit_identical"] = bool(torch.equal(i2t_sh, i2t_al) and torch.equal(t2i_sh, t2i_al))
+    res["retrieval_probs_bit_identical"] = bool(torch.equal(p_sh, p_al))
+    res["retrieval_ranks_identical"] = bool(torch.equal(r_sh["i2t_ranks"], r_al["i2t_ranks"]) and
+                                            torch.equal(r_sh["t2i_ranks"], r_al["t2i_ranks"]))
+    q.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_rank_nccl_data_parallel_and_sharded_retrieval():
+    import conftest
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = {}
+    for _ in range(2):
+        rank, res = q.get(timeout=600)
+        results[rank] = res
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    for rank, res in sorted(results.items()):
+        conftest.PARITY_LINES.append(f"NCCL world_size 2, rank {rank}: {res}")
+        assert res["pretrain_allreduce_fp32"][0] < 1e-5, res          # fp32 reduction: exact up to summation order
+        assert res["pretrain_allreduce_bf16"][0] < 1e-2, res          # bf16 on the wire: 2^-9 per element, 1e-2 of the norm
+        assert res["pretrain_ranks_identical_fp32"] and res["pretrain_ranks_identical_bf16"], res
+        assert res["vqa_dp_vs_single_gpu_fp32"] < 1e-4, res          # rows are batch independent: only fp32 summation order differs
+        assert res["vqa_dp_vs_single_gpu_bf16"] < 1e-2, res
+        for k in ("retrieval_embeddings_bit_identical", "retrieval_candidates_bit_identical",
+                  "retrieval_probs_bit_identical", "retrieval_ranks_identical"):
+            assert res[k], (k, res)

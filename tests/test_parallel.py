@@ -39,12 +39,21 @@ def _worker(rank, world, port, out):
     # bucketed all-reduce == mean of the replicas, whatever the bucket order / coverage
     arena = _FakeArena(1000, rank)
     expect = (_FakeArena(1000, 0).grad + _FakeArena(1000, 1).grad) / 2
-    sync = P.GradientSync(arena)
-    assert sync.enabled
+    sync = P.GradientSync(arena, min_bucket=0)
+    assert sync.enabled and sync.reduce_dtype == torch.float32  # CPU / gloo: fp32 in place
     sync.layer_done(600, 800)
+    sync.will_write(650, 700)  # second pass over a range already handed to the collective: must not deadlock
     sync.layer_done(100, 300)
     sync.finish()
     assert torch.allclose(arena.grad, expect, atol=1e-6)
+    # small ranges (per-layer bias slices) are deferred to finish() instead of being sent on their own
+    arena2 = _FakeArena(1000, rank)
+    sync2 = P.GradientSync(arena2, min_bucket=500)
+    sync2.layer_done(600, 800)
+    assert sync2.done == []
+    sync2.layer_done(0, 600)
+    sync2.finish()
+    assert torch.allclose(arena2.grad, expect, atol=1e-6)
     # sharded scoring: every rank scores its shard of the pairs, results gathered in pair order
     scores = torch.arange(23, dtype=torch.float32) * 0.5
     plo, phi = P.shard_range(23, rank, world)
