@@ -101,9 +101,9 @@ def test_reference_call_sequences_through_the_compat_imports():
         assert abs(got - ref) <= 1e-2 * abs(ref), (out["losses"], out["oracle_losses"])
     for gn, ref in out["grad_norm"]:  # torch.nn.utils.clip_grad_norm_ saw the arena's gradients
         assert abs(gn - ref) <= 2e-2 * ref
-    # Adam's first steps move every element by ~lr * sign(g): an element whose gradient is below the bf16 noise floor
-    # (|g| < ~1 % of the typical magnitude: ~0.8 % of a Gaussian-distributed gradient) moves in a random direction, an
-    # error of 2 lr on that element -> expected relative L2 error of the update vector ~ sqrt(0.008 * 4 / 2) = 0.13.
-    # The losses and gradient norms above are the tight (1e-2 / 2e-2) checks; the update is bounded at twice that.
-    assert out["param_update_rel_err"] < 0.25
+    # Adam moves every element by ~lr whatever the size of its gradient, so elements whose gradient is below the
+    # bf16 noise floor move in a noise-determined direction: the update vector is compared with the fp32 reference
+    # update like every other quantity -- within max(1e-2, 2 x what bf16 storage alone does to it on the same state)
+    for err_cuda, err_floor in out["param_update_err_vs_fp32_and_bf16_floor_per_step"]:
+        assert err_cuda <= max(1e-2, 2 * err_floor), out
     assert out["half_eval_sims_err"] < 3e-2 and out["half_eval_prob_err"] < 3e-2
