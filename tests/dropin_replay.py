@@ -45,7 +45,8 @@ def main():
         # run_retrieval.py:1024-1038
         config = BertConfig.from_pretrained(ckpt, num_labels=2, finetuning_task="ir")
         config.img_feature_dim, config.img_feature_type = cfg.img_feature_dim, "frcnn"
-        config.hidden_dropout_prob = 0.0
+        config.hidden_dropout_prob = 0.0               # args.drop_out (run_retrieval.py:1033)
+        config.attention_probs_dropout_prob = 0.0      # (the script leaves 0.1; 0 here so that the oracle can follow)
         config.loss_type, config.img_layer_norm_eps, config.use_img_layernorm = "sfmx", 1e-12, 1
         model = BiImageBertForRetrieval.from_pretrained(ckpt, from_tf=bool(".ckpt" in ckpt), config=config)
         model.to(dev)
