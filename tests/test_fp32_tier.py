@@ -226,27 +226,23 @@ def test_base_shape_fp32_forward_and_pretrain_step(golden_dir):
     for n, a, r in zip(LOSS_NAMES, losses, g["losses"]):
         check(f"pretrain_base loss {n}", a.detach(), r)
     params = dict(model.named_parameters())
+    # every one of the 314 gradient tensors against the fp32 oracle (== the reference: its losses / gradient norms /
+    # small tensors are the golden's, checked below)
+    _, g32 = oracle_pretrain(cfg, sd, b, Lt, bf16=False)
+    _check_grads("pretrain_base gradients", params, g32)
     top = max(g["grad_norms"].values())
-    worst, wk, bad = 0.0, "", []
+    worst, wk = 0.0, ""
     for k, n in g["grad_norms"].items():
-        got = float(params[k].grad.float().norm())
-        if n <= 1e-5 * top:
-            assert got <= 2e-5 * top, k
-            continue
+        if n <= 1e-5 * top or params[k].numel() > (1 << 22):
+            continue  # (the stored fp32 norm of the 66 M-element embedding gradient carries ~1e-4 of summation noise itself)
+        got = float(params[k].grad.double().norm())
         if abs(got - n) / n > worst:
             worst, wk = abs(got - n) / n, k
-        # 1e-4 relative, plus fp32 resolution of the gradient scale (1e-6 of the largest norm): the image LayerNorm
-        # weight's gradient cancels to 1/8 of its term-wise magnitude at random init (measured with the oracle), so
-        # fp32 summation-order noise shows ~8x magnified on that one small tensor
-        if abs(got - n) > TOL * n + 1e-6 * top:
-            bad.append((k, got, n))
-    _lines().append(f"[fp32 tier] pretrain_base: {len(g['grad_norms'])} gradient norms, worst relative error vs reference "
-                    f"{worst:.2e} ({wk}, norm {g['grad_norms'][wk]:.3e}; largest norm {top:.3e})")
-    assert not bad, bad
+    _lines().append(f"[fp32 tier] pretrain_base: gradient norms vs the reference's stored norms, worst relative error {worst:.2e} ({wk})")
+    assert worst <= TOL
     for k, gr in g["grads"].items():
         if float(gr.norm()) > 1e-5 * top:
-            err = float((params[k].grad.float().cpu() - gr.float()).norm())
-            assert err <= TOL * float(gr.norm()) + 1e-6 * top, (k, err, float(gr.norm()))
+            assert P.rel_l2(params[k].grad, gr) < TOL, k
 
 
 def test_retrieval_subset_ranking_order_fp32():
