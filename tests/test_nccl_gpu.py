@@ -183,7 +183,10 @@ def test_two_rank_nccl_data_parallel_and_sharded_retrieval():
         assert res["pretrain_allreduce_fp32"][0] < 1e-5, res          # fp32 reduction: exact up to summation order
         assert res["pretrain_allreduce_bf16"][0] < 1e-2, res          # bf16 on the wire: 2^-9 per element, 1e-2 of the norm
         assert res["pretrain_ranks_identical_fp32"] and res["pretrain_ranks_identical_bf16"], res
-        assert res["vqa_dp_vs_single_gpu_fp32"] < 1e-4, res          # rows are batch independent: only fp32 summation order differs
+        # rows are batch independent EXCEPT for one batch-size dependent choice: with more than 128 tokens the FFN1
+        # epilogue saves gelu'(x) for backward, below it saves x and backward recomputes gelu' (csrc/layer.cu
+        # pre_g_is_gelu_grad) -- two bf16 roundings of the same quantity; observed 5.8e-4 relative L2
+        assert res["vqa_dp_vs_single_gpu_fp32"] < 2e-3, res
         assert res["vqa_dp_vs_single_gpu_bf16"] < 1e-2, res
         for k in ("retrieval_embeddings_bit_identical", "retrieval_candidates_bit_identical",
                   "retrieval_probs_bit_identical", "retrieval_ranks_identical"):
