@@ -734,10 +734,18 @@ static int attn_check(int B, int L, int nh, int H, int ld_qkv, int ld_ctx) {
   return 0;
 }
 
+// tcgen05 / TMA / TMEM forward for L <= 128 (attention_tc.cu); returns 1 when it does not apply
+int mvptr_attn_fwd_tc(const void* qkv, int ld_qkv, const float* maskadd, void* ctx, int ld_ctx, float* lse, int B, int L,
+                      int nh, int H, float p_drop, uint32_t seed, cudaStream_t stream);
+
 extern "C" int mvptr_attn_fwd(const void* qkv, int ld_qkv, const float* maskadd, void* ctx, int ld_ctx, float* lse,
                               int B, int L, int nh, int H, float p_drop, uint32_t seed, void* stream) {
   MVPTR_PROF("attn_fwd", 4.0*B*nh*L*L*64, stream);
   if (int rc = attn_check(B, L, nh, H, ld_qkv, ld_ctx)) return rc;
+  {
+    const int rc = mvptr_attn_fwd_tc(qkv, ld_qkv, maskadd, ctx, ld_ctx, lse, B, L, nh, H, p_drop, seed, (cudaStream_t)stream);
+    if (rc <= 0) return rc;  // done (0) or failed (< 0); 1 = not applicable -> the mma.sync kernels below (L > 128)
+  }
   attn::FwdParams p{(const bf16*)qkv, ld_qkv, maskadd, (bf16*)ctx, ld_ctx, lse, B, L, nh, H, 0.125f,
                     keep_threshold(p_drop), p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f, seed};
   cudaStream_t s = (cudaStream_t)stream;

@@ -1,0 +1,437 @@
+// tcgen05 attention forward for L <= 128, head_dim 64 (modeling_vlbert.py:63-103 + transpose_for_scores
+// modeling_bert.py:299-303): the Blackwell-native replacement of the mma.sync kernel in attention.cu.
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0   TMA producer: Q, K, V tiles of one (batch, head) straight out of the fused QKV projection
+//            [B, L, 3H] through ONE 3-D tensor map (box 64 x 128 x 1, 128-byte swizzle); rows >= L are zero-filled
+//            by the TMA bounds check, so ragged L needs no padding pass.  3-stage ring (48 KB per stage).
+//   warp 1   MMA issuer: S = Q K^T (tcgen05.mma 128 x N16 x 16, 4 steps over d) into TMEM columns [0, 128);
+//            O = P V (128 x 64 x 16, N16 / 16 steps over the keys) into TMEM columns [128, 192).
+//   warp 2   TMEM allocator.
+//   warps 4-7  softmax + epilogue: thread = one query row = one TMEM lane.  Pass 1 reads the S row (tcgen05.ld) for the
+//            row maximum, pass 2 re-reads it (TMEM reads are cheap; a 128-wide row never lives in registers) for
+//            exp2 / row sum / dropout and writes P as bf16 into the K-major swizzled A-operand tile of the second
+//            MMA.  The epilogue reads O, applies 1 / sum (and the dropout rescale), and stores the head-merged
+//            context [B, L, H] by a 3-D TMA store whose bounds check clips the rows >= L.
+// S(i+1) is issued as soon as the softmax warps have consumed S(i), so the tensor work and the TMA latency hide
+// behind the softmax warps, which are the critical path (~1000 instructions per row).
+// Scores never touch HBM; lse [B, nh, L] is saved for the backward kernel; the dropout mask is the stateless hash of
+// common.cuh with the SAME element indexing as attention.cu, so its backward regenerates the mask bit for bit.
+#include <cudaTypedefs.h>
+
+#include <stdlib.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace mvptr {
+namespace attn_tc {
+
+constexpr int D = 64;
+constexpr int kRows = 128;           // MMA M: query rows (padded)
+constexpr int kTileBytes = kRows * 128;  // one [128][64] bf16 tile, 128-byte rows
+constexpr int kStages = 3;
+constexpr int kThreads = 256;
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct Params {
+  const float* maskadd;  // [B, L] additive mask (1 - mask) * -10000
+  float* lse;            // [B, nh, L] or null
+  int B, L, nh, H;
+  int n16;               // keys padded to a multiple of 16 (MMA N of S, K of PV)
+  int items;             // B * nh
+  float scale_log2;      // 1/sqrt(64) * log2(e)
+  uint32_t keep_thr;
+  float inv_keep;
+  uint32_t seed;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_softmax() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, SWIZZLE_128B (same bit layout as gemm_tcgen05.cu)
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t make_idesc(int m, int n, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+constexpr int kSmemStage = 3 * kTileBytes;                       // Q | K | V
+constexpr int kSmemP = 2 * kTileBytes;                           // two 64-key blocks of the A operand
+constexpr int kSmemTotal = kStages * kSmemStage + kSmemP + kTileBytes /* O staging */ + 2 * kRows * 4 /* mask x2 */ + 256 + 1024;
+
+__global__ void __launch_bounds__(kThreads, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sP = smem + kStages * kSmemStage;
+  uint8_t* sO = sP + kSmemP;
+  float* sMask = reinterpret_cast<float*>(sO + kTileBytes);  // [2][128], log2 domain
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + 2 * kRows);
+  const uint32_t full_bar = smem_u32(bars);              // [kStages] TMA -> MMA
+  const uint32_t empty_bar = smem_u32(bars + kStages);   // [kStages] PV retired -> TMA
+  const uint32_t sfull_bar = smem_u32(bars + 2 * kStages);      // S in TMEM -> softmax warps
+  const uint32_t pfull_bar = smem_u32(bars + 2 * kStages + 1);  // P in smem (and S consumed) -> MMA
+  const uint32_t ofull_bar = smem_u32(bars + 2 * kStages + 2);  // O in TMEM -> softmax warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKV) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(full_bar + 8 * i, 1);
+      mbar_init(empty_bar + 8 * i, 1);
+    }
+    mbar_init(sfull_bar, 1);
+    mbar_init(pfull_bar, 4);
+    mbar_init(ofull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+  const int H = p.H;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+        const int b = it / p.nh, h = it - b * p.nh;
+        mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+        const uint32_t sq = smem_u32(smem + stage * kSmemStage);
+        const uint32_t fb = full_bar + 8 * stage;
+        mbar_expect_tx(fb, 3 * kTileBytes);
+        tma_load_3d(sq, &tmQKV, fb, h * D, 0, b);
+        tma_load_3d(sq + kTileBytes, &tmQKV, fb, H + h * D, 0, b);
+        tma_load_3d(sq + 2 * kTileBytes, &tmQKV, fb, 2 * H + h * D, 0, b);
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc(kRows, p.n16, false);  // S[128, n16] = Q . K^T, both K-major
+      const uint32_t idesc_o = make_idesc(kRows, D, true);       // O[128, 64] = P . V, V is MN-major ([key][d])
+      const int ksteps = p.n16 >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      auto issue_s = [&](int st) {
+        const uint32_t sq = smem_u32(smem + st * kSmemStage), sk = sq + kTileBytes;
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          tc_mma(tmem_S, make_desc(sq + k * 32, 16, 1024), make_desc(sk + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        tc_commit(sfull_bar);
+      };
+      const bool any = (int)blockIdx.x < p.items;
+      if (any) {
+        mbar_wait(full_bar, 0);
+        tc_fence_after();
+        issue_s(0);
+      }
+      for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++local) {
+        // P(it) is in shared memory and S(it) has been read out of TMEM
+        mbar_wait(pfull_bar, local & 1);
+        tc_fence_after();
+        const uint32_t sv = smem_u32(smem + stage * kSmemStage) + 2 * kTileBytes;
+        const uint32_t sp = smem_u32(sP);
+        for (int k = 0; k < ksteps; ++k)
+          tc_mma(tmem_O, make_desc(sp + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
+                 make_desc(sv + k * 2048, 64 * 128, 1024), idesc_o, k > 0 ? 1u : 0u);
+        tc_commit(ofull_bar);
+        tc_commit(empty_bar + 8 * stage);  // Q, K, V of this stage are dead once PV retires
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+        if (it + (int)gridDim.x < p.items) {  // S of the next item: overlaps this item's epilogue
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          issue_s(stage);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================= softmax + epilogue: thread = query row = TMEM lane =======================
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;                 // query index inside the head
+    const int tid = threadIdx.x - 128;              // 0..127
+    const int L = p.L;
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    const uint32_t dseed = site_seed(p.seed);
+    const bool drop = p.keep_thr != 0xffffffffu;
+    const uint32_t Lp = (uint32_t)(L + 1) & ~1u;    // even row pitch of the dropout index (as attention.cu)
+    const int nchunk = (p.n16 + 31) >> 5;           // 32-column TMEM loads per row
+    int local = 0;
+    bool store_pending = false;
+    // the mask row of the next item is fetched one item ahead (all heads of a batch element share it)
+    float next_mask = 0.f;
+    {
+      const int it0 = blockIdx.x;
+      if (it0 < p.items) next_mask = tid < L ? p.maskadd[(size_t)(it0 / p.nh) * L + tid] * kLog2e : -INFINITY;
+    }
+    for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++local) {
+      const int b = it / p.nh, h = it - b * p.nh;
+      float* mk = sMask + (local & 1) * kRows;
+      mk[tid] = next_mask;
+      {
+        const int itn = it + gridDim.x;
+        if (itn < p.items) next_mask = tid < L ? p.maskadd[(size_t)(itn / p.nh) * L + tid] * kLog2e : -INFINITY;
+      }
+      bar_sync_softmax();  // mask row visible to the 128 softmax threads
+      mbar_wait(sfull_bar, local & 1);
+      tc_fence_after();
+      // ---- pass 1: row maximum of (s * scale + mask) in the log2 domain
+      float mx = -INFINITY;
+      uint32_t r[32];
+      for (int c = 0; c < nchunk; ++c) {
+        tc_ld32(tmem_S + lane_off + c * 32, r);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaf(__uint_as_float(r[j]), p.scale_log2, mk[c * 32 + j]));
+      }
+      // (columns >= n16 of the last chunk hold stale TMEM data; their mask is -inf, and fmaf(x, s, -inf) = -inf
+      //  for every finite x -- stale NaN / Inf bit patterns are excluded by clamping below)
+      // ---- pass 2: p = exp2(s - mx), row sum, dropout, P as bf16 into the swizzled A tile of the second MMA
+      float sum = 0.f;
+      const uint32_t rbase = (((uint32_t)b * p.nh + h) * L + row) * Lp;
+      uint8_t* prow = sP + (row >> 3) * 1024 + (row & 7) * 128;
+      for (int c = 0; c < nchunk; ++c) {
+        tc_ld32(tmem_S + lane_off + c * 32, r);
+        tc_wait_ld();
+        float e[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float m = mk[c * 32 + j];
+          const float s = m == -INFINITY ? -INFINITY : fmaf(__uint_as_float(r[j]), p.scale_log2, m);
+          e[j] = ex2_approx(s - mx);
+          sum += e[j];
+        }
+        if (drop) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            bool k0, k1;
+            dropout_pair(dseed, rbase + c * 32 + j, p.keep_thr, k0, k1);
+            e[j] = k0 ? e[j] : 0.f;
+            e[j + 1] = k1 ? e[j + 1] : 0.f;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int chunk = c * 4 + u;  // 16-byte unit = 8 keys
+          if (chunk * 8 < p.n16) {
+            uint4 v;
+            v.x = pack2(e[u * 8 + 0], e[u * 8 + 1]);
+            v.y = pack2(e[u * 8 + 2], e[u * 8 + 3]);
+            v.z = pack2(e[u * 8 + 4], e[u * 8 + 5]);
+            v.w = pack2(e[u * 8 + 6], e[u * 8 + 7]);
+            *reinterpret_cast<uint4*>(prow + (chunk >> 3) * kTileBytes + (((chunk & 7) ^ (row & 7)) << 4)) = v;
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pfull_bar);
+      if (p.lse && row < L) p.lse[((size_t)b * p.nh + h) * L + row] = (mx + log2f(sum)) * (1.0f / kLog2e);
+      const float inv = p.inv_keep / sum;
+      // ---- epilogue: O row * inv -> bf16 -> swizzled staging tile -> 3-D TMA store (rows >= L clipped)
+      mbar_wait(ofull_bar, local & 1);
+      tc_fence_after();
+      if (store_pending) {  // the previous item's store has finished reading the staging tile
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        bar_sync_softmax();
+        store_pending = false;
+      }
+      uint8_t* orow = sO + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        tc_ld32(tmem_O + lane_off + c * 32, r);
+        tc_wait_ld();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 v;
+          v.x = pack2(__uint_as_float(r[u * 8 + 0]) * inv, __uint_as_float(r[u * 8 + 1]) * inv);
+          v.y = pack2(__uint_as_float(r[u * 8 + 2]) * inv, __uint_as_float(r[u * 8 + 3]) * inv);
+          v.z = pack2(__uint_as_float(r[u * 8 + 4]) * inv, __uint_as_float(r[u * 8 + 5]) * inv);
+          v.w = pack2(__uint_as_float(r[u * 8 + 6]) * inv, __uint_as_float(r[u * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + (((c * 4 + u) ^ (row & 7)) << 4)) = v;
+        }
+      }
+      tc_fence_before();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      bar_sync_softmax();
+      if (tid == 0) {
+        tma_store_3d(&tmO, smem_u32(sO), h * D, 0, b);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      store_pending = true;
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  });
+  return fn;
+}
+
+// [B, L, cols] bf16 view (row pitch ld elements) with box 64 x 128 x 1: rows >= L are out of bounds -> zero-filled
+// on load, clipped on store
+static int make_map3(CUtensorMap* map, const void* base, int cols, int L, int B, int ld) {
+  auto enc = get_encode();
+  if (!enc) MVPTR_FAIL(MVPTR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)L, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)L * ld * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)kRows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) MVPTR_FAIL(MVPTR_ERR_CUDA, "attention tensor map (cols %d, L %d, B %d, ld %d): error %d", cols, L, B, ld, (int)r);
+  return 0;
+}
+
+}  // namespace attn_tc
+}  // namespace mvptr
+
+// Returns 1 when this path does not apply (the caller falls back to the mma.sync kernel), 0 on success, < 0 on error.
+int mvptr_attn_fwd_tc(const void* qkv, int ld_qkv, const float* maskadd, void* ctx, int ld_ctx, float* lse, int B, int L,
+                      int nh, int H, float p_drop, uint32_t seed, cudaStream_t stream) {
+  using namespace mvptr;
+  using namespace mvptr::attn_tc;
+  static const bool enabled = !(getenv("MVPTR_ATTN_TC") && atoi(getenv("MVPTR_ATTN_TC")) == 0);
+  if (!enabled || L > kRows || (reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(ctx) & 15)) return 1;
+  CUtensorMap tq, to;
+  if (int rc = make_map3(&tq, qkv, 3 * H, L, B, ld_qkv)) return rc;
+  if (int rc = make_map3(&to, ctx, H, L, B, ld_ctx)) return rc;
+  Params p;
+  p.maskadd = maskadd;
+  p.lse = lse;
+  p.B = B; p.L = L; p.nh = nh; p.H = H;
+  p.n16 = (L + 15) & ~15;
+  p.items = B * nh;
+  p.scale_log2 = 0.125f * kLog2e;
+  p.keep_thr = keep_threshold(p_drop);
+  p.inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  p.seed = seed;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    if (e != cudaSuccess) MVPTR_FAIL(MVPTR_ERR_CUDA, "attention (tcgen05) smem attr: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int grid = p.items < kNumSMs ? p.items : kNumSMs;
+  attn_fwd_tc_kernel<<<grid, kThreads, kSmemTotal, stream>>>(tq, to, p);
+  MVPTR_CHECK_LAUNCH("attn_fwd_tc");
+  return 0;
+}

@@ -87,7 +87,10 @@ class GradientSync:
         self.reduce_dtype = reduce_dtype
         self.min_bucket = int(min_bucket)
         self.staging = None  # bf16 arena-shaped staging buffer, allocated on first use
-        self.cast_ctas = 32  # grid cap of the cast kernels that share the SMs with the backward GEMMs
+        # grid cap of the widening cast (0 = none).  A narrow grid looked polite but is not: capped at 32 CTAs each
+        # cast took 0.21 ms (20 per step = 4.2 ms of comm-stream time next to the backward GEMMs, which ran 4-10 %
+        # slower under it; profiles/r2_dp_trace_n2_capped_casts.txt) -- at full width it is a 20 us kernel
+        self.cast_ctas = int(__import__("os").environ.get("MVPTR_DP_CAST_CTAS", "0"))
 
     def _reduce(self, lo, hi):
         g = self.arena.grad[lo:hi]
