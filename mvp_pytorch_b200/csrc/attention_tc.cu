@@ -5,16 +5,19 @@
 //   warp 0   TMA producer: Q, K, V tiles of one (batch, head) straight out of the fused QKV projection
 //            [B, L, 3H] through ONE 3-D tensor map (box 64 x 128 x 1, 128-byte swizzle); rows >= L are zero-filled
 //            by the TMA bounds check, so ragged L needs no padding pass.  3-stage ring (48 KB per stage).
-//   warp 1   MMA issuer: S = Q K^T (tcgen05.mma 128 x N16 x 16, 4 steps over d) into TMEM columns [0, 128);
-//            O = P V (128 x 64 x 16, N16 / 16 steps over the keys) into TMEM columns [128, 192).
+//   warp 1   MMA issuer: S = Q K^T (tcgen05.mma 128 x N16 x 16, 4 steps over d) and O = P V (128 x 64 x 16,
+//            N16 / 16 steps over the keys), accumulators in TMEM (512 columns: two groups x {S 128, O 64}).
 //   warp 2   TMEM allocator.
-//   warps 4-7  softmax + epilogue: thread = one query row = one TMEM lane.  Pass 1 reads the S row (tcgen05.ld) for the
-//            row maximum, pass 2 re-reads it (TMEM reads are cheap; a 128-wide row never lives in registers) for
-//            exp2 / row sum / dropout and writes P as bf16 into the K-major swizzled A-operand tile of the second
-//            MMA.  The epilogue reads O, applies 1 / sum (and the dropout rescale), and stores the head-merged
-//            context [B, L, H] by a 3-D TMA store whose bounds check clips the rows >= L.
-// S(i+1) is issued as soon as the softmax warps have consumed S(i), so the tensor work and the TMA latency hide
-// behind the softmax warps, which are the critical path (~1000 instructions per row).
+//   warps 4-7, 8-11  two softmax + epilogue warpgroups, each owning every other item (its own S / O columns in TMEM and
+//            its own P tile), thread = one query row = one TMEM lane.  The score row is fetched by back-to-back
+//            tcgen05.ld and one wait, stays in registers from the row maximum to exp2 / row sum / dropout, and goes
+//            as bf16 into the K-major swizzled A-operand tile of the second MMA.  The epilogue reads O, applies
+//            1 / sum (and the dropout rescale), and stores the head-merged context [B, L, H] by a 3-D TMA store
+//            (staged in the item's dead Q tile) whose bounds check clips the rows >= L.
+// The first version had ONE softmax warpgroup and a two-pass row: correct, but the serial chain per item (8 TMEM
+// round trips, the PV latency, two barriers) made it latency bound at ~2.6 us per head -- slower than the mma.sync
+// kernel (profiles/r2_attention_tc.txt).  Two groups overlap each other's latencies; S(n + 2) is issued as soon as
+// group n & 1 has consumed S(n), so tensor work and TMA latency hide behind the softmax warps.
 // Scores never touch HBM; lse [B, nh, L] is saved for the backward kernel; the dropout mask is the stateless hash of
 // common.cuh with the SAME element indexing as attention.cu, so its backward regenerates the mask bit for bit.
 #include <cudaTypedefs.h>
@@ -32,7 +35,7 @@ constexpr int D = 64;
 constexpr int kRows = 128;           // MMA M: query rows (padded)
 constexpr int kTileBytes = kRows * 128;  // one [128][64] bf16 tile, 128-byte rows
 constexpr int kStages = 3;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct Params {
@@ -119,7 +122,6 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void bar_sync_softmax() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, SWIZZLE_128B (same bit layout as gemm_tcgen05.cu)
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -135,24 +137,82 @@ __device__ __forceinline__ uint32_t make_idesc(int m, int n, bool b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-constexpr int kSmemStage = 3 * kTileBytes;                       // Q | K | V
-constexpr int kSmemP = 2 * kTileBytes;                           // two 64-key blocks of the A operand
-constexpr int kSmemTotal = kStages * kSmemStage + kSmemP + kTileBytes /* O staging */ + 2 * kRows * 4 /* mask x2 */ + 256 + 1024;
+constexpr int kGroups = 2;                                      // softmax warpgroups, each owns every other item
+constexpr int kSmemStage = 3 * kTileBytes;                       // Q | K | V  (the Q tile doubles as the O staging tile)
+constexpr int kSmemP = 2 * kTileBytes;                           // two 64-key blocks of the A operand, per group
+constexpr int kSmemTotal = kStages * kSmemStage + kGroups * kSmemP + kGroups * kRows * 4 /* mask */ + 256 + 1024;
+
+// One softmax warpgroup's work on one item.  NCH = 32-column chunks of the score row (n16 <= 32 NCH): the whole row
+// is fetched from TMEM by NCH back-to-back tcgen05.ld and ONE wait, and lives in registers from the row maximum to
+// the packed bf16 probabilities -- a single pass, no second TMEM read.
+template <int NCH>
+__device__ __forceinline__ void softmax_row(const Params& p, uint32_t tmem_row, const float* mk, int row, uint32_t rbase,
+                                            uint32_t dseed, bool drop, uint8_t* sPg, float& mx_out, float& sum_out) {
+  uint32_t r[NCH][32];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) tc_ld32(tmem_row + c * 32, r[c]);
+  tc_wait_ld();
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      // columns >= L: mask -inf (zero-filled K rows give finite scores; columns >= n16 hold stale TMEM bits, which
+      // the select keeps out of the arithmetic)
+      const float m = mk[c * 32 + j];
+      const float v = m == -INFINITY ? -INFINITY : fmaf(__uint_as_float(r[c][j]), p.scale_log2, m);
+      r[c][j] = __float_as_uint(v);
+      mx = fmaxf(mx, v);
+    }
+  float sum = 0.f;
+  uint8_t* prow = sPg + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    float e[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      e[j] = ex2_approx(__uint_as_float(r[c][j]) - mx);
+      sum += e[j];
+    }
+    if (drop) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        bool k0, k1;
+        dropout_pair(dseed, rbase + c * 32 + j, p.keep_thr, k0, k1);
+        e[j] = k0 ? e[j] : 0.f;
+        e[j + 1] = k1 ? e[j + 1] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int chunk = c * 4 + u;  // 16-byte unit = 8 keys
+      if (chunk * 8 < p.n16) {
+        uint4 v;
+        v.x = pack2(e[u * 8 + 0], e[u * 8 + 1]);
+        v.y = pack2(e[u * 8 + 2], e[u * 8 + 3]);
+        v.z = pack2(e[u * 8 + 4], e[u * 8 + 5]);
+        v.w = pack2(e[u * 8 + 6], e[u * 8 + 7]);
+        *reinterpret_cast<uint4*>(prow + (chunk >> 3) * kTileBytes + (((chunk & 7) ^ (row & 7)) << 4)) = v;
+      }
+    }
+  }
+  mx_out = mx;
+  sum_out = sum;
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sP = smem + kStages * kSmemStage;
-  uint8_t* sO = sP + kSmemP;
-  float* sMask = reinterpret_cast<float*>(sO + kTileBytes);  // [2][128], log2 domain
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + 2 * kRows);
-  const uint32_t full_bar = smem_u32(bars);              // [kStages] TMA -> MMA
-  const uint32_t empty_bar = smem_u32(bars + kStages);   // [kStages] PV retired -> TMA
-  const uint32_t sfull_bar = smem_u32(bars + 2 * kStages);      // S in TMEM -> softmax warps
-  const uint32_t pfull_bar = smem_u32(bars + 2 * kStages + 1);  // P in smem (and S consumed) -> MMA
-  const uint32_t ofull_bar = smem_u32(bars + 2 * kStages + 2);  // O in TMEM -> softmax warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 3);
+  uint8_t* sP = smem + kStages * kSmemStage;                                   // [kGroups][2 blocks][16 KB]
+  float* sMask = reinterpret_cast<float*>(sP + kGroups * kSmemP);             // [kGroups][128], log2 domain
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + kGroups * kRows);
+  const uint32_t full_bar = smem_u32(bars);                      // [kStages] TMA -> MMA
+  const uint32_t empty_bar = smem_u32(bars + kStages);           // [kStages] context stored -> TMA
+  const uint32_t sfull_bar = smem_u32(bars + 2 * kStages);       // [kGroups] S in TMEM -> softmax group
+  const uint32_t pfull_bar = smem_u32(bars + 2 * kStages + 2);   // [kGroups] P in smem (and S consumed) -> MMA
+  const uint32_t ofull_bar = smem_u32(bars + 2 * kStages + 4);   // [kGroups] O in TMEM -> softmax group
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -164,29 +224,32 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       mbar_init(full_bar + 8 * i, 1);
       mbar_init(empty_bar + 8 * i, 1);
     }
-    mbar_init(sfull_bar, 1);
-    mbar_init(pfull_bar, 4);
-    mbar_init(ofull_bar, 1);
+    for (int g = 0; g < kGroups; ++g) {
+      mbar_init(sfull_bar + 8 * g, 1);
+      mbar_init(pfull_bar + 8 * g, 4);
+      mbar_init(ofull_bar + 8 * g, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+  const uint32_t tmem_base = *tmem_slot;  // group g: S at columns [256 g, 256 g + 128), O at [256 g + 128, 256 g + 192)
   const int H = p.H;
+  const int n_local = p.items > (int)blockIdx.x ? (p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (warp == 0) {
     // ======================= TMA producer =======================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+      for (int n = 0; n < n_local; ++n) {
+        const int it = blockIdx.x + n * gridDim.x;
         const int b = it / p.nh, h = it - b * p.nh;
         mbar_wait(empty_bar + 8 * stage, phase ^ 1);
         const uint32_t sq = smem_u32(smem + stage * kSmemStage);
@@ -207,159 +270,134 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       const uint32_t idesc_s = make_idesc(kRows, p.n16, false);  // S[128, n16] = Q . K^T, both K-major
       const uint32_t idesc_o = make_idesc(kRows, D, true);       // O[128, 64] = P . V, V is MN-major ([key][d])
       const int ksteps = p.n16 >> 4;
-      int stage = 0;
-      uint32_t phase = 0;
-      int local = 0;
-      auto issue_s = [&](int st) {
-        const uint32_t sq = smem_u32(smem + st * kSmemStage), sk = sq + kTileBytes;
-#pragma unroll
-        for (int k = 0; k < D / 16; ++k)
-          tc_mma(tmem_S, make_desc(sq + k * 32, 16, 1024), make_desc(sk + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-        tc_commit(sfull_bar);
+      auto try_wait = [](uint32_t bar, uint32_t parity) -> bool {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        return ok != 0;
       };
-      const bool any = (int)blockIdx.x < p.items;
-      if (any) {
-        mbar_wait(full_bar, 0);
-        tc_fence_after();
-        issue_s(0);
-      }
-      for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++local) {
-        // P(it) is in shared memory and S(it) has been read out of TMEM
-        mbar_wait(pfull_bar, local & 1);
-        tc_fence_after();
-        const uint32_t sv = smem_u32(smem + stage * kSmemStage) + 2 * kTileBytes;
-        const uint32_t sp = smem_u32(sP);
-        for (int k = 0; k < ksteps; ++k)
-          tc_mma(tmem_O, make_desc(sp + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
-                 make_desc(sv + k * 2048, 64 * 128, 1024), idesc_o, k > 0 ? 1u : 0u);
-        tc_commit(ofull_bar);
-        tc_commit(empty_bar + 8 * stage);  // Q, K, V of this stage are dead once PV retires
-        if (++stage == kStages) {
-          stage = 0;
-          phase ^= 1;
+      // Two independent event streams feed this thread -- "Q, K of item s have landed" (-> issue S(s)) and "group
+      // n & 1 has written P(n)" (-> issue O(n) = P V) -- and neither may wait behind the other: it polls both.
+      // S(s) may overwrite its group's score columns once P(s - 2) has been taken, i.e. s < next_pv + kGroups.
+      int next_s = 0, next_pv = 0;
+      while (next_pv < n_local) {
+        if (next_s < n_local && next_s < next_pv + kGroups) {
+          const int st = next_s % kStages, g = next_s & 1;
+          if (try_wait(full_bar + 8 * st, (uint32_t)(next_s / kStages) & 1u)) {
+            tc_fence_after();
+            const uint32_t sq = smem_u32(smem + st * kSmemStage), sk = sq + kTileBytes;
+#pragma unroll
+            for (int k = 0; k < D / 16; ++k)
+              tc_mma(tmem_base + g * 256, make_desc(sq + k * 32, 16, 1024), make_desc(sk + k * 32, 16, 1024), idesc_s,
+                     k > 0 ? 1u : 0u);
+            tc_commit(sfull_bar + 8 * g);
+            ++next_s;
+          }
         }
-        if (it + (int)gridDim.x < p.items) {  // S of the next item: overlaps this item's epilogue
-          mbar_wait(full_bar + 8 * stage, phase);
-          tc_fence_after();
-          issue_s(stage);
+        if (next_pv < next_s) {
+          const int st = next_pv % kStages, g = next_pv & 1;
+          if (try_wait(pfull_bar + 8 * g, (uint32_t)(next_pv >> 1) & 1u)) {  // P in smem, S read out of TMEM
+            tc_fence_after();
+            const uint32_t sv = smem_u32(smem + st * kSmemStage) + 2 * kTileBytes;
+            const uint32_t sp = smem_u32(sP + g * kSmemP);
+            for (int k = 0; k < ksteps; ++k)
+              tc_mma(tmem_base + g * 256 + 128, make_desc(sp + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
+                     make_desc(sv + k * 2048, 64 * 128, 1024), idesc_o, k > 0 ? 1u : 0u);
+            tc_commit(ofull_bar + 8 * g);
+            ++next_pv;
+          }
         }
       }
     }
   } else if (warp >= 4) {
     // ======================= softmax + epilogue: thread = query row = TMEM lane =======================
+    const int g = (warp - 4) >> 2;                  // warpgroup: items n with n & 1 == g
     const int q4 = warp & 3;
     const int row = q4 * 32 + lane;                 // query index inside the head
-    const int tid = threadIdx.x - 128;              // 0..127
+    const int tid = (threadIdx.x - 128) & 127;      // 0..127 inside the group
     const int L = p.L;
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    const uint32_t tmem_S = tmem_base + g * 256 + lane_off, tmem_O = tmem_S + 128;
     const uint32_t dseed = site_seed(p.seed);
     const bool drop = p.keep_thr != 0xffffffffu;
     const uint32_t Lp = (uint32_t)(L + 1) & ~1u;    // even row pitch of the dropout index (as attention.cu)
-    const int nchunk = (p.n16 + 31) >> 5;           // 32-column TMEM loads per row
-    int local = 0;
-    bool store_pending = false;
+    const int nch = (p.n16 + 31) >> 5;
+    uint8_t* sPg = sP + g * kSmemP;
+    float* mk = sMask + g * kRows;
+    auto group_sync = [&]() {
+      if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+    };
     // the mask row of the next item is fetched one item ahead (all heads of a batch element share it)
     float next_mask = 0.f;
-    {
-      const int it0 = blockIdx.x;
-      if (it0 < p.items) next_mask = tid < L ? p.maskadd[(size_t)(it0 / p.nh) * L + tid] * kLog2e : -INFINITY;
+    if (g < n_local) {
+      const int it0 = blockIdx.x + g * gridDim.x;
+      next_mask = tid < L ? p.maskadd[(size_t)(it0 / p.nh) * L + tid] * kLog2e : -INFINITY;
     }
-    for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++local) {
+    int m = 0;  // items this group has processed
+    for (int n = g; n < n_local; n += kGroups, ++m) {
+      const int it = blockIdx.x + n * gridDim.x;
       const int b = it / p.nh, h = it - b * p.nh;
-      float* mk = sMask + (local & 1) * kRows;
-      mk[tid] = next_mask;
-      {
-        const int itn = it + gridDim.x;
-        if (itn < p.items) next_mask = tid < L ? p.maskadd[(size_t)(itn / p.nh) * L + tid] * kLog2e : -INFINITY;
+      const int st = n % kStages;
+      mk[tid] = next_mask;  // (the previous item's rows were consumed before its epilogue barrier)
+      if (n + kGroups < n_local) {
+        const int itn = it + kGroups * gridDim.x;
+        next_mask = tid < L ? p.maskadd[(size_t)(itn / p.nh) * L + tid] * kLog2e : -INFINITY;
       }
-      bar_sync_softmax();  // mask row visible to the 128 softmax threads
-      mbar_wait(sfull_bar, local & 1);
+      group_sync();  // mask row visible to the 128 threads of the group
+      mbar_wait(sfull_bar + 8 * g, (uint32_t)m & 1u);
       tc_fence_after();
-      // ---- pass 1: row maximum of (s * scale + mask) in the log2 domain
-      float mx = -INFINITY;
-      uint32_t r[32];
-      for (int c = 0; c < nchunk; ++c) {
-        tc_ld32(tmem_S + lane_off + c * 32, r);
-        tc_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaf(__uint_as_float(r[j]), p.scale_log2, mk[c * 32 + j]));
-      }
-      // (columns >= n16 of the last chunk hold stale TMEM data; their mask is -inf, and fmaf(x, s, -inf) = -inf
-      //  for every finite x -- stale NaN / Inf bit patterns are excluded by clamping below)
-      // ---- pass 2: p = exp2(s - mx), row sum, dropout, P as bf16 into the swizzled A tile of the second MMA
-      float sum = 0.f;
       const uint32_t rbase = (((uint32_t)b * p.nh + h) * L + row) * Lp;
-      uint8_t* prow = sP + (row >> 3) * 1024 + (row & 7) * 128;
-      for (int c = 0; c < nchunk; ++c) {
-        tc_ld32(tmem_S + lane_off + c * 32, r);
-        tc_wait_ld();
-        float e[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float m = mk[c * 32 + j];
-          const float s = m == -INFINITY ? -INFINITY : fmaf(__uint_as_float(r[j]), p.scale_log2, m);
-          e[j] = ex2_approx(s - mx);
-          sum += e[j];
-        }
-        if (drop) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            bool k0, k1;
-            dropout_pair(dseed, rbase + c * 32 + j, p.keep_thr, k0, k1);
-            e[j] = k0 ? e[j] : 0.f;
-            e[j + 1] = k1 ? e[j + 1] : 0.f;
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int chunk = c * 4 + u;  // 16-byte unit = 8 keys
-          if (chunk * 8 < p.n16) {
-            uint4 v;
-            v.x = pack2(e[u * 8 + 0], e[u * 8 + 1]);
-            v.y = pack2(e[u * 8 + 2], e[u * 8 + 3]);
-            v.z = pack2(e[u * 8 + 4], e[u * 8 + 5]);
-            v.w = pack2(e[u * 8 + 6], e[u * 8 + 7]);
-            *reinterpret_cast<uint4*>(prow + (chunk >> 3) * kTileBytes + (((chunk & 7) ^ (row & 7)) << 4)) = v;
-          }
-        }
+      float mx, sum;
+      switch (nch) {
+        case 1: softmax_row<1>(p, tmem_S, mk, row, rbase, dseed, drop, sPg, mx, sum); break;
+        case 2: softmax_row<2>(p, tmem_S, mk, row, rbase, dseed, drop, sPg, mx, sum); break;
+        case 3: softmax_row<3>(p, tmem_S, mk, row, rbase, dseed, drop, sPg, mx, sum); break;
+        default: softmax_row<4>(p, tmem_S, mk, row, rbase, dseed, drop, sPg, mx, sum); break;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P visible to the tensor core (async proxy)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(pfull_bar);
+      if (lane == 0) mbar_arrive(pfull_bar + 8 * g);
       if (p.lse && row < L) p.lse[((size_t)b * p.nh + h) * L + row] = (mx + log2f(sum)) * (1.0f / kLog2e);
       const float inv = p.inv_keep / sum;
-      // ---- epilogue: O row * inv -> bf16 -> swizzled staging tile -> 3-D TMA store (rows >= L clipped)
-      mbar_wait(ofull_bar, local & 1);
+      // ---- epilogue: O row * inv -> bf16 -> the (dead) Q tile of this item's stage, swizzled -> 3-D TMA store
+      //      (rows >= L clipped); the stage goes back to the producer once the store has read it
+      mbar_wait(ofull_bar + 8 * g, (uint32_t)m & 1u);
       tc_fence_after();
-      if (store_pending) {  // the previous item's store has finished reading the staging tile
-        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        bar_sync_softmax();
-        store_pending = false;
-      }
+      uint8_t* sO = smem + st * kSmemStage;
       uint8_t* orow = sO + (row >> 3) * 1024 + (row & 7) * 128;
+      uint32_t r[2][32];
+      tc_ld32(tmem_O, r[0]);
+      tc_ld32(tmem_O + 32, r[1]);
+      tc_wait_ld();
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        tc_ld32(tmem_O + lane_off + c * 32, r);
-        tc_wait_ld();
+      for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           uint4 v;
-          v.x = pack2(__uint_as_float(r[u * 8 + 0]) * inv, __uint_as_float(r[u * 8 + 1]) * inv);
-          v.y = pack2(__uint_as_float(r[u * 8 + 2]) * inv, __uint_as_float(r[u * 8 + 3]) * inv);
-          v.z = pack2(__uint_as_float(r[u * 8 + 4]) * inv, __uint_as_float(r[u * 8 + 5]) * inv);
-          v.w = pack2(__uint_as_float(r[u * 8 + 6]) * inv, __uint_as_float(r[u * 8 + 7]) * inv);
+          v.x = pack2(__uint_as_float(r[c][u * 8 + 0]) * inv, __uint_as_float(r[c][u * 8 + 1]) * inv);
+          v.y = pack2(__uint_as_float(r[c][u * 8 + 2]) * inv, __uint_as_float(r[c][u * 8 + 3]) * inv);
+          v.z = pack2(__uint_as_float(r[c][u * 8 + 4]) * inv, __uint_as_float(r[c][u * 8 + 5]) * inv);
+          v.w = pack2(__uint_as_float(r[c][u * 8 + 6]) * inv, __uint_as_float(r[c][u * 8 + 7]) * inv);
           *reinterpret_cast<uint4*>(orow + (((c * 4 + u) ^ (row & 7)) << 4)) = v;
         }
-      }
       tc_fence_before();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      bar_sync_softmax();
+      group_sync();
       if (tid == 0) {
         tma_store_3d(&tmO, smem_u32(sO), h * D, 0, b);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(empty_bar + 8 * st);  // Q, K, V (PV has retired) and the staging tile are free
       }
-      store_pending = true;
     }
     if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -368,7 +406,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
