@@ -738,6 +738,10 @@ static int attn_check(int B, int L, int nh, int H, int ld_qkv, int ld_ctx) {
 int mvptr_attn_fwd_tc(const void* qkv, int ld_qkv, const float* maskadd, void* ctx, int ld_ctx, float* lse, int B, int L,
                       int nh, int H, float p_drop, uint32_t seed, cudaStream_t stream);
 
+int mvptr_attn_bwd_tc(const void* qkv, int ld_qkv, const float* maskadd, const void* dctx, int ld_ctx, const float* lse,
+                      void* dqkv, float* dbias, int B, int L, int nh, int H, float p_drop, uint32_t seed,
+                      cudaStream_t stream);
+
 extern "C" int mvptr_attn_fwd(const void* qkv, int ld_qkv, const float* maskadd, void* ctx, int ld_ctx, float* lse,
                               int B, int L, int nh, int H, float p_drop, uint32_t seed, void* stream) {
   MVPTR_PROF("attn_fwd", 4.0*B*nh*L*L*64, stream);
@@ -769,6 +773,11 @@ extern "C" int mvptr_attn_bwd(const void* qkv, int ld_qkv, const float* maskadd,
                               float p_drop, uint32_t seed, void* stream) {
   MVPTR_PROF("attn_bwd", 10.0*B*nh*L*L*64, stream);
   if (int rc = attn_check(B, L, nh, H, ld_qkv, ld_ctx)) return rc;
+  {
+    const int rc = mvptr_attn_bwd_tc(qkv, ld_qkv, maskadd, dctx, ld_ctx, lse, dqkv, dbias, B, L, nh, H, p_drop, seed,
+                                     (cudaStream_t)stream);
+    if (rc <= 0) return rc;
+  }
   attn::BwdParams p{(const bf16*)qkv, ld_qkv, maskadd, (const bf16*)ctx, (const bf16*)dctx, ld_ctx, lse, (bf16*)dqkv,
                     dbias, B, L, nh, H, 0.125f, keep_threshold(p_drop), p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f, seed};
   cudaStream_t s = (cudaStream_t)stream;

@@ -410,6 +410,303 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   }
 }
 
+// =====================================================================================================
+// Backward, L <= 128.  Per (batch, head) item, all five contractions on the tensor core, accumulators in TMEM:
+//   S = Q K^T, dP = dO V^T                      (K-major operands)                      -> columns [0,128), [128,256)
+//   softmax warps: p = exp2(s * scale + mask - lse), Pd = dropout(p), dS = p * (dropout(dP) - D),  D = rowsum(Pd * dP)
+//                  (D from the scores themselves: O = Pd V  =>  dO . O = sum_k Pd dP -- the forward output is not read)
+//   dV = Pd^T dO, dK = dS^T Q * scale           (A MN-major: the SAME swizzled [q][k] tiles read transposed)
+//   dQ = dS K * scale                           (A K-major, B = K tile MN-major)        -> columns [256,448)
+// Warp roles as in the forward; ONE softmax group of 8 warps, two threads per query row (16-column sub-chunks of the
+// row alternate between them; the row sum D is exchanged through shared memory).  Q, K, V, dO arrive by 3-D TMA (rows
+// >= L zero-filled), dQ | dK | dV leave by 3-D TMA stores staged in the item's dead Q | K | V tiles, and the QKV-bias
+// gradient (column sums of dQ | dK | dV) is accumulated from the staged tiles.  Same dropout hash / indexing as the
+// forward.  Replaces attn_bwd_smem_kernel (mma.sync) of attention.cu for L <= 128.
+// =====================================================================================================
+struct BwdParams {
+  const float* maskadd;  // [B, L]
+  const float* lse;      // [B, nh, L]
+  float* dbias;          // [3H] fp32 (+=) or null
+  int B, L, nh, H;
+  int n16, items;
+  float scale, scale_log2;
+  uint32_t keep_thr;
+  float inv_keep;
+  uint32_t seed;
+};
+constexpr int kBwdStages = 2;
+constexpr int kBwdStageBytes = 4 * kTileBytes;  // Q | K | V | dO
+constexpr int kBwdSmem = kBwdStages * kBwdStageBytes + 2 * kSmemP /* Pd, dS */ + 4 * kRows * 4 /* mask, lse, D halves */ + 256 + 1024;
+
+__global__ void __launch_bounds__(kThreads, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                   const __grid_constant__ CUtensorMap tmDQKV, const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sPd = smem + kBwdStages * kBwdStageBytes;  // [2 blocks][16 KB]: [q][k] tile, 64 keys per block
+  uint8_t* sDS = sPd + kSmemP;
+  float* sMask = reinterpret_cast<float*>(sDS + kSmemP);  // [128] log2 domain
+  float* sLse = sMask + kRows;                            // [128] log2 domain (+inf for rows >= L)
+  float* sD = sLse + kRows;                               // [2][128] partial row sums of the two column halves
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 2 * kRows);
+  const uint32_t full_bar = smem_u32(bars);                       // [2] TMA -> MMA
+  const uint32_t empty_bar = smem_u32(bars + kBwdStages);         // [2] gradients stored -> TMA
+  const uint32_t sfull_bar = smem_u32(bars + 2 * kBwdStages);     // S, dP in TMEM -> softmax warps
+  const uint32_t pfull_bar = smem_u32(bars + 2 * kBwdStages + 1); // Pd, dS in smem (S, dP consumed) -> MMA
+  const uint32_t gfull_bar = smem_u32(bars + 2 * kBwdStages + 2); // dQ, dK, dV in TMEM -> softmax warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kBwdStages + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKV) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDO) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDQKV) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kBwdStages; ++i) {
+      mbar_init(full_bar + 8 * i, 1);
+      mbar_init(empty_bar + 8 * i, 1);
+    }
+    mbar_init(sfull_bar, 1);
+    mbar_init(pfull_bar, 8);
+    mbar_init(gfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDQ = tmem_base + 256, tDK = tmem_base + 320, tDV = tmem_base + 384;
+  const int H = p.H;
+  const int n_local = p.items > (int)blockIdx.x ? (p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      for (int n = 0; n < n_local; ++n) {
+        const int it = blockIdx.x + n * gridDim.x;
+        const int b = it / p.nh, h = it - b * p.nh;
+        const int st = n & 1;
+        mbar_wait(empty_bar + 8 * st, ((uint32_t)(n >> 1) & 1u) ^ 1u);
+        const uint32_t sq = smem_u32(smem + st * kBwdStageBytes);
+        const uint32_t fb = full_bar + 8 * st;
+        mbar_expect_tx(fb, 4 * kTileBytes);
+        tma_load_3d(sq, &tmQKV, fb, h * D, 0, b);
+        tma_load_3d(sq + kTileBytes, &tmQKV, fb, H + h * D, 0, b);
+        tma_load_3d(sq + 2 * kTileBytes, &tmQKV, fb, 2 * H + h * D, 0, b);
+        tma_load_3d(sq + 3 * kTileBytes, &tmDO, fb, h * D, 0, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc(kRows, p.n16, false);                      // [q, k] = A[q, d] B[k, d]^T, K-major both
+      const uint32_t idesc_dq = make_idesc(kRows, D, true);                          // dQ[q, d] = dS[q, k] K[k, d]
+      const uint32_t idesc_t = make_idesc(kRows, D, true) | (1u << 15);              // dK / dV: A MN-major, B MN-major
+      const int ksteps_k = p.n16 >> 4;                 // contraction over keys (dQ)
+      const int ksteps_q = (p.L + 15) >> 4;            // contraction over queries (dK, dV); rows >= L are zero
+      auto issue_s = [&](int n) {
+        const int st = n & 1;
+        mbar_wait(full_bar + 8 * st, (uint32_t)(n >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t sq = smem_u32(smem + st * kBwdStageBytes), sk = sq + kTileBytes, sv = sq + 2 * kTileBytes,
+                       sdo = sq + 3 * kTileBytes;
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          tc_mma(tS, make_desc(sq + k * 32, 16, 1024), make_desc(sk + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          tc_mma(tDP, make_desc(sdo + k * 32, 16, 1024), make_desc(sv + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        tc_commit(sfull_bar);
+      };
+      if (n_local > 0) issue_s(0);
+      for (int n = 0; n < n_local; ++n) {
+        const int st = n & 1;
+        mbar_wait(pfull_bar, (uint32_t)n & 1u);  // Pd, dS in shared memory; S, dP read out of TMEM
+        tc_fence_after();
+        const uint32_t sq = smem_u32(smem + st * kBwdStageBytes), sk = sq + kTileBytes, sdo = sq + 3 * kTileBytes;
+        const uint32_t sp = smem_u32(sPd), sds = smem_u32(sDS);
+        // A MN-major from the [q][k] tiles: 64-key chunks kTileBytes apart (LBO), 8-query groups 1024 B apart (SBO),
+        // 16 queries (one K step) = 2048 B
+        for (int k = 0; k < ksteps_q; ++k)
+          tc_mma(tDV, make_desc(sp + k * 2048, kTileBytes, 1024), make_desc(sdo + k * 2048, 64 * 128, 1024), idesc_t,
+                 k > 0 ? 1u : 0u);
+        for (int k = 0; k < ksteps_q; ++k)
+          tc_mma(tDK, make_desc(sds + k * 2048, kTileBytes, 1024), make_desc(sq + k * 2048, 64 * 128, 1024), idesc_t,
+                 k > 0 ? 1u : 0u);
+        for (int k = 0; k < ksteps_k; ++k)
+          tc_mma(tDQ, make_desc(sds + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
+                 make_desc(sk + k * 2048, 64 * 128, 1024), idesc_dq, k > 0 ? 1u : 0u);
+        tc_commit(gfull_bar);
+        if (n + 1 < n_local) issue_s(n + 1);  // overlaps the epilogue of item n
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================= softmax / gradient warps: two threads per query row =======================
+    const int q4 = warp & 3;
+    const int hf = (warp - 4) >> 2;                 // which 16-column sub-chunks (and which 32-column halves of the outputs)
+    const int row = q4 * 32 + lane;
+    const int tid = threadIdx.x - 128;              // 0..255
+    const int L = p.L;
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    const uint32_t dseed = site_seed(p.seed);
+    const bool drop = p.keep_thr != 0xffffffffu;
+    const uint32_t Lp = (uint32_t)(L + 1) & ~1u;
+    const int nsub = p.n16 >> 4;                    // 16-column sub-chunks of the row
+    auto group_sync = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    float next_mask = 0.f, next_lse = 0.f;
+    auto prefetch = [&](int it) {
+      if (tid < kRows) next_mask = tid < L ? p.maskadd[(size_t)(it / p.nh) * L + tid] * kLog2e : -INFINITY;
+      else next_lse = (tid - kRows) < L ? p.lse[(size_t)it * L + (tid - kRows)] * kLog2e : INFINITY;
+    };
+    if (n_local > 0) prefetch(blockIdx.x);
+    for (int n = 0; n < n_local; ++n) {
+      const int it = blockIdx.x + n * gridDim.x;
+      const int b = it / p.nh, h = it - b * p.nh;
+      const int st = n & 1;
+      if (tid < kRows) sMask[tid] = next_mask;
+      else sLse[tid - kRows] = next_lse;
+      if (n + 1 < n_local) prefetch(it + gridDim.x);
+      group_sync();
+      mbar_wait(sfull_bar, (uint32_t)n & 1u);
+      tc_fence_after();
+      const float lse2 = sLse[row];
+      const uint32_t rbase = (((uint32_t)b * p.nh + h) * L + row) * Lp;
+      // ---- pass 1: partial D = sum_k Pd * dP over this thread's sub-chunks; dropout keep bits kept for pass 2
+      float dpart = 0.f;
+      uint32_t keep_bits[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};  // 16 bits per sub-chunk, up to 8
+      for (int sc = hf; sc < nsub; sc += 2) {
+        uint32_t rs[16], rd[16];
+        tc_ld16(tS + lane_off + sc * 16, rs);
+        tc_ld16(tDP + lane_off + sc * 16, rd);
+        tc_wait_ld();
+        uint32_t bits = 0xffffu;
+        if (drop) {
+          bits = 0;
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            bool k0, k1;
+            dropout_pair(dseed, rbase + sc * 16 + j, p.keep_thr, k0, k1);
+            bits |= (k0 ? 1u : 0u) << j;
+            bits |= (k1 ? 1u : 0u) << (j + 1);
+          }
+        }
+        const int slot = sc >> 1;
+        keep_bits[slot >> 1] = (keep_bits[slot >> 1] & ~(0xffffu << ((slot & 1) * 16))) | (bits << ((slot & 1) * 16));
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float m = sMask[sc * 16 + j];
+          const float pr = m == -INFINITY ? 0.f : ex2_approx(fmaf(__uint_as_float(rs[j]), p.scale_log2, m - lse2));
+          const float pd = ((bits >> j) & 1u) ? pr * p.inv_keep : 0.f;
+          dpart = fmaf(pd, __uint_as_float(rd[j]), dpart);
+        }
+      }
+      sD[hf * kRows + row] = dpart;
+      group_sync();
+      const float Drow = sD[row] + sD[kRows + row];
+      // ---- pass 2: Pd and dS as bf16 into the swizzled [q][k] tiles
+      const bool live = row < L;
+      uint8_t* prow = sPd + (row >> 3) * 1024 + (row & 7) * 128;
+      uint8_t* drow = sDS + (row >> 3) * 1024 + (row & 7) * 128;
+      for (int sc = hf; sc < nsub; sc += 2) {
+        uint32_t rs[16], rd[16];
+        tc_ld16(tS + lane_off + sc * 16, rs);
+        tc_ld16(tDP + lane_off + sc * 16, rd);
+        tc_wait_ld();
+        const int slot = sc >> 1;
+        const uint32_t bits = (keep_bits[slot >> 1] >> ((slot & 1) * 16)) & 0xffffu;
+        float pd[16], ds[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float m = sMask[sc * 16 + j];
+          const float pr = (!live || m == -INFINITY) ? 0.f : ex2_approx(fmaf(__uint_as_float(rs[j]), p.scale_log2, m - lse2));
+          const bool keep = (bits >> j) & 1u;
+          pd[j] = keep ? pr * p.inv_keep : 0.f;
+          ds[j] = pr * ((keep ? __uint_as_float(rd[j]) * p.inv_keep : 0.f) - Drow);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int chunk = sc * 2 + u;  // 16-byte unit = 8 keys
+          const int off = (chunk >> 3) * kTileBytes + (((chunk & 7) ^ (row & 7)) << 4);
+          uint4 v;
+          v.x = pack2(pd[u * 8 + 0], pd[u * 8 + 1]); v.y = pack2(pd[u * 8 + 2], pd[u * 8 + 3]);
+          v.z = pack2(pd[u * 8 + 4], pd[u * 8 + 5]); v.w = pack2(pd[u * 8 + 6], pd[u * 8 + 7]);
+          *reinterpret_cast<uint4*>(prow + off) = v;
+          v.x = pack2(ds[u * 8 + 0], ds[u * 8 + 1]); v.y = pack2(ds[u * 8 + 2], ds[u * 8 + 3]);
+          v.z = pack2(ds[u * 8 + 4], ds[u * 8 + 5]); v.w = pack2(ds[u * 8 + 6], ds[u * 8 + 7]);
+          *reinterpret_cast<uint4*>(drow + off) = v;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pfull_bar);
+      // ---- epilogue: dQ | dK | dV rows (this thread: 32 of the 64 columns) -> bf16 -> the item's dead Q | K | V tiles
+      mbar_wait(gfull_bar, (uint32_t)n & 1u);
+      tc_fence_after();
+      uint8_t* stg = smem + st * kBwdStageBytes;
+      {
+        uint32_t r[3][32];
+        tc_ld32(tDQ + lane_off + hf * 32, r[0]);
+        tc_ld32(tDK + lane_off + hf * 32, r[1]);
+        tc_ld32(tDV + lane_off + hf * 32, r[2]);
+        tc_wait_ld();
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+          const float f = w == 2 ? 1.f : p.scale;
+          uint8_t* orow = stg + w * kTileBytes + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint4 v;
+            v.x = pack2(__uint_as_float(r[w][u * 8 + 0]) * f, __uint_as_float(r[w][u * 8 + 1]) * f);
+            v.y = pack2(__uint_as_float(r[w][u * 8 + 2]) * f, __uint_as_float(r[w][u * 8 + 3]) * f);
+            v.z = pack2(__uint_as_float(r[w][u * 8 + 4]) * f, __uint_as_float(r[w][u * 8 + 5]) * f);
+            v.w = pack2(__uint_as_float(r[w][u * 8 + 6]) * f, __uint_as_float(r[w][u * 8 + 7]) * f);
+            *reinterpret_cast<uint4*>(orow + (((hf * 4 + u) ^ (row & 7)) << 4)) = v;
+          }
+        }
+      }
+      tc_fence_before();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      group_sync();
+      if (tid == 0) {
+        tma_store_3d(&tmDQKV, smem_u32(stg), h * D, 0, b);
+        tma_store_3d(&tmDQKV, smem_u32(stg + kTileBytes), H + h * D, 0, b);
+        tma_store_3d(&tmDQKV, smem_u32(stg + 2 * kTileBytes), 2 * H + h * D, 0, b);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if (p.dbias != nullptr && tid < 192) {
+        // column sums of the staged (bf16-rounded) dQ | dK | dV tiles over the valid rows = QKV bias gradient
+        const int w = tid >> 6, col = tid & 63;
+        const uint8_t* tile = stg + w * kTileBytes;
+        float s = 0.f;
+        for (int r = 0; r < L; ++r)
+          s += __bfloat162float(*reinterpret_cast<const bf16*>(tile + (r >> 3) * 1024 + (r & 7) * 128 +
+                                                                 (((col >> 3) ^ (r & 7)) << 4) + (col & 7) * 2));
+        atomicAdd(p.dbias + w * H + h * D + col, s);
+      }
+      group_sync();  // the column sums have read the staging tiles
+      if (tid == 0) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(empty_bar + 8 * st);
+      }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   static std::once_flag once;
@@ -471,5 +768,44 @@ int mvptr_attn_fwd_tc(const void* qkv, int ld_qkv, const float* maskadd, void* c
   const int grid = p.items < kNumSMs ? p.items : kNumSMs;
   attn_fwd_tc_kernel<<<grid, kThreads, kSmemTotal, stream>>>(tq, to, p);
   MVPTR_CHECK_LAUNCH("attn_fwd_tc");
+  return 0;
+}
+
+// Returns 1 when this path does not apply (the caller falls back to the mma.sync kernels), 0 on success, < 0 on error.
+int mvptr_attn_bwd_tc(const void* qkv, int ld_qkv, const float* maskadd, const void* dctx, int ld_ctx, const float* lse,
+                      void* dqkv, float* dbias, int B, int L, int nh, int H, float p_drop, uint32_t seed,
+                      cudaStream_t stream) {
+  using namespace mvptr;
+  using namespace mvptr::attn_tc;
+  static const bool enabled = !(getenv("MVPTR_ATTN_TC") && atoi(getenv("MVPTR_ATTN_TC")) == 0) &&
+                              !(getenv("MVPTR_ATTN_BWD_TC") && atoi(getenv("MVPTR_ATTN_BWD_TC")) == 0);
+  if (!enabled || L > kRows || ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(dctx) |
+                                 reinterpret_cast<uintptr_t>(dqkv)) & 15))
+    return 1;
+  CUtensorMap tq, tdo, tdq;
+  if (int rc = make_map3(&tq, qkv, 3 * H, L, B, ld_qkv)) return rc;
+  if (int rc = make_map3(&tdo, dctx, H, L, B, ld_ctx)) return rc;
+  if (int rc = make_map3(&tdq, dqkv, 3 * H, L, B, ld_qkv)) return rc;
+  BwdParams p;
+  p.maskadd = maskadd;
+  p.lse = lse;
+  p.dbias = dbias;
+  p.B = B; p.L = L; p.nh = nh; p.H = H;
+  p.n16 = (L + 15) & ~15;
+  p.items = B * nh;
+  p.scale = 0.125f;
+  p.scale_log2 = 0.125f * kLog2e;
+  p.keep_thr = keep_threshold(p_drop);
+  p.inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  p.seed = seed;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+    if (e != cudaSuccess) MVPTR_FAIL(MVPTR_ERR_CUDA, "attention backward (tcgen05) smem attr: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int grid = p.items < kNumSMs ? p.items : kNumSMs;
+  attn_bwd_tc_kernel<<<grid, kThreads, kBwdSmem, stream>>>(tq, tdo, tdq, p);
+  MVPTR_CHECK_LAUNCH("attn_bwd_tc");
   return 0;
 }
