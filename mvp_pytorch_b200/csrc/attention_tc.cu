@@ -137,12 +137,22 @@ __device__ __forceinline__ uint32_t make_idesc(int m, int n, bool b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-constexpr int kGroups = 2;                                      // softmax warpgroups, each owns every other item
-constexpr int kSmemStage = 3 * kTileBytes;                       // Q | K | V  (the Q tile doubles as the O staging tile)
-constexpr int kSmemP = 2 * kTileBytes;                           // two 64-key blocks of the A operand, per group
-constexpr int kSmemTotal = kStages * kSmemStage + kGroups * kSmemP + kGroups * kRows * 4 /* mask */ + 256 + 1024;
+constexpr int kGroups = 2;  // softmax warpgroups, each owns every other item
 
-// One softmax warpgroup's work on one item.  NCH = 32-column chunks of the score row (n16 <= 32 NCH): the whole row
+// Forward geometry by tile rows R (= TMA box rows >= L): smaller tiles buy pipeline stages, and the stage count is
+// what bounds this kernel -- a stage is held from its TMA issue until O = P V retires (~4-5 us), so bytes in flight,
+// not instruction issue, set the rate (measured: 3 stages of 48 KB gave 2.1-2.8 us per item whatever L was).
+template <int R>
+struct FwdCfg {
+  static constexpr int kTile = R * 128;                  // one [R][64] bf16 tile
+  static constexpr int kStage = 3 * kTile;               // Q | K | V
+  static constexpr int kStages = R == 64 ? 6 : R == 96 ? 4 : 3;
+  static constexpr int kPBlocks = R > 64 ? 2 : 1;        // 64-key blocks of the P tile
+  static constexpr int kPBytes = kPBlocks * kTileBytes;  // P keeps 128-row blocks: the second MMA reads M = 128 rows
+  static constexpr int kSmem = kStages * kStage + kGroups * kPBytes + 8 * kRows * 4 /* per-warp mask rows */ + 256 + 1024;
+};
+
+// One softmax warp's work on one item.  NCH = 32-column chunks of the score row (n16 <= 32 NCH): the whole row
 // is fetched from TMEM by NCH back-to-back tcgen05.ld and ONE wait, and lives in registers from the row maximum to
 // the packed bf16 probabilities -- a single pass, no second TMEM read.
 template <int NCH>
@@ -200,25 +210,25 @@ __device__ __forceinline__ void softmax_row(const Params& p, uint32_t tmem_row, 
   sum_out = sum;
 }
 
+template <int R>
 __global__ void __launch_bounds__(kThreads, 1)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, const Params p) {
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ ctx, int ld_ctx, const Params p) {
+  using C = FwdCfg<R>;
+  constexpr int kStages = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sP = smem + kStages * kSmemStage;                                   // [kGroups][2 blocks][16 KB]
-  float* sMask = reinterpret_cast<float*>(sP + kGroups * kSmemP);             // [kGroups][128], log2 domain
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + kGroups * kRows);
+  uint8_t* sP = smem + kStages * C::kStage;                                     // [kGroups][kPBlocks][16 KB]
+  float* sMask = reinterpret_cast<float*>(sP + kGroups * C::kPBytes);           // [8 warps][128], log2 domain
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + 8 * kRows);
   const uint32_t full_bar = smem_u32(bars);                      // [kStages] TMA -> MMA
-  const uint32_t empty_bar = smem_u32(bars + kStages);           // [kStages] context stored -> TMA
+  const uint32_t empty_bar = smem_u32(bars + kStages);           // [kStages] O = P V retired -> TMA
   const uint32_t sfull_bar = smem_u32(bars + 2 * kStages);       // [kGroups] S in TMEM -> softmax group
   const uint32_t pfull_bar = smem_u32(bars + 2 * kStages + 2);   // [kGroups] P in smem (and S consumed) -> MMA
   const uint32_t ofull_bar = smem_u32(bars + 2 * kStages + 4);   // [kGroups] O in TMEM -> softmax group
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKV) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
-  }
+  if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKV) : "memory");
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(full_bar + 8 * i, 1);
@@ -252,12 +262,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         const int it = blockIdx.x + n * gridDim.x;
         const int b = it / p.nh, h = it - b * p.nh;
         mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-        const uint32_t sq = smem_u32(smem + stage * kSmemStage);
+        const uint32_t sq = smem_u32(smem + stage * C::kStage);
         const uint32_t fb = full_bar + 8 * stage;
-        mbar_expect_tx(fb, 3 * kTileBytes);
+        mbar_expect_tx(fb, C::kStage);
         tma_load_3d(sq, &tmQKV, fb, h * D, 0, b);
-        tma_load_3d(sq + kTileBytes, &tmQKV, fb, H + h * D, 0, b);
-        tma_load_3d(sq + 2 * kTileBytes, &tmQKV, fb, 2 * H + h * D, 0, b);
+        tma_load_3d(sq + C::kTile, &tmQKV, fb, H + h * D, 0, b);
+        tma_load_3d(sq + 2 * C::kTile, &tmQKV, fb, 2 * H + h * D, 0, b);
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
@@ -267,7 +277,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
     if (lane == 0) {
-      const uint32_t idesc_s = make_idesc(kRows, p.n16, false);  // S[128, n16] = Q . K^T, both K-major
+      // S[128, n16] = Q . K^T (both K-major; Q rows >= R read the K / V tiles behind it: garbage rows nobody stores)
+      const uint32_t idesc_s = make_idesc(kRows, p.n16, false);
       const uint32_t idesc_o = make_idesc(kRows, D, true);       // O[128, 64] = P . V, V is MN-major ([key][d])
       const int ksteps = p.n16 >> 4;
       auto try_wait = [](uint32_t bar, uint32_t parity) -> bool {
@@ -292,7 +303,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           const int st = next_s % kStages, g = next_s & 1;
           if (try_wait(full_bar + 8 * st, (uint32_t)(next_s / kStages) & 1u)) {
             tc_fence_after();
-            const uint32_t sq = smem_u32(smem + st * kSmemStage), sk = sq + kTileBytes;
+            const uint32_t sq = smem_u32(smem + st * C::kStage), sk = sq + C::kTile;
 #pragma unroll
             for (int k = 0; k < D / 16; ++k)
               tc_mma(tmem_base + g * 256, make_desc(sq + k * 32, 16, 1024), make_desc(sk + k * 32, 16, 1024), idesc_s,
@@ -305,23 +316,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           const int st = next_pv % kStages, g = next_pv & 1;
           if (try_wait(pfull_bar + 8 * g, (uint32_t)(next_pv >> 1) & 1u)) {  // P in smem, S read out of TMEM
             tc_fence_after();
-            const uint32_t sv = smem_u32(smem + st * kSmemStage) + 2 * kTileBytes;
-            const uint32_t sp = smem_u32(sP + g * kSmemP);
+            const uint32_t sv = smem_u32(smem + st * C::kStage) + 2 * C::kTile;
+            const uint32_t sp = smem_u32(sP + g * C::kPBytes);
             for (int k = 0; k < ksteps; ++k)
               tc_mma(tmem_base + g * 256 + 128, make_desc(sp + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
                      make_desc(sv + k * 2048, 64 * 128, 1024), idesc_o, k > 0 ? 1u : 0u);
             tc_commit(ofull_bar + 8 * g);
+            tc_commit(empty_bar + 8 * st);  // Q, K, V of this stage are dead once O = P V retires
             ++next_pv;
           }
         }
       }
     }
   } else if (warp >= 4) {
-    // ======================= softmax + epilogue: thread = query row = TMEM lane =======================
+    // ======================= softmax + epilogue: thread = query row = TMEM lane; warps are independent ==========
     const int g = (warp - 4) >> 2;                  // warpgroup: items n with n & 1 == g
     const int q4 = warp & 3;
     const int row = q4 * 32 + lane;                 // query index inside the head
-    const int tid = (threadIdx.x - 128) & 127;      // 0..127 inside the group
     const int L = p.L;
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
     const uint32_t tmem_S = tmem_base + g * 256 + lane_off, tmem_O = tmem_S + 128;
@@ -329,38 +340,38 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     const bool drop = p.keep_thr != 0xffffffffu;
     const uint32_t Lp = (uint32_t)(L + 1) & ~1u;    // even row pitch of the dropout index (as attention.cu)
     const int nch = (p.n16 + 31) >> 5;
-    uint8_t* sPg = sP + g * kSmemP;
-    float* mk = sMask + g * kRows;
-    auto group_sync = [&]() {
-      if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-      else asm volatile("bar.sync 2, 128;" ::: "memory");
-    };
+    uint8_t* sPg = sP + g * C::kPBytes;
+    float* mk = sMask + (warp - 4) * kRows;         // this warp's copy of the mask row
     // the mask row of the next item is fetched one item ahead (all heads of a batch element share it)
-    float next_mask = 0.f;
-    if (g < n_local) {
-      const int it0 = blockIdx.x + g * gridDim.x;
-      next_mask = tid < L ? p.maskadd[(size_t)(it0 / p.nh) * L + tid] * kLog2e : -INFINITY;
-    }
+    float next_mask[4];
+    auto fetch_mask = [&](int it) {
+      const float* src = p.maskadd + (size_t)(it / p.nh) * L;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = lane + 32 * i;
+        next_mask[i] = k < L ? __ldg(src + k) * kLog2e : -INFINITY;
+      }
+    };
+    if (g < n_local) fetch_mask(blockIdx.x + g * gridDim.x);
     int m = 0;  // items this group has processed
     for (int n = g; n < n_local; n += kGroups, ++m) {
       const int it = blockIdx.x + n * gridDim.x;
       const int b = it / p.nh, h = it - b * p.nh;
-      const int st = n % kStages;
-      mk[tid] = next_mask;  // (the previous item's rows were consumed before its epilogue barrier)
-      if (n + kGroups < n_local) {
-        const int itn = it + kGroups * gridDim.x;
-        next_mask = tid < L ? p.maskadd[(size_t)(itn / p.nh) * L + tid] * kLog2e : -INFINITY;
-      }
-      group_sync();  // mask row visible to the 128 threads of the group
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mk[lane + 32 * i] = next_mask[i];
+      if (n + kGroups < n_local) fetch_mask(it + kGroups * gridDim.x);
+      __syncwarp();
       mbar_wait(sfull_bar + 8 * g, (uint32_t)m & 1u);
       tc_fence_after();
       const uint32_t rbase = (((uint32_t)b * p.nh + h) * L + row) * Lp;
       float mx, sum;
-      switch (nch) {
-        case 1: softmax_row<1>(p, tmem_S, mk, row, rbase, dseed, drop, sPg, mx, sum); break;
-        case 2: softmax_row<2>(p, tmem_S, mk, row, rbase, dseed, drop, sPg, mx, sum); break;
-        case 3: softmax_row<3>(p, tmem_S, mk, row, rbase, dseed, drop, sPg, mx, sum); break;
-        default: softmax_row<4>(p, tmem_S, mk, row, rbase, dseed, drop, sPg, mx, sum); break;
+      if constexpr (R == 64) {  // n16 <= 64
+        if (nch == 1) softmax_row<1>(p, tmem_S, mk, row, rbase, dseed, drop, sPg, mx, sum);
+        else softmax_row<2>(p, tmem_S, mk, row, rbase, dseed, drop, sPg, mx, sum);
+      } else if constexpr (R == 96) {  // n16 = 80 or 96
+        softmax_row<3>(p, tmem_S, mk, row, rbase, dseed, drop, sPg, mx, sum);
+      } else {  // n16 = 112 or 128
+        softmax_row<4>(p, tmem_S, mk, row, rbase, dseed, drop, sPg, mx, sum);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P visible to the tensor core (async proxy)
       tc_fence_before();
@@ -368,38 +379,29 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       if (lane == 0) mbar_arrive(pfull_bar + 8 * g);
       if (p.lse && row < L) p.lse[((size_t)b * p.nh + h) * L + row] = (mx + log2f(sum)) * (1.0f / kLog2e);
       const float inv = p.inv_keep / sum;
-      // ---- epilogue: O row * inv -> bf16 -> the (dead) Q tile of this item's stage, swizzled -> 3-D TMA store
-      //      (rows >= L clipped); the stage goes back to the producer once the store has read it
+      // ---- epilogue: O row * inv -> bf16 -> this thread's 128 bytes of the head-merged context [B*L, H]
       mbar_wait(ofull_bar + 8 * g, (uint32_t)m & 1u);
       tc_fence_after();
-      uint8_t* sO = smem + st * kSmemStage;
-      uint8_t* orow = sO + (row >> 3) * 1024 + (row & 7) * 128;
       uint32_t r[2][32];
       tc_ld32(tmem_O, r[0]);
       tc_ld32(tmem_O + 32, r[1]);
       tc_wait_ld();
-#pragma unroll
-      for (int c = 0; c < 2; ++c)
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          uint4 v;
-          v.x = pack2(__uint_as_float(r[c][u * 8 + 0]) * inv, __uint_as_float(r[c][u * 8 + 1]) * inv);
-          v.y = pack2(__uint_as_float(r[c][u * 8 + 2]) * inv, __uint_as_float(r[c][u * 8 + 3]) * inv);
-          v.z = pack2(__uint_as_float(r[c][u * 8 + 4]) * inv, __uint_as_float(r[c][u * 8 + 5]) * inv);
-          v.w = pack2(__uint_as_float(r[c][u * 8 + 6]) * inv, __uint_as_float(r[c][u * 8 + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + (((c * 4 + u) ^ (row & 7)) << 4)) = v;
-        }
       tc_fence_before();
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      group_sync();
-      if (tid == 0) {
-        tma_store_3d(&tmO, smem_u32(sO), h * D, 0, b);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        mbar_arrive(empty_bar + 8 * st);  // Q, K, V (PV has retired) and the staging tile are free
+      if (row < L) {
+        uint4* dst = reinterpret_cast<uint4*>(ctx + ((size_t)b * L + row) * ld_ctx + h * D);
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint4 v;
+            v.x = pack2(__uint_as_float(r[c][u * 8 + 0]) * inv, __uint_as_float(r[c][u * 8 + 1]) * inv);
+            v.y = pack2(__uint_as_float(r[c][u * 8 + 2]) * inv, __uint_as_float(r[c][u * 8 + 3]) * inv);
+            v.z = pack2(__uint_as_float(r[c][u * 8 + 4]) * inv, __uint_as_float(r[c][u * 8 + 5]) * inv);
+            v.w = pack2(__uint_as_float(r[c][u * 8 + 6]) * inv, __uint_as_float(r[c][u * 8 + 7]) * inv);
+            dst[c * 4 + u] = v;
+          }
       }
     }
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -434,6 +436,7 @@ struct BwdParams {
   float inv_keep;
   uint32_t seed;
 };
+constexpr int kSmemP = 2 * kTileBytes;  // a [128 q][128 k] bf16 tile: two 64-key blocks
 constexpr int kBwdStages = 2;
 constexpr int kBwdStageBytes = 4 * kTileBytes;  // Q | K | V | dO
 constexpr int kBwdSmem = kBwdStages * kBwdStageBytes + 2 * kSmemP /* Pd, dS */ + 4 * kRows * 4 /* mask, lse, D halves */ + 256 + 1024;
@@ -722,12 +725,12 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 
 // [B, L, cols] bf16 view (row pitch ld elements) with box 64 x 128 x 1: rows >= L are out of bounds -> zero-filled
 // on load, clipped on store
-static int make_map3(CUtensorMap* map, const void* base, int cols, int L, int B, int ld) {
+static int make_map3(CUtensorMap* map, const void* base, int cols, int L, int B, int ld, int box_rows = kRows) {
   auto enc = get_encode();
   if (!enc) MVPTR_FAIL(MVPTR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)L, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)L * ld * 2};
-  cuuint32_t box[3] = {64, (cuuint32_t)kRows, 1};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -740,15 +743,34 @@ static int make_map3(CUtensorMap* map, const void* base, int cols, int L, int B,
 }  // namespace mvptr
 
 // Returns 1 when this path does not apply (the caller falls back to the mma.sync kernel), 0 on success, < 0 on error.
+template <int R>
+static int launch_fwd_tc(const CUtensorMap& tq, void* ctx, int ld_ctx, const mvptr::attn_tc::Params& p, cudaStream_t stream) {
+  using namespace mvptr;
+  using namespace mvptr::attn_tc;
+  auto kern = attn_fwd_tc_kernel<R>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<R>::kSmem);
+    if (e != cudaSuccess) MVPTR_FAIL(MVPTR_ERR_CUDA, "attention (tcgen05) smem attr: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  static_assert(FwdCfg<R>::kSmem <= 227 * 1024, "shared memory budget");
+  const int grid = p.items < kNumSMs ? p.items : kNumSMs;
+  kern<<<grid, kThreads, FwdCfg<R>::kSmem, stream>>>(tq, (bf16*)ctx, ld_ctx, p);
+  MVPTR_CHECK_LAUNCH("attn_fwd_tc");
+  return 0;
+}
+
 int mvptr_attn_fwd_tc(const void* qkv, int ld_qkv, const float* maskadd, void* ctx, int ld_ctx, float* lse, int B, int L,
                       int nh, int H, float p_drop, uint32_t seed, cudaStream_t stream) {
   using namespace mvptr;
   using namespace mvptr::attn_tc;
-  static const bool enabled = !(getenv("MVPTR_ATTN_TC") && atoi(getenv("MVPTR_ATTN_TC")) == 0);
+  static const bool enabled = !(getenv("MVPTR_ATTN_TC") && atoi(getenv("MVPTR_ATTN_TC")) == 0) &&
+                              !(getenv("MVPTR_ATTN_FWD_TC") && atoi(getenv("MVPTR_ATTN_FWD_TC")) == 0);
   if (!enabled || L > kRows || (reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(ctx) & 15)) return 1;
-  CUtensorMap tq, to;
-  if (int rc = make_map3(&tq, qkv, 3 * H, L, B, ld_qkv)) return rc;
-  if (int rc = make_map3(&to, ctx, H, L, B, ld_ctx)) return rc;
+  const int R = L <= 64 ? 64 : L <= 96 ? 96 : 128;
+  CUtensorMap tq;
+  if (int rc = make_map3(&tq, qkv, 3 * H, L, B, ld_qkv, R)) return rc;
   Params p;
   p.maskadd = maskadd;
   p.lse = lse;
@@ -759,16 +781,9 @@ int mvptr_attn_fwd_tc(const void* qkv, int ld_qkv, const float* maskadd, void* c
   p.keep_thr = keep_threshold(p_drop);
   p.inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   p.seed = seed;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
-    if (e != cudaSuccess) MVPTR_FAIL(MVPTR_ERR_CUDA, "attention (tcgen05) smem attr: %s", cudaGetErrorString(e));
-    configured = true;
-  }
-  const int grid = p.items < kNumSMs ? p.items : kNumSMs;
-  attn_fwd_tc_kernel<<<grid, kThreads, kSmemTotal, stream>>>(tq, to, p);
-  MVPTR_CHECK_LAUNCH("attn_fwd_tc");
-  return 0;
+  if (R == 64) return launch_fwd_tc<64>(tq, ctx, ld_ctx, p, stream);
+  if (R == 96) return launch_fwd_tc<96>(tq, ctx, ld_ctx, p, stream);
+  return launch_fwd_tc<128>(tq, ctx, ld_ctx, p, stream);
 }
 
 // Returns 1 when this path does not apply (the caller falls back to the mma.sync kernels), 0 on success, < 0 on error.
