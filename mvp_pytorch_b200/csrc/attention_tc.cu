@@ -439,11 +439,14 @@ struct BwdParams {
 constexpr int kSmemP = 2 * kTileBytes;  // a [128 q][128 k] bf16 tile: two 64-key blocks
 constexpr int kBwdStages = 2;
 constexpr int kBwdStageBytes = 4 * kTileBytes;  // Q | K | V | dO
-constexpr int kBwdSmem = kBwdStages * kBwdStageBytes + 2 * kSmemP /* Pd, dS */ + 4 * kRows * 4 /* mask, lse, D halves */ + 256 + 1024;
+constexpr int kBwdMaxH = 1024;                  // bias-gradient accumulators [3][H] live in shared memory
+constexpr int kBwdSmem = kBwdStages * kBwdStageBytes + 2 * kSmemP /* Pd, dS */ + 4 * kRows * 4 /* mask, lse, D halves */ +
+                         3 * kBwdMaxH * 4 + 256 + 1024;
 
+template <int NS>  // 16-column sub-chunks of a score row per thread: ceil(n16 / 32)
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                   const __grid_constant__ CUtensorMap tmDQKV, const BwdParams p) {
+                   bf16* __restrict__ dqkv, int ld_qkv, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sPd = smem + kBwdStages * kBwdStageBytes;  // [2 blocks][16 KB]: [q][k] tile, 64 keys per block
@@ -451,7 +454,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   float* sMask = reinterpret_cast<float*>(sDS + kSmemP);  // [128] log2 domain
   float* sLse = sMask + kRows;                            // [128] log2 domain (+inf for rows >= L)
   float* sD = sLse + kRows;                               // [2][128] partial row sums of the two column halves
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 2 * kRows);
+  float* sBias = sD + 2 * kRows;                          // [3][H] column sums of dQ | dK | dV over this CTA's items
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 3 * kBwdMaxH);
   const uint32_t full_bar = smem_u32(bars);                       // [2] TMA -> MMA
   const uint32_t empty_bar = smem_u32(bars + kBwdStages);         // [2] gradients stored -> TMA
   const uint32_t sfull_bar = smem_u32(bars + 2 * kBwdStages);     // S, dP in TMEM -> softmax warps
@@ -463,7 +467,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKV) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDO) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDQKV) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kBwdStages; ++i) {
@@ -480,6 +483,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (p.dbias != nullptr)
+    for (int i = threadIdx.x; i < 3 * p.H; i += blockDim.x) sBias[(i / p.H) * kBwdMaxH + (i % p.H)] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -546,6 +551,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           tc_mma(tDQ, make_desc(sds + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
                  make_desc(sk + k * 2048, 64 * 128, 1024), idesc_dq, k > 0 ? 1u : 0u);
         tc_commit(gfull_bar);
+        tc_commit(empty_bar + 8 * st);        // Q, K, V, dO of this stage are dead once the gradient MMAs retire
         if (n + 1 < n_local) issue_s(n + 1);  // overlaps the epilogue of item n
       }
     }
@@ -580,126 +586,142 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       tc_fence_after();
       const float lse2 = sLse[row];
       const uint32_t rbase = (((uint32_t)b * p.nh + h) * L + row) * Lp;
-      // ---- pass 1: partial D = sum_k Pd * dP over this thread's sub-chunks; dropout keep bits kept for pass 2
-      float dpart = 0.f;
-      uint32_t keep_bits[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};  // 16 bits per sub-chunk, up to 8
-      for (int sc = hf; sc < nsub; sc += 2) {
-        uint32_t rs[16], rd[16];
-        tc_ld16(tS + lane_off + sc * 16, rs);
-        tc_ld16(tDP + lane_off + sc * 16, rd);
-        tc_wait_ld();
-        uint32_t bits = 0xffffu;
-        if (drop) {
-          bits = 0;
+      const bool live = row < L;
+      // ---- this thread's sub-chunks of the S and dP rows: all TMEM loads back to back, ONE wait; p and the dropped
+      //      dP stay in registers from the row sum D to dS (single pass: one exp, one dropout hash per score)
+      uint32_t rs[NS][16], rd[NS][16];
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            bool k0, k1;
-            dropout_pair(dseed, rbase + sc * 16 + j, p.keep_thr, k0, k1);
-            bits |= (k0 ? 1u : 0u) << j;
-            bits |= (k1 ? 1u : 0u) << (j + 1);
-          }
+      for (int i = 0; i < NS; ++i) {
+        const int sc = 2 * i + hf;
+        if (sc < nsub) {
+          tc_ld16(tS + lane_off + sc * 16, rs[i]);
+          tc_ld16(tDP + lane_off + sc * 16, rd[i]);
         }
-        const int slot = sc >> 1;
-        keep_bits[slot >> 1] = (keep_bits[slot >> 1] & ~(0xffffu << ((slot & 1) * 16))) | (bits << ((slot & 1) * 16));
+      }
+      tc_wait_ld();
+      float dpart = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float m = sMask[sc * 16 + j];
-          const float pr = m == -INFINITY ? 0.f : ex2_approx(fmaf(__uint_as_float(rs[j]), p.scale_log2, m - lse2));
-          const float pd = ((bits >> j) & 1u) ? pr * p.inv_keep : 0.f;
-          dpart = fmaf(pd, __uint_as_float(rd[j]), dpart);
+      for (int i = 0; i < NS; ++i) {
+        const int sc = 2 * i + hf;
+        if (sc < nsub) {
+          uint32_t bits = 0xffffu;
+          if (drop) {
+            bits = 0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              bool k0, k1;
+              dropout_pair(dseed, rbase + sc * 16 + j, p.keep_thr, k0, k1);
+              bits |= (k0 ? 1u : 0u) << j;
+              bits |= (k1 ? 1u : 0u) << (j + 1);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float m = sMask[sc * 16 + j];
+            const float pr = (!live || m == -INFINITY) ? 0.f : ex2_approx(fmaf(__uint_as_float(rs[i][j]), p.scale_log2, m - lse2));
+            const bool keep = (bits >> j) & 1u;
+            const float dpd = keep ? __uint_as_float(rd[i][j]) * p.inv_keep : 0.f;  // dropout applied to dP
+            dpart = fmaf(keep ? pr * p.inv_keep : 0.f, __uint_as_float(rd[i][j]), dpart);
+            rs[i][j] = __float_as_uint(pr);
+            rd[i][j] = __float_as_uint(dpd);
+          }
+          // Pd = dropout(p) as bf16 into the swizzled [q][k] tile (dpd == 0 exactly where the element was dropped)
+          uint8_t* prow = sPd + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int chunk = sc * 2 + u;
+            float v8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              v8[j] = ((bits >> (u * 8 + j)) & 1u) ? __uint_as_float(rs[i][u * 8 + j]) * p.inv_keep : 0.f;
+            uint4 v;
+            v.x = pack2(v8[0], v8[1]); v.y = pack2(v8[2], v8[3]); v.z = pack2(v8[4], v8[5]); v.w = pack2(v8[6], v8[7]);
+            *reinterpret_cast<uint4*>(prow + (chunk >> 3) * kTileBytes + (((chunk & 7) ^ (row & 7)) << 4)) = v;
+          }
         }
       }
       sD[hf * kRows + row] = dpart;
       group_sync();
       const float Drow = sD[row] + sD[kRows + row];
-      // ---- pass 2: Pd and dS as bf16 into the swizzled [q][k] tiles
-      const bool live = row < L;
-      uint8_t* prow = sPd + (row >> 3) * 1024 + (row & 7) * 128;
       uint8_t* drow = sDS + (row >> 3) * 1024 + (row & 7) * 128;
-      for (int sc = hf; sc < nsub; sc += 2) {
-        uint32_t rs[16], rd[16];
-        tc_ld16(tS + lane_off + sc * 16, rs);
-        tc_ld16(tDP + lane_off + sc * 16, rd);
-        tc_wait_ld();
-        const int slot = sc >> 1;
-        const uint32_t bits = (keep_bits[slot >> 1] >> ((slot & 1) * 16)) & 0xffffu;
-        float pd[16], ds[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float m = sMask[sc * 16 + j];
-          const float pr = (!live || m == -INFINITY) ? 0.f : ex2_approx(fmaf(__uint_as_float(rs[j]), p.scale_log2, m - lse2));
-          const bool keep = (bits >> j) & 1u;
-          pd[j] = keep ? pr * p.inv_keep : 0.f;
-          ds[j] = pr * ((keep ? __uint_as_float(rd[j]) * p.inv_keep : 0.f) - Drow);
-        }
+      for (int i = 0; i < NS; ++i) {
+        const int sc = 2 * i + hf;
+        if (sc < nsub) {
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int chunk = sc * 2 + u;  // 16-byte unit = 8 keys
-          const int off = (chunk >> 3) * kTileBytes + (((chunk & 7) ^ (row & 7)) << 4);
-          uint4 v;
-          v.x = pack2(pd[u * 8 + 0], pd[u * 8 + 1]); v.y = pack2(pd[u * 8 + 2], pd[u * 8 + 3]);
-          v.z = pack2(pd[u * 8 + 4], pd[u * 8 + 5]); v.w = pack2(pd[u * 8 + 6], pd[u * 8 + 7]);
-          *reinterpret_cast<uint4*>(prow + off) = v;
-          v.x = pack2(ds[u * 8 + 0], ds[u * 8 + 1]); v.y = pack2(ds[u * 8 + 2], ds[u * 8 + 3]);
-          v.z = pack2(ds[u * 8 + 4], ds[u * 8 + 5]); v.w = pack2(ds[u * 8 + 6], ds[u * 8 + 7]);
-          *reinterpret_cast<uint4*>(drow + off) = v;
+          for (int u = 0; u < 2; ++u) {
+            const int chunk = sc * 2 + u;
+            float v8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)  // dS = p * (dropout(dP) - D)
+              v8[j] = __uint_as_float(rs[i][u * 8 + j]) * (__uint_as_float(rd[i][u * 8 + j]) - Drow);
+            uint4 v;
+            v.x = pack2(v8[0], v8[1]); v.y = pack2(v8[2], v8[3]); v.z = pack2(v8[4], v8[5]); v.w = pack2(v8[6], v8[7]);
+            *reinterpret_cast<uint4*>(drow + (chunk >> 3) * kTileBytes + (((chunk & 7) ^ (row & 7)) << 4)) = v;
+          }
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pfull_bar);
-      // ---- epilogue: dQ | dK | dV rows (this thread: 32 of the 64 columns) -> bf16 -> the item's dead Q | K | V tiles
+      // ---- epilogue: dQ | dK | dV rows (this thread: 32 of the 64 columns) -> bf16 -> this thread's 3 x 64 bytes of
+      //      dqkv [B*L, 3H]; the QKV-bias gradient = column sums of the rounded values, reduced across the warp's
+      //      32 rows by the halving butterfly (31 shuffles per 32 columns) into the CTA's shared accumulators
       mbar_wait(gfull_bar, (uint32_t)n & 1u);
       tc_fence_after();
-      uint8_t* stg = smem + st * kBwdStageBytes;
       {
-        uint32_t r[3][32];
+        uint32_t r[2][32];  // double buffered: tensor w + 1 is in flight while w is packed, stored and column-summed
         tc_ld32(tDQ + lane_off + hf * 32, r[0]);
-        tc_ld32(tDK + lane_off + hf * 32, r[1]);
-        tc_ld32(tDV + lane_off + hf * 32, r[2]);
-        tc_wait_ld();
 #pragma unroll
         for (int w = 0; w < 3; ++w) {
+          tc_wait_ld();
+          if (w == 0) tc_ld32(tDK + lane_off + hf * 32, r[1]);
+          if (w == 1) tc_ld32(tDV + lane_off + hf * 32, r[0]);
           const float f = w == 2 ? 1.f : p.scale;
-          uint8_t* orow = stg + w * kTileBytes + (row >> 3) * 1024 + (row & 7) * 128;
+          uint32_t pk[16];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            uint4 v;
-            v.x = pack2(__uint_as_float(r[w][u * 8 + 0]) * f, __uint_as_float(r[w][u * 8 + 1]) * f);
-            v.y = pack2(__uint_as_float(r[w][u * 8 + 2]) * f, __uint_as_float(r[w][u * 8 + 3]) * f);
-            v.z = pack2(__uint_as_float(r[w][u * 8 + 4]) * f, __uint_as_float(r[w][u * 8 + 5]) * f);
-            v.w = pack2(__uint_as_float(r[w][u * 8 + 6]) * f, __uint_as_float(r[w][u * 8 + 7]) * f);
-            *reinterpret_cast<uint4*>(orow + (((hf * 4 + u) ^ (row & 7)) << 4)) = v;
+          for (int j = 0; j < 16; ++j)
+            pk[j] = pack2(__uint_as_float(r[w & 1][2 * j]) * f, __uint_as_float(r[w & 1][2 * j + 1]) * f);
+          if (live) {
+            uint4* dst = reinterpret_cast<uint4*>(dqkv + ((size_t)b * L + row) * ld_qkv + w * H + h * D + hf * 32);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) dst[u] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+          }
+          if (p.dbias != nullptr) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              v[2 * j] = live ? __uint_as_float(pk[j] << 16) : 0.f;
+              v[2 * j + 1] = live ? __uint_as_float(pk[j] & 0xffff0000u) : 0.f;
+            }
+            // after step s (offset 16 >> s) lane l holds the partial sums of 16 >> s columns; at the end: column (l)
+#pragma unroll
+            for (int off = 16, cnt = 16; off >= 1; off >>= 1, cnt >>= 1) {
+              const bool upper = (lane & off) != 0;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (j < cnt) {
+                  const float mine = upper ? v[j + cnt] : v[j];
+                  const float send = upper ? v[j] : v[j + cnt];
+                  v[j] = mine + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+              }
+            }
+            // lane l now holds the sum over the warp's 32 rows of column bitrev-free index: columns were halved MSB
+            // first, so lane l owns column l
+            atomicAdd(sBias + w * kBwdMaxH + h * D + hf * 32 + lane, v[0]);
           }
         }
-      }
-      tc_fence_before();
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      group_sync();
-      if (tid == 0) {
-        tma_store_3d(&tmDQKV, smem_u32(stg), h * D, 0, b);
-        tma_store_3d(&tmDQKV, smem_u32(stg + kTileBytes), H + h * D, 0, b);
-        tma_store_3d(&tmDQKV, smem_u32(stg + 2 * kTileBytes), 2 * H + h * D, 0, b);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
-      if (p.dbias != nullptr && tid < 192) {
-        // column sums of the staged (bf16-rounded) dQ | dK | dV tiles over the valid rows = QKV bias gradient
-        const int w = tid >> 6, col = tid & 63;
-        const uint8_t* tile = stg + w * kTileBytes;
-        float s = 0.f;
-        for (int r = 0; r < L; ++r)
-          s += __bfloat162float(*reinterpret_cast<const bf16*>(tile + (r >> 3) * 1024 + (r & 7) * 128 +
-                                                                 (((col >> 3) ^ (r & 7)) << 4) + (col & 7) * 2));
-        atomicAdd(p.dbias + w * H + h * D + col, s);
-      }
-      group_sync();  // the column sums have read the staging tiles
-      if (tid == 0) {
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        mbar_arrive(empty_bar + 8 * st);
+        tc_fence_before();
       }
     }
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    group_sync();  // all shared-memory bias accumulations of this CTA are done
+    if (p.dbias != nullptr)
+      for (int i = tid; i < 3 * p.H; i += 256) {
+        const float v = sBias[(i / p.H) * kBwdMaxH + (i % p.H)];
+        if (v != 0.f) atomicAdd(p.dbias + i, v);
+      }
   }
 
   tc_fence_before();
@@ -786,6 +808,24 @@ int mvptr_attn_fwd_tc(const void* qkv, int ld_qkv, const float* maskadd, void* c
   return launch_fwd_tc<128>(tq, ctx, ld_ctx, p, stream);
 }
 
+template <int NS>
+static int launch_bwd_tc(const CUtensorMap& tq, const CUtensorMap& tdo, void* dqkv, int ld_qkv,
+                         const mvptr::attn_tc::BwdParams& p, cudaStream_t stream) {
+  using namespace mvptr;
+  using namespace mvptr::attn_tc;
+  auto kern = attn_bwd_tc_kernel<NS>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+    if (e != cudaSuccess) MVPTR_FAIL(MVPTR_ERR_CUDA, "attention backward (tcgen05) smem attr: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int grid = p.items < kNumSMs ? p.items : kNumSMs;
+  kern<<<grid, kThreads, kBwdSmem, stream>>>(tq, tdo, (bf16*)dqkv, ld_qkv, p);
+  MVPTR_CHECK_LAUNCH("attn_bwd_tc");
+  return 0;
+}
+
 // Returns 1 when this path does not apply (the caller falls back to the mma.sync kernels), 0 on success, < 0 on error.
 int mvptr_attn_bwd_tc(const void* qkv, int ld_qkv, const float* maskadd, const void* dctx, int ld_ctx, const float* lse,
                       void* dqkv, float* dbias, int B, int L, int nh, int H, float p_drop, uint32_t seed,
@@ -797,10 +837,10 @@ int mvptr_attn_bwd_tc(const void* qkv, int ld_qkv, const float* maskadd, const v
   if (!enabled || L > kRows || ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(dctx) |
                                  reinterpret_cast<uintptr_t>(dqkv)) & 15))
     return 1;
-  CUtensorMap tq, tdo, tdq;
+  if (H > kBwdMaxH) return 1;
+  CUtensorMap tq, tdo;
   if (int rc = make_map3(&tq, qkv, 3 * H, L, B, ld_qkv)) return rc;
   if (int rc = make_map3(&tdo, dctx, H, L, B, ld_ctx)) return rc;
-  if (int rc = make_map3(&tdq, dqkv, 3 * H, L, B, ld_qkv)) return rc;
   BwdParams p;
   p.maskadd = maskadd;
   p.lse = lse;
@@ -813,14 +853,10 @@ int mvptr_attn_bwd_tc(const void* qkv, int ld_qkv, const float* maskadd, const v
   p.keep_thr = keep_threshold(p_drop);
   p.inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   p.seed = seed;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
-    if (e != cudaSuccess) MVPTR_FAIL(MVPTR_ERR_CUDA, "attention backward (tcgen05) smem attr: %s", cudaGetErrorString(e));
-    configured = true;
+  switch ((p.n16 + 31) >> 5) {
+    case 1: return launch_bwd_tc<1>(tq, tdo, dqkv, ld_qkv, p, stream);
+    case 2: return launch_bwd_tc<2>(tq, tdo, dqkv, ld_qkv, p, stream);
+    case 3: return launch_bwd_tc<3>(tq, tdo, dqkv, ld_qkv, p, stream);
+    default: return launch_bwd_tc<4>(tq, tdo, dqkv, ld_qkv, p, stream);
   }
-  const int grid = p.items < kNumSMs ? p.items : kNumSMs;
-  attn_bwd_tc_kernel<<<grid, kThreads, kBwdSmem, stream>>>(tq, tdo, tdq, p);
-  MVPTR_CHECK_LAUNCH("attn_bwd_tc");
-  return 0;
 }
