@@ -34,7 +34,6 @@ namespace attn_tc {
 constexpr int D = 64;
 constexpr int kRows = 128;           // MMA M: query rows (padded)
 constexpr int kTileBytes = kRows * 128;  // one [128][64] bf16 tile, 128-byte rows
-constexpr int kStages = 3;
 constexpr int kThreads = 384;
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -146,10 +145,11 @@ template <int R>
 struct FwdCfg {
   static constexpr int kTile = R * 128;                  // one [R][64] bf16 tile
   static constexpr int kStage = 3 * kTile;               // Q | K | V
-  static constexpr int kStages = R == 64 ? 6 : R == 96 ? 4 : 3;
+  static constexpr int kStages = R == 64 ? 5 : R == 96 ? 3 : 2;
   static constexpr int kPBlocks = R > 64 ? 2 : 1;        // 64-key blocks of the P tile
   static constexpr int kPBytes = kPBlocks * kTileBytes;  // P keeps 128-row blocks: the second MMA reads M = 128 rows
-  static constexpr int kSmem = kStages * kStage + kGroups * kPBytes + 8 * kRows * 4 /* per-warp mask rows */ + 256 + 1024;
+  static constexpr int kSlab = 32 * 128;                 // one warp's 32 context rows: a TMA-store box
+  static constexpr int kSmem = kStages * kStage + kGroups * kPBytes + 8 * kSlab + 8 * kRows * 4 /* per-warp mask rows */ + 256 + 1024;
 };
 
 // One softmax warp's work on one item.  NCH = 32-column chunks of the score row (n16 <= 32 NCH): the whole row
@@ -212,13 +212,14 @@ __device__ __forceinline__ void softmax_row(const Params& p, uint32_t tmem_row, 
 
 template <int R>
 __global__ void __launch_bounds__(kThreads, 1)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ ctx, int ld_ctx, const Params p) {
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, const Params p) {
   using C = FwdCfg<R>;
   constexpr int kStages = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sP = smem + kStages * C::kStage;                                     // [kGroups][kPBlocks][16 KB]
-  float* sMask = reinterpret_cast<float*>(sP + kGroups * C::kPBytes);           // [8 warps][128], log2 domain
+  uint8_t* sSlab = sP + kGroups * C::kPBytes;                                   // [8 warps][32 rows][128 B] store slabs
+  float* sMask = reinterpret_cast<float*>(sSlab + 8 * C::kSlab);                // [8 warps][128], log2 domain
   uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + 8 * kRows);
   const uint32_t full_bar = smem_u32(bars);                      // [kStages] TMA -> MMA
   const uint32_t empty_bar = smem_u32(bars + kStages);           // [kStages] O = P V retired -> TMA
@@ -228,7 +229,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKV) : "memory");
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKV) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
+  }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(full_bar + 8 * i, 1);
@@ -379,7 +383,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
       if (lane == 0) mbar_arrive(pfull_bar + 8 * g);
       if (p.lse && row < L) p.lse[((size_t)b * p.nh + h) * L + row] = (mx + log2f(sum)) * (1.0f / kLog2e);
       const float inv = p.inv_keep / sum;
-      // ---- epilogue: O row * inv -> bf16 -> this thread's 128 bytes of the head-merged context [B*L, H]
+      // ---- epilogue: O row * inv -> bf16 -> this warp's swizzled 32-row slab -> its own 3-D TMA store (rows >= L
+      //      clipped by the tensor map).  Thread-per-row st.global of the 128-byte rows was tried and is 20-65 %
+      //      slower (16-byte pieces at a 1536-byte stride; profiles/r2_attention_tc_v3_direct_stores_microbench.txt)
       mbar_wait(ofull_bar + 8 * g, (uint32_t)m & 1u);
       tc_fence_after();
       uint32_t r[2][32];
@@ -387,21 +393,31 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
       tc_ld32(tmem_O + 32, r[1]);
       tc_wait_ld();
       tc_fence_before();
-      if (row < L) {
-        uint4* dst = reinterpret_cast<uint4*>(ctx + ((size_t)b * L + row) * ld_ctx + h * D);
+      if (m > 0) {  // this warp's previous store has been read out of the slab
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+      }
+      uint8_t* slab = sSlab + (warp - 4) * C::kSlab;
+      uint8_t* orow = slab + lane * 128;
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
+      for (int c = 0; c < 2; ++c)
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            uint4 v;
-            v.x = pack2(__uint_as_float(r[c][u * 8 + 0]) * inv, __uint_as_float(r[c][u * 8 + 1]) * inv);
-            v.y = pack2(__uint_as_float(r[c][u * 8 + 2]) * inv, __uint_as_float(r[c][u * 8 + 3]) * inv);
-            v.z = pack2(__uint_as_float(r[c][u * 8 + 4]) * inv, __uint_as_float(r[c][u * 8 + 5]) * inv);
-            v.w = pack2(__uint_as_float(r[c][u * 8 + 6]) * inv, __uint_as_float(r[c][u * 8 + 7]) * inv);
-            dst[c * 4 + u] = v;
-          }
+        for (int u = 0; u < 4; ++u) {
+          uint4 v;
+          v.x = pack2(__uint_as_float(r[c][u * 8 + 0]) * inv, __uint_as_float(r[c][u * 8 + 1]) * inv);
+          v.y = pack2(__uint_as_float(r[c][u * 8 + 2]) * inv, __uint_as_float(r[c][u * 8 + 3]) * inv);
+          v.z = pack2(__uint_as_float(r[c][u * 8 + 4]) * inv, __uint_as_float(r[c][u * 8 + 5]) * inv);
+          v.w = pack2(__uint_as_float(r[c][u * 8 + 6]) * inv, __uint_as_float(r[c][u * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + (((c * 4 + u) ^ (lane & 7)) << 4)) = v;
+        }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0 && q4 * 32 < L) {
+        tma_store_3d(&tmO, smem_u32(slab), h * D, q4 * 32, b);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -440,18 +456,20 @@ constexpr int kSmemP = 2 * kTileBytes;  // a [128 q][128 k] bf16 tile: two 64-ke
 constexpr int kBwdStages = 2;
 constexpr int kBwdStageBytes = 4 * kTileBytes;  // Q | K | V | dO
 constexpr int kBwdMaxH = 1024;                  // bias-gradient accumulators [3][H] live in shared memory
-constexpr int kBwdSmem = kBwdStages * kBwdStageBytes + 2 * kSmemP /* Pd, dS */ + 4 * kRows * 4 /* mask, lse, D halves */ +
-                         3 * kBwdMaxH * 4 + 256 + 1024;
+constexpr int kBwdSlab = 32 * 128;              // 32 rows x 64 columns of one gradient tensor: a TMA-store box
+constexpr int kBwdSmem = kBwdStages * kBwdStageBytes + 2 * kSmemP /* Pd, dS */ + 4 * 3 * kBwdSlab /* store slabs */ +
+                         4 * kRows * 4 /* mask, lse, D halves */ + 3 * kBwdMaxH * 4 + 256 + 1024;
 
 template <int NS>  // 16-column sub-chunks of a score row per thread: ceil(n16 / 32)
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                   bf16* __restrict__ dqkv, int ld_qkv, const BwdParams p) {
+                   const __grid_constant__ CUtensorMap tmDQKV, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sPd = smem + kBwdStages * kBwdStageBytes;  // [2 blocks][16 KB]: [q][k] tile, 64 keys per block
   uint8_t* sDS = sPd + kSmemP;
-  float* sMask = reinterpret_cast<float*>(sDS + kSmemP);  // [128] log2 domain
+  uint8_t* sSlab = sDS + kSmemP;                          // [4 row quarters][dQ | dK | dV][32 rows][128 B]
+  float* sMask = reinterpret_cast<float*>(sSlab + 4 * 3 * kBwdSlab);  // [128] log2 domain
   float* sLse = sMask + kRows;                            // [128] log2 domain (+inf for rows >= L)
   float* sD = sLse + kRows;                               // [2][128] partial row sums of the two column halves
   float* sBias = sD + 2 * kRows;                          // [3][H] column sums of dQ | dK | dV over this CTA's items
@@ -467,6 +485,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQKV) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDO) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDQKV) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kBwdStages; ++i) {
@@ -665,11 +684,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pfull_bar);
-      // ---- epilogue: dQ | dK | dV rows (this thread: 32 of the 64 columns) -> bf16 -> this thread's 3 x 64 bytes of
-      //      dqkv [B*L, 3H]; the QKV-bias gradient = column sums of the rounded values, reduced across the warp's
-      //      32 rows by the halving butterfly (31 shuffles per 32 columns) into the CTA's shared accumulators
+      // ---- epilogue: dQ | dK | dV rows (this thread: 32 of the 64 columns) -> bf16 -> the 32-row slab this warp
+      //      shares with its partner (the other column half) -> one 3-D TMA store per tensor and row quarter (rows >= L
+      //      clipped); the QKV-bias gradient = column sums of the rounded values, reduced across the warp's 32 rows by
+      //      the halving butterfly (31 shuffles per 32 columns) into the CTA's shared accumulators
       mbar_wait(gfull_bar, (uint32_t)n & 1u);
       tc_fence_after();
+      if (n > 0) {  // the pair's previous stores have been read out of the slabs
+        if (hf == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q4) : "memory");
+      }
       {
         uint32_t r[2][32];  // double buffered: tensor w + 1 is in flight while w is packed, stored and column-summed
         tc_ld32(tDQ + lane_off + hf * 32, r[0]);
@@ -683,10 +707,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             pk[j] = pack2(__uint_as_float(r[w & 1][2 * j]) * f, __uint_as_float(r[w & 1][2 * j + 1]) * f);
-          if (live) {
-            uint4* dst = reinterpret_cast<uint4*>(dqkv + ((size_t)b * L + row) * ld_qkv + w * H + h * D + hf * 32);
+          {
+            uint8_t* orow = sSlab + (q4 * 3 + w) * kBwdSlab + lane * 128;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) dst[u] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+            for (int u = 0; u < 4; ++u)
+              *reinterpret_cast<uint4*>(orow + (((hf * 4 + u) ^ (lane & 7)) << 4)) =
+                  make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
           }
           if (p.dbias != nullptr) {
             float v[32];
@@ -714,8 +740,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           }
         }
         tc_fence_before();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q4) : "memory");  // both column halves of the slabs are written
+        if (hf == 0 && lane == 0 && q4 * 32 < L) {
+#pragma unroll
+          for (int w = 0; w < 3; ++w)
+            tma_store_3d(&tmDQKV, smem_u32(sSlab + (q4 * 3 + w) * kBwdSlab), w * H + h * D, q4 * 32, b);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
       }
     }
+    if (hf == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     group_sync();  // all shared-memory bias accumulations of this CTA are done
     if (p.dbias != nullptr)
       for (int i = tid; i < 3 * p.H; i += 256) {
@@ -766,7 +801,7 @@ static int make_map3(CUtensorMap* map, const void* base, int cols, int L, int B,
 
 // Returns 1 when this path does not apply (the caller falls back to the mma.sync kernel), 0 on success, < 0 on error.
 template <int R>
-static int launch_fwd_tc(const CUtensorMap& tq, void* ctx, int ld_ctx, const mvptr::attn_tc::Params& p, cudaStream_t stream) {
+static int launch_fwd_tc(const CUtensorMap& tq, const CUtensorMap& to, const mvptr::attn_tc::Params& p, cudaStream_t stream) {
   using namespace mvptr;
   using namespace mvptr::attn_tc;
   auto kern = attn_fwd_tc_kernel<R>;
@@ -778,7 +813,7 @@ static int launch_fwd_tc(const CUtensorMap& tq, void* ctx, int ld_ctx, const mvp
   }
   static_assert(FwdCfg<R>::kSmem <= 227 * 1024, "shared memory budget");
   const int grid = p.items < kNumSMs ? p.items : kNumSMs;
-  kern<<<grid, kThreads, FwdCfg<R>::kSmem, stream>>>(tq, (bf16*)ctx, ld_ctx, p);
+  kern<<<grid, kThreads, FwdCfg<R>::kSmem, stream>>>(tq, to, p);
   MVPTR_CHECK_LAUNCH("attn_fwd_tc");
   return 0;
 }
@@ -791,8 +826,9 @@ int mvptr_attn_fwd_tc(const void* qkv, int ld_qkv, const float* maskadd, void* c
                               !(getenv("MVPTR_ATTN_FWD_TC") && atoi(getenv("MVPTR_ATTN_FWD_TC")) == 0);
   if (!enabled || L > kRows || (reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(ctx) & 15)) return 1;
   const int R = L <= 64 ? 64 : L <= 96 ? 96 : 128;
-  CUtensorMap tq;
+  CUtensorMap tq, to;
   if (int rc = make_map3(&tq, qkv, 3 * H, L, B, ld_qkv, R)) return rc;
+  if (int rc = make_map3(&to, ctx, H, L, B, ld_ctx, 32)) return rc;  // one warp's 32 rows per store box
   Params p;
   p.maskadd = maskadd;
   p.lse = lse;
@@ -803,13 +839,13 @@ int mvptr_attn_fwd_tc(const void* qkv, int ld_qkv, const float* maskadd, void* c
   p.keep_thr = keep_threshold(p_drop);
   p.inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   p.seed = seed;
-  if (R == 64) return launch_fwd_tc<64>(tq, ctx, ld_ctx, p, stream);
-  if (R == 96) return launch_fwd_tc<96>(tq, ctx, ld_ctx, p, stream);
-  return launch_fwd_tc<128>(tq, ctx, ld_ctx, p, stream);
+  if (R == 64) return launch_fwd_tc<64>(tq, to, p, stream);
+  if (R == 96) return launch_fwd_tc<96>(tq, to, p, stream);
+  return launch_fwd_tc<128>(tq, to, p, stream);
 }
 
 template <int NS>
-static int launch_bwd_tc(const CUtensorMap& tq, const CUtensorMap& tdo, void* dqkv, int ld_qkv,
+static int launch_bwd_tc(const CUtensorMap& tq, const CUtensorMap& tdo, const CUtensorMap& tdq,
                          const mvptr::attn_tc::BwdParams& p, cudaStream_t stream) {
   using namespace mvptr;
   using namespace mvptr::attn_tc;
@@ -821,7 +857,7 @@ static int launch_bwd_tc(const CUtensorMap& tq, const CUtensorMap& tdo, void* dq
     configured = true;
   }
   const int grid = p.items < kNumSMs ? p.items : kNumSMs;
-  kern<<<grid, kThreads, kBwdSmem, stream>>>(tq, tdo, (bf16*)dqkv, ld_qkv, p);
+  kern<<<grid, kThreads, kBwdSmem, stream>>>(tq, tdo, tdq, p);
   MVPTR_CHECK_LAUNCH("attn_bwd_tc");
   return 0;
 }
@@ -838,9 +874,10 @@ int mvptr_attn_bwd_tc(const void* qkv, int ld_qkv, const float* maskadd, const v
                                  reinterpret_cast<uintptr_t>(dqkv)) & 15))
     return 1;
   if (H > kBwdMaxH) return 1;
-  CUtensorMap tq, tdo;
+  CUtensorMap tq, tdo, tdq;
   if (int rc = make_map3(&tq, qkv, 3 * H, L, B, ld_qkv)) return rc;
   if (int rc = make_map3(&tdo, dctx, H, L, B, ld_ctx)) return rc;
+  if (int rc = make_map3(&tdq, dqkv, 3 * H, L, B, ld_qkv, 32)) return rc;  // 32-row store boxes
   BwdParams p;
   p.maskadd = maskadd;
   p.lse = lse;
@@ -854,9 +891,9 @@ int mvptr_attn_bwd_tc(const void* qkv, int ld_qkv, const float* maskadd, const v
   p.inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   p.seed = seed;
   switch ((p.n16 + 31) >> 5) {
-    case 1: return launch_bwd_tc<1>(tq, tdo, dqkv, ld_qkv, p, stream);
-    case 2: return launch_bwd_tc<2>(tq, tdo, dqkv, ld_qkv, p, stream);
-    case 3: return launch_bwd_tc<3>(tq, tdo, dqkv, ld_qkv, p, stream);
-    default: return launch_bwd_tc<4>(tq, tdo, dqkv, ld_qkv, p, stream);
+    case 1: return launch_bwd_tc<1>(tq, tdo, tdq, p, stream);
+    case 2: return launch_bwd_tc<2>(tq, tdo, tdq, p, stream);
+    case 3: return launch_bwd_tc<3>(tq, tdo, tdq, p, stream);
+    default: return launch_bwd_tc<4>(tq, tdo, tdq, p, stream);
   }
 }
