@@ -457,8 +457,8 @@ constexpr int kBwdStages = 2;
 constexpr int kBwdStageBytes = 4 * kTileBytes;  // Q | K | V | dO
 constexpr int kBwdMaxH = 1024;                  // bias-gradient accumulators [3][H] live in shared memory
 constexpr int kBwdSlab = 32 * 128;              // 32 rows x 64 columns of one gradient tensor: a TMA-store box
-constexpr int kBwdSmem = kBwdStages * kBwdStageBytes + 2 * kSmemP /* Pd, dS */ + 4 * 3 * kBwdSlab /* store slabs */ +
-                         4 * kRows * 4 /* mask, lse, D halves */ + 3 * kBwdMaxH * 4 + 256 + 1024;
+constexpr int kBwdSmem = kBwdStages * kBwdStageBytes + 2 * kSmemP /* Pd, dS */ + 4 * kRows * 4 /* mask, lse, D halves */ +
+                         3 * kBwdMaxH * 4 + 256 + 1024;
 
 template <int NS>  // 16-column sub-chunks of a score row per thread: ceil(n16 / 32)
 __global__ void __launch_bounds__(kThreads, 1)
@@ -468,8 +468,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sPd = smem + kBwdStages * kBwdStageBytes;  // [2 blocks][16 KB]: [q][k] tile, 64 keys per block
   uint8_t* sDS = sPd + kSmemP;
-  uint8_t* sSlab = sDS + kSmemP;                          // [4 row quarters][dQ | dK | dV][32 rows][128 B]
-  float* sMask = reinterpret_cast<float*>(sSlab + 4 * 3 * kBwdSlab);  // [128] log2 domain
+  float* sMask = reinterpret_cast<float*>(sDS + kSmemP);  // [128] log2 domain
   float* sLse = sMask + kRows;                            // [128] log2 domain (+inf for rows >= L)
   float* sD = sLse + kRows;                               // [2][128] partial row sums of the two column halves
   float* sBias = sD + 2 * kRows;                          // [3][H] column sums of dQ | dK | dV over this CTA's items
@@ -490,7 +489,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kBwdStages; ++i) {
       mbar_init(full_bar + 8 * i, 1);
-      mbar_init(empty_bar + 8 * i, 1);
+      mbar_init(empty_bar + 8 * i, 4);  // the four warp pairs, each once its gradient stores have read the stage
     }
     mbar_init(sfull_bar, 1);
     mbar_init(pfull_bar, 8);
@@ -570,7 +569,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           tc_mma(tDQ, make_desc(sds + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
                  make_desc(sk + k * 2048, 64 * 128, 1024), idesc_dq, k > 0 ? 1u : 0u);
         tc_commit(gfull_bar);
-        tc_commit(empty_bar + 8 * st);        // Q, K, V, dO of this stage are dead once the gradient MMAs retire
         if (n + 1 < n_local) issue_s(n + 1);  // overlaps the epilogue of item n
       }
     }
@@ -690,10 +688,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       //      the halving butterfly (31 shuffles per 32 columns) into the CTA's shared accumulators
       mbar_wait(gfull_bar, (uint32_t)n & 1u);
       tc_fence_after();
-      if (n > 0) {  // the pair's previous stores have been read out of the slabs
-        if (hf == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        asm volatile("bar.sync %0, 64;" ::"r"(2 + q4) : "memory");
-      }
+      // store slabs = this warp pair's 32 rows of the item's dead Q | K | V tiles (all MMAs that read them have retired)
+      uint8_t* stg = smem + st * kBwdStageBytes;
       {
         uint32_t r[2][32];  // double buffered: tensor w + 1 is in flight while w is packed, stored and column-summed
         tc_ld32(tDQ + lane_off + hf * 32, r[0]);
@@ -708,7 +704,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           for (int j = 0; j < 16; ++j)
             pk[j] = pack2(__uint_as_float(r[w & 1][2 * j]) * f, __uint_as_float(r[w & 1][2 * j + 1]) * f);
           {
-            uint8_t* orow = sSlab + (q4 * 3 + w) * kBwdSlab + lane * 128;
+            uint8_t* orow = stg + w * kTileBytes + q4 * kBwdSlab + lane * 128;
 #pragma unroll
             for (int u = 0; u < 4; ++u)
               *reinterpret_cast<uint4*>(orow + (((hf * 4 + u) ^ (lane & 7)) << 4)) =
@@ -742,11 +738,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         tc_fence_before();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync %0, 64;" ::"r"(2 + q4) : "memory");  // both column halves of the slabs are written
-        if (hf == 0 && lane == 0 && q4 * 32 < L) {
+        if (hf == 0 && lane == 0) {
+          if (q4 * 32 < L) {
 #pragma unroll
-          for (int w = 0; w < 3; ++w)
-            tma_store_3d(&tmDQKV, smem_u32(sSlab + (q4 * 3 + w) * kBwdSlab), w * H + h * D, q4 * 32, b);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            for (int w = 0; w < 3; ++w)
+              tma_store_3d(&tmDQKV, smem_u32(stg + w * kTileBytes + q4 * kBwdSlab), w * H + h * D, q4 * 32, b);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+          mbar_arrive(empty_bar + 8 * st);  // this pair is done with the stage
         }
       }
     }
