@@ -167,6 +167,11 @@ int mvptr_cast_f32_bf16(const float* src, void* dst, size_t n, void* stream);
 int mvptr_cast_bf16_f32(const void* src, float* dst, size_t n, int max_ctas, void* stream);
 int mvptr_add_cast(const float* a, const void* b, void* d, size_t n, void* stream);
 
+/* Which attention kernels run for L <= 128: the tcgen05 / TMA / TMEM kernels of csrc/attention_tc.cu or the mma.sync
+ * kernels of csrc/attention.cu (the only ones for 128 < L <= 256).  Per direction: -1 follow MVPTR_ATTN_FWD_TC /
+ * MVPTR_ATTN_BWD_TC, 0 auto (the faster one per shape, as measured), 1 tcgen05, 2 mma.sync.  Both families implement the
+ * same entry points below bit-compatibly in their dropout masks, so forward and backward may use different families. */
+int mvptr_attn_set_path(int fwd_mode, int bwd_mode);
 /* ---- fused masked attention, head_dim 64, L <= 256 ---------------------------------
  * ctx = dropout(softmax(q k^T / 8 + maskadd)) v per head, reading the fused QKV projection
  * [B*L, 3H] and writing head-merged context [B*L, H].  Replaces CaptionBertSelfAttention.forward

@@ -73,6 +73,7 @@ SIGNATURES = {
     "mvptr_cast_f32_bf16": "ppzp",
     "mvptr_add_cast": "pppzp",
     "mvptr_cast_bf16_f32": "ppzip",
+    "mvptr_attn_set_path": "ii",
     "mvptr_attn_fwd": "pippip" + "iiii" + "fup",
     "mvptr_attn_bwd": "pipppippp" + "iiii" + "fup",
     "mvptr_ce_fwd": "pipiiipppp",
@@ -148,6 +149,13 @@ class LaunchProfiler:
 
 
 PROFILER = None
+
+
+def set_attention_path(fwd="auto", bwd="auto"):
+    """Attention kernel family per direction for L <= 128: 'auto' (the faster one per shape, as measured), 'tc'
+    (tcgen05 / TMA / TMEM, csrc/attention_tc.cu), 'mma' (mma.sync, csrc/attention.cu), 'env' (MVPTR_ATTN_*_TC)."""
+    m = {"env": -1, "auto": 0, "tc": 1, "mma": 2}
+    check(lib().mvptr_attn_set_path(m[fwd], m[bwd]), "mvptr_attn_set_path")
 
 
 def set_gemm_max_ctas(n):

@@ -800,6 +800,22 @@ static int make_map3(CUtensorMap* map, const void* base, int cols, int L, int B,
 }  // namespace mvptr
 
 // Returns 1 when this path does not apply (the caller falls back to the mma.sync kernel), 0 on success, < 0 on error.
+// kernel selection: -1 = follow the environment (MVPTR_ATTN_FWD_TC / MVPTR_ATTN_BWD_TC: unset or "auto" = 0, "1" = tcgen05,
+// "0" = mma.sync), otherwise the mode set through mvptr_attn_set_path
+static int g_fwd_mode = -1, g_bwd_mode = -1;
+static int env_mode(const char* name) {
+  const char* v = getenv(name);
+  if (!v || !*v || v[0] == 'a') return 0;
+  return atoi(v) != 0 ? 1 : 2;
+}
+extern "C" int mvptr_attn_set_path(int fwd_mode, int bwd_mode) {
+  if (fwd_mode < -1 || fwd_mode > 2 || bwd_mode < -1 || bwd_mode > 2)
+    MVPTR_FAIL(MVPTR_ERR_ARG, "attn_set_path: modes are -1 (environment), 0 (auto), 1 (tcgen05), 2 (mma.sync)");
+  g_fwd_mode = fwd_mode;
+  g_bwd_mode = bwd_mode;
+  return 0;
+}
+
 template <int R>
 static int launch_fwd_tc(const CUtensorMap& tq, const CUtensorMap& to, const mvptr::attn_tc::Params& p, cudaStream_t stream) {
   using namespace mvptr;
@@ -822,9 +838,12 @@ int mvptr_attn_fwd_tc(const void* qkv, int ld_qkv, const float* maskadd, void* c
                       int nh, int H, float p_drop, uint32_t seed, cudaStream_t stream) {
   using namespace mvptr;
   using namespace mvptr::attn_tc;
-  static const bool enabled = !(getenv("MVPTR_ATTN_TC") && atoi(getenv("MVPTR_ATTN_TC")) == 0) &&
-                              !(getenv("MVPTR_ATTN_FWD_TC") && atoi(getenv("MVPTR_ATTN_FWD_TC")) == 0);
-  if (!enabled || L > kRows || (reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(ctx) & 15)) return 1;
+  // 0 = auto (the measured choice, profiles/r2_attention_tc_v4_microbench.txt: the tcgen05 kernel where it is at least
+  // as fast as the mma.sync one -- the 80 < L <= 96 class, i.e. the cross-modal encoder of the pre-training step),
+  // 1 = tcgen05 for every L <= 128, 2 = mma.sync only.  mvptr_attn_set_path / MVPTR_ATTN_FWD_TC select it.
+  const int mode = g_fwd_mode >= 0 ? g_fwd_mode : env_mode("MVPTR_ATTN_FWD_TC");
+  const bool use = mode == 1 ? true : mode == 2 ? false : (L > 80 && L <= 96);
+  if (!use || L > kRows || (reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(ctx) & 15)) return 1;
   const int R = L <= 64 ? 64 : L <= 96 ? 96 : 128;
   CUtensorMap tq, to;
   if (int rc = make_map3(&tq, qkv, 3 * H, L, B, ld_qkv, R)) return rc;
@@ -868,10 +887,10 @@ int mvptr_attn_bwd_tc(const void* qkv, int ld_qkv, const float* maskadd, const v
                       cudaStream_t stream) {
   using namespace mvptr;
   using namespace mvptr::attn_tc;
-  static const bool enabled = !(getenv("MVPTR_ATTN_TC") && atoi(getenv("MVPTR_ATTN_TC")) == 0) &&
-                              !(getenv("MVPTR_ATTN_BWD_TC") && atoi(getenv("MVPTR_ATTN_BWD_TC")) == 0);
-  if (!enabled || L > kRows || ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(dctx) |
-                                 reinterpret_cast<uintptr_t>(dqkv)) & 15))
+  // auto = mma.sync: the tcgen05 backward is parity-green but 5-15 % slower at the step's shapes (same profile file)
+  const int mode = g_bwd_mode >= 0 ? g_bwd_mode : env_mode("MVPTR_ATTN_BWD_TC");
+  if (mode != 1 || L > kRows || ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(dctx) |
+                                  reinterpret_cast<uintptr_t>(dqkv)) & 15))
     return 1;
   if (H > kBwdMaxH) return 1;
   CUtensorMap tq, tdo, tdq;

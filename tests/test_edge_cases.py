@@ -26,10 +26,12 @@ def _attn_ref(qkv, maskadd, B, L, nh, H):
     return (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * L, H)
 
 
-@pytest.mark.parametrize("L", [1, 2, 255, 256])
-def test_attention_extreme_lengths_and_fully_masked_keys(lib, L):
+@pytest.mark.parametrize("path", ["tc", "mma"])
+@pytest.mark.parametrize("L", [1, 2, 17, 64, 65, 96, 97, 127, 128, 255, 256])
+def test_attention_extreme_lengths_and_fully_masked_keys(lib, L, path):
     """L = 1 and the maximum L = 256; batch row 1 has EVERY key masked: the reference's additive -10000 then
     cancels in the softmax and the row attends uniformly-by-score to all keys (modeling_vlbert.py:430-460)."""
+    lib.set_attention_path(path, path)  # tcgen05 kernels (L <= 128; tile-row classes 64 / 96 / 128) and mma.sync kernels
     B, nh = 2, 2
     H = nh * 64
     g = torch.Generator(device="cuda").manual_seed(L)
@@ -51,6 +53,7 @@ def test_attention_extreme_lengths_and_fully_masked_keys(lib, L):
     assert torch.isfinite(dqkv.float()).all()
     rel = ((dqkv.float() - x.grad).norm() / (x.grad.norm() + 1e-12)).item()
     assert rel < 3e-2, f"attn bwd rel l2 {rel} at L={L}"
+    lib.set_attention_path("auto", "auto")
 
 
 def test_attention_rejects_unsupported_shapes(lib):

@@ -171,8 +171,16 @@ def attn_ref(qkv, maskadd, B, L, nh, H):
     return (p @ v).permute(0, 2, 1, 3).reshape(B * L, H)
 
 
+@pytest.fixture(params=["auto", "tc", "mma"])
+def attn_path(request, lib):
+    """Every attention test runs on the tcgen05 kernels (L <= 128), on the mma.sync kernels, and on the default mix."""
+    lib.set_attention_path(request.param, request.param)
+    yield request.param
+    lib.set_attention_path("auto", "auto")
+
+
 @pytest.mark.parametrize("L", [7, 16, 35, 40, 70, 90, 105, 128, 133, 183, 193])
-def test_attention_fwd_bwd(lib, L):
+def test_attention_fwd_bwd(lib, L, attn_path):
     B, nh = 3, 12
     H = nh * 64
     qkv = rnd(B * L, 3 * H, seed=L)
@@ -196,7 +204,7 @@ def test_attention_fwd_bwd(lib, L):
     assert_close(dqkv, x.grad, 3e-2, 3e-2, "attn bwd")
 
 
-def test_attention_dropout_consistency(lib):
+def test_attention_dropout_consistency(lib, attn_path):
     """fwd and bwd regenerate the same keep mask: check d(ctx)/dV against finite structure."""
     B, L, nh = 2, 40, 2
     H = nh * 64
@@ -220,7 +228,7 @@ def test_attention_dropout_consistency(lib):
 
 
 @pytest.mark.parametrize("L", [40, 90, 150])
-def test_attention_dropout_matches_autograd_with_the_extracted_mask(lib, L):
+def test_attention_dropout_matches_autograd_with_the_extracted_mask(lib, L, attn_path):
     """The keep mask depends only on (seed, batch, head, query, key): extract it by pushing one-hot V
     columns through the forward kernel, then check forward AND backward (dQ, dK, dV) against torch
     autograd using that exact mask.  L=40/90 run the shared-memory backward, L=150 the recompute one."""

@@ -200,6 +200,17 @@ def test_pretrain_tiny_losses_and_grads_match_reference_golden(golden_dir):
         assert float(params[k].grad.abs().max()) == 0.0
 
 
+def test_pretrain_tiny_with_tcgen05_attention_forward_and_backward(golden_dir):
+    """The same step with BOTH attention directions forced onto the tcgen05 / TMA / TMEM kernels (csrc/attention_tc.cu;
+    by default the dispatcher picks the faster family per shape, profiles/r2_attention_tc_v4_microbench.txt)."""
+    from mvp_pytorch_b200 import _lib
+    _lib.set_attention_path("tc", "tc")
+    try:
+        test_pretrain_tiny_losses_and_grads_match_reference_golden(golden_dir)
+    finally:
+        _lib.set_attention_path("auto", "auto")
+
+
 def test_pretrain_hard_phrase_mode_and_qa_match_reference_golden(golden_dir):
     """phrase_mod='hard' (modeling_vlbert.py:1270-1283) + qa_ans with ignored (-1) labels (:1260-1264): 7 losses
     and gradients against the reference (tests/golden/r2_tiny.pt, oracle/make_golden_r2.py)."""
