@@ -380,8 +380,9 @@ def run_b200(args):
     arena = rt.arena
     if world > 1:  # bucketed gradient all-reduce on a side stream, overlapped with backward
         from mvp_pytorch_b200.parallel import allreduce_gradients, enable_overlapped_allreduce
-        # gradients travel as bf16 (fp32 in the arena); MVPTR_DP_REDUCE=fp32 / MVPTR_DP_MIN_BUCKET are A/B knobs
-        rd = torch.float32 if os.environ.get("MVPTR_DP_REDUCE", "bf16") == "fp32" else torch.bfloat16
+        # default "tail-bf16": overlapped per-layer buckets fp32 in place, the exposed tail as bf16 (parallel.GradientSync);
+        # MVPTR_DP_REDUCE=fp32 | bf16 and MVPTR_DP_MIN_BUCKET are A/B knobs
+        rd = {"fp32": torch.float32, "bf16": torch.bfloat16}.get(os.environ.get("MVPTR_DP_REDUCE", "tail-bf16"), "tail-bf16")
         enable_overlapped_allreduce(model, reduce_dtype=rd, min_bucket=int(os.environ.get("MVPTR_DP_MIN_BUCKET", str(1 << 16))))
 
     n_batches = 4
@@ -584,7 +585,7 @@ def run_b200(args):
                                "dropout 0.1, BASELINE.json configs[1]",
                    "batch_per_gpu": B, "global_batch": B * world, "text_phrase_len": W["La"], "tags": W["Lt"],
                    "regions": W["R"], "img_dim": W["img_dim"], "parallelism": f"dp{world}",
-                   "gradient_allreduce": None if world == 1 else os.environ.get("MVPTR_DP_REDUCE", "bf16") + " on the wire, fp32 arena, overlapped with backward",
+                   "gradient_allreduce": None if world == 1 else os.environ.get("MVPTR_DP_REDUCE", "tail-bf16") + " (per-layer buckets overlapped with backward; fp32 arena)",
                    "master_weights": "fp32", "cuda_graph": graphed_was_used, "l2": "inputs larger than L2: per-step working set (~11 GB activations, "
                                                     "2.4 GB weights/grads/moments) >> 126 MB L2, 4 rotating batches"},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",

@@ -65,11 +65,16 @@ class GradientSync:
     communication stream.  ``finish()`` reduces whatever was not covered and joins the streams.
     Every rank runs the same model, so the collective order is identical everywhere.
 
-    ``reduce_dtype=torch.bfloat16`` (default on CUDA) halves the bytes on NVLink -- what SURVEY 2b specifies and
-    what the reference's DeepSpeed fp16 configuration does (tmp_config.json: fp16 gradients): on the communication
-    stream each range is narrowed into a bf16 staging arena (mvptr_cast_f32_bf16), all-reduced there, and widened
-    back into the fp32 gradient arena (mvptr_cast_bf16_f32), so ``p.grad``, clip_grad_norm_ and the fused AdamW keep
-    seeing fp32 averaged gradients.  ``torch.float32`` reduces the arena in place.
+    ``reduce_dtype``: ``torch.bfloat16`` halves the bytes on NVLink -- what SURVEY 2b specifies and what the
+    reference's DeepSpeed fp16 configuration does (tmp_config.json: fp16 gradients): on the communication stream a
+    range is narrowed into a bf16 staging arena (mvptr_cast_f32_bf16), all-reduced there, and widened back into the
+    fp32 gradient arena (mvptr_cast_bf16_f32), so ``p.grad``, clip_grad_norm_ and the fused AdamW keep seeing fp32
+    averaged gradients.  ``torch.float32`` reduces the arena in place.  The default on CUDA is ``"tail-bf16"``, the
+    measured best of both (profiles/r2_dp_ab_n2.txt): the per-layer buckets, which run UNDER the backward GEMMs, go
+    in place as fp32 -- their wire time is hidden anyway and the two cast kernels per bucket only took SM time from
+    the GEMMs (N = 2: 32.5 ms fp32 vs 33.0 ms bf16 per step) -- while what is left for ``finish()``, above all the
+    264 MB word-embedding gradient that is final only when backward ends and whose transfer is therefore EXPOSED,
+    travels as bf16.
 
     Ranges below ``min_bucket`` elements (the per-layer bias / LayerNorm slices, ~10 k elements each) are not sent
     on their own -- a collective of a few KB is pure launch latency -- but left to ``finish()``, which sends all
@@ -81,10 +86,11 @@ class GradientSync:
         self.stream = torch.cuda.Stream() if arena.device.type == "cuda" else None
         self.enabled = world()[1] > 1
         if reduce_dtype is None:
-            reduce_dtype = torch.bfloat16 if arena.device.type == "cuda" else torch.float32
-        if reduce_dtype not in (torch.bfloat16, torch.float32):
-            raise ValueError("reduce_dtype must be torch.bfloat16 or torch.float32")
+            reduce_dtype = "tail-bf16" if arena.device.type == "cuda" else torch.float32
+        if reduce_dtype not in (torch.bfloat16, torch.float32, "tail-bf16"):
+            raise ValueError("reduce_dtype must be torch.bfloat16, torch.float32 or 'tail-bf16'")
         self.reduce_dtype = reduce_dtype
+        self._in_finish = False
         self.min_bucket = int(min_bucket)
         self.staging = None  # bf16 arena-shaped staging buffer, allocated on first use
         # grid cap of the widening cast (0 = none).  A narrow grid looked polite but is not: capped at 32 CTAs each
@@ -102,7 +108,7 @@ class GradientSync:
         ev.record()
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ev)
-            if self.reduce_dtype == torch.float32:
+            if self.reduce_dtype == torch.float32 or (self.reduce_dtype == "tail-bf16" and not self._in_finish):
                 dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
                 return
             from . import _lib
@@ -132,12 +138,16 @@ class GradientSync:
         if not self.enabled:
             return
         pos = 0
-        for lo, hi in sorted(self.done):
-            if lo > pos:
-                self._reduce(pos, lo)
-            pos = max(pos, hi)
-        if pos < self.arena.numel:
-            self._reduce(pos, self.arena.numel)
+        self._in_finish = True
+        try:
+            for lo, hi in sorted(self.done):
+                if lo > pos:
+                    self._reduce(pos, lo)
+                pos = max(pos, hi)
+            if pos < self.arena.numel:
+                self._reduce(pos, self.arena.numel)
+        finally:
+            self._in_finish = False
         self.done = []
         if self.stream is not None:
             torch.cuda.current_stream().wait_stream(self.stream)
