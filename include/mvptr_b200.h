@@ -303,6 +303,25 @@ int mvptr_topk_rows(const float* x, long long ld, int rows, int n, int k, int64_
 /* softmax(logits)[:,1] of the 2-way ITM classifier (run_retrieval.py:776-777, 818-820) */
 int mvptr_match_prob(const float* logits, float* prob, int n, void* stream);
 
+/* ---- input pipeline (SURVEY f-2; csrc/data_prep.cu) -------------------------------------------------
+ * Region features as the reference's TSV files hold them: base64 text of float32[num_boxes, K] per sample
+ * (oscar_datasets_ml/oscar_tsv4.py:696-727: np.frombuffer(base64.b64decode(..), float32).reshape(num_boxes, K) ->
+ * torch.tensor(dtype)), zero-padded to R rows.  src = the samples' texts back to back, offsets[B+1] their byte
+ * offsets; dst [B, R, ld_dst] bf16 or fp32 (rows >= num_boxes and columns >= K zeroed).  max_boxes >= max(num_boxes)
+ * sizes the grid.  error_flag (device int, caller-zeroed): bit 0 length mismatch, bit 1 invalid character, bit 2
+ * misplaced padding. */
+int mvptr_b64_decode_features(const void* src, const int64_t* offsets, const int32_t* num_boxes, void* dst,
+                              int dst_is_f32, int B, int R, int K, int ld_dst, int max_boxes, int* error_flag,
+                              void* stream);
+/* BERT token masking (random_word, oscar_tsv4.py:782-820) and phrase masking (random_phrases, :822-850, labels
+ * dropped by :960) in place on ids [B, L]; labels [B, L] receives the original id at selected token positions, -1
+ * elsewhere.  u [B, L] uniforms / r [B, L] non-negative integer draws replay recorded random numbers (nullable:
+ * hash of seed).  links [B, L, max_links] int32 (nullable): phrase indexes tied to caption token i, -1 padded. */
+int mvptr_mlm_mask(int64_t* ids, int64_t* labels, const int32_t* tok_first, const int32_t* tok_count,
+                   const int32_t* phr_first, const int32_t* phr_count, const int32_t* links, int max_links,
+                   const float* u, const int64_t* r, int B, int L, long long mask_id, long long word_vocab,
+                   long long phrase_vocab, long long vocab_size, uint32_t seed, void* stream);
+
 /* ---- fp32 verification tier (csrc/fp32_tier.cu) ---------------------------------------------
  * north_star: "bit-exact for token/region indexing, masking and top-k ranking order under fp32", "1e-4 in fp32".
  * The reference computes in fp32 by default (oscar/tmp_config_FP32.json; run_retrieval.py:1047 halves only on a flag).

@@ -99,6 +99,8 @@ SIGNATURES = {
     "mvptr_gelu_bwd": "pppzp",
     "mvptr_bce_fwd": "pipiipp",
     "mvptr_bce_bwd": "pipiippip",
+    "mvptr_b64_decode_features": "pppp" + "iiiiii" + "pp",
+    "mvptr_mlm_mask": "ppppppp" + "i" + "pp" + "ii" + "llll" + "up",
     # fp32 verification tier (csrc/fp32_tier.cu)
     "mvptr_f32_split3": "pliipppip",
     "mvptr_f32_ln_fwd": "ppppp" + "il" + "ppp" + "iif" + "p",
