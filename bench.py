@@ -28,13 +28,22 @@ sys.path.insert(0, ROOT)
 # grow allocator segments by virtual-memory mapping instead of cudaMalloc/cudaFree (which synchronise):
 # the number of masked-LM rows is data dependent, so buffer sizes vary a little from step to step
 os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
-# stdout carries the ONE JSON line; NCCL's communicator-init lines ("ncclCommInitRank ... nranks N") go to stderr,
-# where the driver checks that every rank joined one communicator of the expected size
+# stdout carries the ONE JSON line and nothing else: keep a private handle on the real stdout for it and point
+# descriptor 1 at stderr, so that NCCL's own lines (it logs to stdout: version, "ncclCommInitRank ... nranks N",
+# the NVLS / ring / tree channel setup) and anything a library prints land on stderr, in order, for every rank
+# (done in _claim_stdout(), only when bench.py is the program: tools and tests import this module)
+_JSON_OUT = sys.stdout
 os.environ.setdefault("NCCL_DEBUG", "INFO")
 os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import torch  # noqa: E402
+
+
+def _claim_stdout():
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
 WORK = dict(B=256, La=40, Lt=20, R=50, n_phrase=5, H=768, I=3072, layers=6, heads=12, vocab=86051,
             only_word=30522, img_dim=2054, p_drop=0.1, mlm_prob=0.15)
@@ -346,7 +355,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------
@@ -523,7 +532,7 @@ def run_b200(args):
             ms_r, _ = timed(lambda i: train_step(resident[i % n_batches]), args.steps)
             res["resident_again_ms_per_step"] = ms_r / args.steps
         if rank == 0:
-            print(json.dumps(res), flush=True)
+            print(json.dumps(res), file=_JSON_OUT, flush=True)
         if graphed is not None:
             torch.cuda.synchronize()
             graphed.release()
@@ -619,7 +628,7 @@ def run_b200(args):
         line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
                                 "sample": f"oracle port of BiBertImgForPreTraining fwd+bwd (fp32), batch 8, "
                                           f"median of 3 after 1 warm-up ({t:.2f} s/step)"}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
     _shutdown(world)
 
 
@@ -681,4 +690,5 @@ def main():
 
 
 if __name__ == "__main__":
+    _claim_stdout()
     main()

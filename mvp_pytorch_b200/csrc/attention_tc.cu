@@ -16,7 +16,7 @@
 //            (staged in the item's dead Q tile) whose bounds check clips the rows >= L.
 // The first version had ONE softmax warpgroup and a two-pass row: correct, but the serial chain per item (8 TMEM
 // round trips, the PV latency, two barriers) made it latency bound at ~2.6 us per head -- slower than the mma.sync
-// kernel (profiles/r2_attention_tc.txt).  Two groups overlap each other's latencies; S(n + 2) is issued as soon as
+// kernel (profiles/r2_attention_tc_v4_microbench.txt).  Two groups overlap each other's latencies; S(n + 2) is issued as soon as
 // group n & 1 has consumed S(n), so tensor work and TMA latency hide behind the softmax warps.
 // Scores never touch HBM; lse [B, nh, L] is saved for the backward kernel; the dropout mask is the stateless hash of
 // common.cuh with the SAME element indexing as attention.cu, so its backward regenerates the mask bit for bit.
