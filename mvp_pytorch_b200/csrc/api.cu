@@ -73,15 +73,18 @@ extern "C" int mvptr_set_epoch_gemm(const uint32_t*, void*);
 extern "C" int mvptr_set_epoch_rows(const uint32_t*, void*);
 extern "C" int mvptr_set_epoch_attn(const uint32_t*, void*);
 extern "C" int mvptr_set_epoch_wra(const uint32_t*, void*);
+extern "C" int mvptr_set_epoch_attn_tc(const uint32_t*, void*);
 extern "C" int mvptr_set_epoch_gemm_addr(uint32_t**);
 extern "C" int mvptr_set_epoch_rows_addr(uint32_t**);
 extern "C" int mvptr_set_epoch_attn_addr(uint32_t**);
 extern "C" int mvptr_set_epoch_wra_addr(uint32_t**);
+extern "C" int mvptr_set_epoch_attn_tc_addr(uint32_t**);
 // src: device or PINNED host pointer (read when the copy executes, i.e. at graph replay time)
 extern "C" int mvptr_set_dropout_epoch(const uint32_t* src, void* stream) {
   if (int rc = mvptr_set_epoch_gemm(src, stream)) return rc;
   if (int rc = mvptr_set_epoch_rows(src, stream)) return rc;
   if (int rc = mvptr_set_epoch_wra(src, stream)) return rc;
+  if (int rc = mvptr_set_epoch_attn_tc(src, stream)) return rc;  // every translation unit that hashes dropout masks
   return mvptr_set_epoch_attn(src, stream);
 }
 
@@ -92,7 +95,8 @@ namespace mvptr {
 // replays that have executed.  The host may run any number (< slots) of replays ahead: replay n always reads
 // slot n, never "whatever the host wrote last" (which is what per-replay memcpy nodes from one host word did).
 __global__ void step_params_kernel(const uint32_t* __restrict__ ring, uint32_t slots, uint32_t* __restrict__ counter,
-                                   float* __restrict__ dyn, uint32_t* e0, uint32_t* e1, uint32_t* e2, uint32_t* e3) {
+                                   float* __restrict__ dyn, uint32_t* e0, uint32_t* e1, uint32_t* e2, uint32_t* e3,
+                                   uint32_t* e4) {
   const uint32_t n = *counter;
   const uint32_t* s = ring + (size_t)(n % slots) * 4;
   uint32_t lr, st, ep;
@@ -107,6 +111,7 @@ __global__ void step_params_kernel(const uint32_t* __restrict__ ring, uint32_t s
   *e1 = ep;
   *e2 = ep;
   *e3 = ep;
+  *e4 = ep;
   *counter = n + 1;
 }
 }  // namespace mvptr
@@ -122,17 +127,18 @@ extern "C" int mvptr_step_params(const void* ring, int slots, uint32_t* counter,
   else if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)
     MVPTR_FAIL(MVPTR_ERR_ARG, "step_params: the ring must be pinned host memory or device memory");
   if (!dev_ring) MVPTR_FAIL(MVPTR_ERR_ARG, "step_params: pinned ring has no device mapping");
-  static uint32_t* addr[4] = {nullptr, nullptr, nullptr, nullptr};
+  static uint32_t* addr[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   if (!addr[0]) {
-    uint32_t* a[4];
+    uint32_t* a[5];
     if (int rc = mvptr_set_epoch_gemm_addr(&a[0])) return rc;
     if (int rc = mvptr_set_epoch_rows_addr(&a[1])) return rc;
     if (int rc = mvptr_set_epoch_attn_addr(&a[2])) return rc;
     if (int rc = mvptr_set_epoch_wra_addr(&a[3])) return rc;
-    for (int i = 3; i >= 0; --i) addr[i] = a[i];
+    if (int rc = mvptr_set_epoch_attn_tc_addr(&a[4])) return rc;
+    for (int i = 4; i >= 0; --i) addr[i] = a[i];
   }
   step_params_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(static_cast<const uint32_t*>(dev_ring), (uint32_t)slots, counter,
-                                                        dyn_lr_step, addr[0], addr[1], addr[2], addr[3]);
+                                                        dyn_lr_step, addr[0], addr[1], addr[2], addr[3], addr[4]);
   MVPTR_CHECK_LAUNCH("step_params");
   return 0;
 }

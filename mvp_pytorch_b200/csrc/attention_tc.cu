@@ -916,3 +916,7 @@ int mvptr_attn_bwd_tc(const void* qkv, int ld_qkv, const float* maskadd, const v
     default: return launch_bwd_tc<4>(tq, tdo, tdq, p, stream);
   }
 }
+
+// this translation unit's copy of the dropout epoch word (common.cuh): without it the forward here and the mma.sync
+// backward in attention.cu would hash different masks as soon as a CUDA-graph replay advances the epoch
+MVPTR_DEFINE_EPOCH_SETTER(mvptr_set_epoch_attn_tc)

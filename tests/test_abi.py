@@ -105,3 +105,26 @@ def test_product_fails_loudly_without_cuda():
         m(input_ids_a=ids, input_ids_b=ids, img_feats=torch.zeros(2, 3, 22))
     with pytest.raises(RuntimeError):  # parameter containers have no eager forward to fall back to
         m.bert.pooler(torch.zeros(2, 4, 64))
+
+
+def test_every_kernel_file_that_hashes_dropout_masks_owns_a_registered_epoch_word():
+    """The dropout epoch (common.cuh: g_dropout_epoch) is one device word PER translation unit.  A kernel file that
+    calls site_seed() without its own MVPTR_DEFINE_EPOCH_SETTER, or whose setter api.cu does not drive from both
+    mvptr_set_dropout_epoch and mvptr_step_params, hashes epoch 0 for ever: forward and backward kernels in different
+    files then disagree about the keep mask as soon as a CUDA-graph replay advances the epoch."""
+    import glob
+    import re
+    csrc = os.path.join(ROOT, "mvp_pytorch_b200", "csrc")
+    api = open(os.path.join(csrc, "api.cu")).read()
+    users = 0
+    for path in sorted(glob.glob(os.path.join(csrc, "*.cu"))):
+        src = open(path).read()
+        if "site_seed(" not in src:
+            continue
+        users += 1
+        m = re.search(r"MVPTR_DEFINE_EPOCH_SETTER\((\w+)\)", src)
+        assert m, f"{os.path.basename(path)} hashes dropout masks but defines no epoch setter"
+        fn = m.group(1)
+        assert re.search(rf"\b{fn}\(src, stream\)", api), f"mvptr_set_dropout_epoch does not call {fn}"
+        assert re.search(rf"\b{fn}_addr\(&a\[\d\]\)", api), f"mvptr_step_params does not write {fn}'s epoch word"
+    assert users >= 5

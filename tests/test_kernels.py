@@ -227,9 +227,22 @@ def test_attention_dropout_consistency(lib, attn_path):
     assert (ctx.float() - (p @ v).permute(0, 2, 1, 3).reshape(B * L, H)).abs().max() > 0.05  # dropout did something
 
 
+@pytest.fixture(params=[0, 7], ids=["epoch0", "epoch7"])
+def dropout_epoch(request, lib):
+    """The per-replay dropout epoch word (mvptr_set_dropout_epoch) lives once per translation unit of the library:
+    a forward in one unit (attention_tc.cu) and a backward in another (attention.cu) must see the same value."""
+    word = torch.tensor([request.param], dtype=torch.int32, device="cuda")
+    lib.call("mvptr_set_dropout_epoch", word, None)
+    torch.cuda.synchronize()
+    yield request.param
+    word.zero_()
+    lib.call("mvptr_set_dropout_epoch", word, None)
+    torch.cuda.synchronize()
+
+
 @pytest.mark.parametrize("L", [40, 90, 150])
-def test_attention_dropout_matches_autograd_with_the_extracted_mask(lib, L, attn_path):
-    """The keep mask depends only on (seed, batch, head, query, key): extract it by pushing one-hot V
+def test_attention_dropout_matches_autograd_with_the_extracted_mask(lib, L, attn_path, dropout_epoch):
+    """The keep mask depends only on (seed, epoch, batch, head, query, key): extract it by pushing one-hot V
     columns through the forward kernel, then check forward AND backward (dQ, dK, dV) against torch
     autograd using that exact mask.  L=40/90 run the shared-memory backward, L=150 the recompute one."""
     B, nh, pd, seed = 2, 3, 0.25, 1234
