@@ -84,6 +84,11 @@ def synthetic_batch(seed, B, La, Lt, R, n_phrase, vocab, only_word, img_dim, mlm
         phrase_index=torch.tensor([[La - n_phrase, La]] * B), img_index=torch.tensor([[La, La + R]] * B))
 
 
+# region features as the reference's loaders deliver them: float32 decoded from the TSV's base64 (oscar_tsv4.py:696-727);
+# the region-projection input kernel (pad/cast) converts to bf16 on the device.  bf16 / fp16: A/B only.
+IMG_DTYPES = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
+
+
 def make_config(drop):
     from mvp_pytorch_b200.modeling_utils import BertConfig
     c = BertConfig(vocab_size_or_config_json_file=WORK["vocab"], hidden_dropout_prob=drop,
@@ -172,7 +177,7 @@ def retrieval_c3(dev, world, rank, n_img=5000, caps_per_img=5, k_i2t=128, k_t2i=
     imgs = dict(input_ids_b=torch.randint(1000, WORK["only_word"], (n_img, Lt), generator=g, device=dev),
                 token_type_ids_b=torch.ones(n_img, Lt, dtype=torch.long, device=dev),
                 attention_mask_b=torch.ones(n_img, Lt + R, dtype=torch.long, device=dev),
-                img_feats=torch.randn(n_img, R, WORK["img_dim"], generator=g, device=dev, dtype=torch.bfloat16))
+                img_feats=torch.randn(n_img, R, WORK["img_dim"], generator=g, device=dev, dtype=torch.float32))  # the loader dtype (2 GB at 5 000 images)
     sc = RetrievalScorer(model, max_tag_length=Lt, stage1_batch=512, pair_batch=pair_batch)
     # warm-up on a sliver (allocator pools, tensor-map entry point)
     sc.encode({k: v[:64] for k, v in caps.items()}, {k: v[:16] for k, v in imgs.items()})
@@ -398,7 +403,7 @@ def run_b200(args):
     host = []
     for i in range(n_batches):
         b = synthetic_batch(100 * rank + i, B, W["La"], W["Lt"], W["R"], W["n_phrase"], W["vocab"], W["only_word"],
-                            W["img_dim"], W["mlm_prob"], torch.bfloat16)
+                            W["img_dim"], W["mlm_prob"], IMG_DTYPES[args.img_dtype])
         host.append({k: v.pin_memory() for k, v in b.items()})
     resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
     h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
@@ -595,7 +600,8 @@ def run_b200(args):
                    "batch_per_gpu": B, "global_batch": B * world, "text_phrase_len": W["La"], "tags": W["Lt"],
                    "regions": W["R"], "img_dim": W["img_dim"], "parallelism": f"dp{world}",
                    "gradient_allreduce": None if world == 1 else os.environ.get("MVPTR_DP_REDUCE", "tail-bf16") + " (per-layer buckets overlapped with backward; fp32 arena)",
-                   "master_weights": "fp32", "cuda_graph": graphed_was_used, "l2": "inputs larger than L2: per-step working set (~11 GB activations, "
+                   "master_weights": "fp32", "cuda_graph": graphed_was_used,
+                   "img_feats": args.img_dtype + " [B, 50, 2054] on the host and in HBM (the reference's loader dtype), cast inside the region-projection input kernel", "l2": "inputs larger than L2: per-step working set (~11 GB activations, "
                                                     "2.4 GB weights/grads/moments) >> 126 MB L2, 4 rotating batches"},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
                      "frac": achieved / sustained, "traffic": traffic,
@@ -672,6 +678,8 @@ def main():
     ap.add_argument("--e2e-debug", default=None,
                     help="with --quick: also time the end-to-end loop; comma list of noh2d / nod2h ('' = the real loop)")
     ap.add_argument("--p-drop", type=float, default=None, help="override dropout (only with --quick; the bench line uses 0.1)")
+    ap.add_argument("--img-dtype", default="fp32", choices=["fp32", "bf16", "fp16"],
+                    help="dtype of the region features fed to the step (default: float32, what the reference's loaders deliver)")
     ap.add_argument("--no-graph", action="store_true", help="run the eager step instead of the CUDA-graph step")
     ap.add_argument("--retrieval-images", type=int, default=5000,
                     help="images of the configs[2] retrieval leg (x5 captions); 5000 = the full COCO-5k shape")

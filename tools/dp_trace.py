@@ -37,7 +37,7 @@ if world > 1:
     rd = {"fp32": torch.float32, "bf16": torch.bfloat16}.get(os.environ.get("MVPTR_DP_REDUCE", "tail-bf16"), "tail-bf16")
     enable_overlapped_allreduce(model, reduce_dtype=rd, min_bucket=int(os.environ.get("MVPTR_DP_MIN_BUCKET", str(1 << 16))))
 b = {k: v.to(dev) for k, v in bench.synthetic_batch(100 * rank, 256, W["La"], W["Lt"], W["R"], W["n_phrase"], W["vocab"],
-                                                    W["only_word"], W["img_dim"], W["mlm_prob"], torch.bfloat16).items()}
+                                                    W["only_word"], W["img_dim"], W["mlm_prob"], torch.float32).items()}
 
 
 def eager():
