@@ -5,7 +5,7 @@ Q="bench.py --gpus 8 --steps 15 --warmup 4 --quick"
 mkdir -p gpurun_out
 best=""; best_ms=1000000
 i=0
-for v in "tail-bf16:65536" "tail-bf16:8388608" "bf16:8388608" "bf16:65536"; do
+for v in "tail-bf16:65536" "bf16:8388608" "tail-bf16:1073741824"; do
   i=$((i+1))
   rd=${v%%:*}; mb=${v##*:}
   MVPTR_DP_REDUCE=$rd MVPTR_DP_MIN_BUCKET=$mb timeout 200 $TR --master-port $((29520+i)) $Q > gpurun_out/n8f_${rd}_${mb}.json 2>/dev/null
