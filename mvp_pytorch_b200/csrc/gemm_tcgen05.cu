@@ -68,6 +68,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Arrivals that only hand a TMEM accumulator stage back to the MMA warp: the reads they order are tcgen05.ld's, already
+// complete (tcgen05.wait::ld) and fenced (tcgen05.fence::before_thread_sync) -- no generic-proxy writes to publish, so
+// the default .release (a MEMBAR in front of every arrive, 8 % of the FFN1 epilogue's stall samples) is not needed.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -134,6 +140,16 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(bar),
+      "r"(cta)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
   asm volatile(
       "{\n"
@@ -350,9 +366,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     else mbar_wait(fb, ring_phase);
     const int t = tile_ring[ring_slot];
     if (whole_warp) __syncwarp();
-    if (!whole_warp || lane == 0) {
-      if (kPair && !leader) mbar_arrive_remote(sempty_bar + 8 * ring_slot, 0);
-      else mbar_arrive(sempty_bar + 8 * ring_slot);
+    // Releasing the slot orders a READ (the load above) before the scheduler's next write: no release fence needed,
+    // only that the load has completed -- the branch on its value (t >= -1 always holds) makes the arrive wait for it.
+    if ((!whole_warp || lane == 0) && t >= -1) {
+      if (kPair && !leader) mbar_arrive_remote_relaxed(sempty_bar + 8 * ring_slot, 0);
+      else mbar_arrive_relaxed(sempty_bar + 8 * ring_slot);
     }
     if (++ring_slot == kSched) {
       ring_slot = 0;
@@ -589,8 +607,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (kPair && !leader) mbar_arrive_remote(tempty_bar + 8 * as, 0);
-          else mbar_arrive(tempty_bar + 8 * as);
+          if (kPair && !leader) mbar_arrive_remote_relaxed(tempty_bar + 8 * as, 0);
+          else mbar_arrive_relaxed(tempty_bar + 8 * as);
         }
         store_pending = true;
         continue;
@@ -601,8 +619,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (kPair && !leader) mbar_arrive_remote(tempty_bar + 8 * as, 0);
-          else mbar_arrive(tempty_bar + 8 * as);
+          if (kPair && !leader) mbar_arrive_remote_relaxed(tempty_bar + 8 * as, 0);
+          else mbar_arrive_relaxed(tempty_bar + 8 * as);
         }
         continue;
       }
@@ -798,8 +816,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (kPair && !leader) mbar_arrive_remote(tempty_bar + 8 * as, 0);  // the leader's MMA warp owns the pair's TMEM
-        else mbar_arrive(tempty_bar + 8 * as);
+        if (kPair && !leader) mbar_arrive_remote_relaxed(tempty_bar + 8 * as, 0);  // the leader's MMA warp owns the pair's TMEM
+        else mbar_arrive_relaxed(tempty_bar + 8 * as);
       }
     }
     if (lane == 0) tma_wait_read<0>();
@@ -1008,15 +1026,17 @@ extern "C" int mvptr_gemm(const mvptr_gemm_args* g, void* stream_) {
   if (bn == 0) bn = (g->N <= 128) ? 128 : 256;
   if (bn != 128 && bn != 256) MVPTR_FAIL(MVPTR_ERR_ARG, "gemm: block_n must be 128 or 256");
 
-  // cta_pair: 0 auto, 1 off, 2 on.  Auto (measured, profiles/bench_gemm_pair_r1.txt): CTA pairs win
-  // 8-13 % when the mainloop is long (K >= 1536) or an operand is MN-major (dgrad / wgrad); the short
-  // K-major K=768 forward GEMMs are a wash or slightly slower, so they keep single-CTA tiles.
-  // (DUAL-store GELU tiles give one pipeline stage to the second slab set: 5 x 32 KB stages of a pair
-  // cover the TMA latency, 3 x 48 KB of a single CTA do not -- 216 vs 243 us on FFN1, tools/bench_ffn1.py)
+  // cta_pair: 0 auto, 1 off, 2 on.  Auto = a CTA pair whenever the tile shape allows it (block_n 256, more than one
+  // 128-row tile).  Round 1 kept single-CTA tiles for the short K-major K=768 forward GEMMs because an ISOLATED
+  // micro-benchmark showed pairs 1-8 % behind there (profiles/bench_gemm_pair_r1.txt); inside the step, where the
+  // GPU runs power-capped and L2 is shared with the neighbours' traffic, the third fewer L2->SM operand bytes of a pair
+  // win clearly: QKV / attention-output projections 2.93 -> 2.24 ms per step (profiles/r2_gemm_pairs_in_graph.txt).
+  // MVPTR_GEMM_PAIR_ALL=0 restores the round-1 rule (K >= 1536, MN-major operands, DUAL-store GELU tiles only).
   const bool want_dual = g->act == 1 && g->pre_act && !g->a_mn && !g->b_mn && !g->d_is_f32 && split == 1 && bn == 256;
+  static const bool pair_all = !(getenv("MVPTR_GEMM_PAIR_ALL") && atoi(getenv("MVPTR_GEMM_PAIR_ALL")) == 0);
   int ctas = g->cta_pair == 1 ? 1
            : g->cta_pair == 2 ? 2
-           : (bn == 256 && g->M > BM && (g->K >= 1536 || g->a_mn || g->b_mn || want_dual)) ? 2 : 1;
+           : (bn == 256 && g->M > BM && (g->K >= 1536 || g->a_mn || g->b_mn || want_dual || pair_all)) ? 2 : 1;
   if (ctas == 2 && bn != 256) MVPTR_FAIL(MVPTR_ERR_ARG, "gemm: CTA pairs need block_n 256");
   const int tile_m = BM * ctas;
 
