@@ -648,24 +648,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int j = 0; j < 8; ++j) v[u * 8 + j] = __uint_as_float(rbuf[c & 1][u * 8 + j]) + x[j];
           }
           const int h = c & 1;
-          if (h == 0 && store_pending) {
-            if (lane == 0) tma_wait_read<0>();
-            __syncwarp();
-            store_pending = false;
-          }
           uint8_t* row = slab + lane * 128;
           if constexpr (AUXG) {
-            // activation and gelu' from one erf evaluation, 8 columns at a time (keeps the live set small)
+            // activation and gelu' from one erf evaluation, 8 columns at a time (keeps the live set small).  The whole
+            // chunk is computed and packed BEFORE the wait for the previous TMA store's read of the slabs: that store
+            // was issued one chunk ago, and waiting for it in front of the arithmetic was the epilogue's largest
+            // single stall (6 % of the kernel's samples, profiles/r2_gemm_mul_encoder_ncu.txt)
             uint8_t* prow = slab_pre + lane * 128;
+            bf16x8 pa[4], pg[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               float a8[8], g8[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) gelu_erf_both(v[u * 8 + j], a8[j], g8[j]);
-              *reinterpret_cast<bf16x8*>(prow + (((h * 4 + u) ^ (lane & 7)) << 4)) = pack8(g8);
-              *reinterpret_cast<bf16x8*>(row + (((h * 4 + u) ^ (lane & 7)) << 4)) = pack8(a8);
+              pg[u] = pack8(g8);
+              pa[u] = pack8(a8);
+            }
+            if (h == 0 && store_pending) {
+              if (lane == 0) tma_wait_read<0>();
+              __syncwarp();
+              store_pending = false;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              *reinterpret_cast<bf16x8*>(prow + (((h * 4 + u) ^ (lane & 7)) << 4)) = pg[u];
+              *reinterpret_cast<bf16x8*>(row + (((h * 4 + u) ^ (lane & 7)) << 4)) = pa[u];
             }
           } else {
+            if (h == 0 && store_pending) {
+              if (lane == 0) tma_wait_read<0>();
+              __syncwarp();
+              store_pending = false;
+            }
             if constexpr (DUAL) {
               uint8_t* prow = slab_pre + lane * 128;
 #pragma unroll
@@ -733,11 +747,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
         const int h = c % kChunksPerStore;  // position of this chunk inside the store box
-        if (h == 0 && store_pending) {
-          if (lane == 0 && !(kProbe && (p.debug & 1))) tma_wait_read<0>();  // previous box(es) have been read out of the slab(s)
-          __syncwarp();
-          store_pending = false;
-        }
         const size_t aux_off = (size_t)m * p.ld_aux + n0;
         if (p.pre_act != nullptr && row_ok) {
 #pragma unroll
@@ -784,6 +793,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[u * 8 + j] += x[j];
             }
+        }
+        // the previous box(es) must have been read out of the slab before it is overwritten; waiting HERE, after the
+        // chunk's arithmetic and auxiliary loads, lets that TMA read overlap them
+        if (h == 0 && store_pending) {
+          if (lane == 0 && !(kProbe && (p.debug & 1))) tma_wait_read<0>();
+          __syncwarp();
+          store_pending = false;
         }
         // registers -> 128B-swizzled slab (16-byte unit u of row r lands at unit u ^ (r & 7))
         uint8_t* row = slab + lane * 128;
