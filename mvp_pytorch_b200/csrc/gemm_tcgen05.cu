@@ -940,9 +940,11 @@ static int make_map(CUtensorMap* map, const void* base, bool f32, uint64_t inner
 // with the same baked-in pair always finds it at 0.  4096 pairs >> the launches that can be in flight at once.
 constexpr int kCounterPairs = 4096;
 __device__ int g_tile_counters[2 * kCounterPairs];
-static int* next_tile_counter() {
+// Launches recorded into a CUDA graph keep their pair for every replay, so they draw from their own half of the pool:
+// an eager launch on another stream can then never be handed a pair that a replaying graph node is using.
+static int* next_tile_counter(cudaStream_t stream) {
   static int* base[16] = {nullptr};
-  static unsigned seq[16] = {0};
+  static unsigned seq[16][2] = {{0, 0}};
   int dev = 0;
   cudaGetDevice(&dev);
   dev &= 15;
@@ -951,7 +953,10 @@ static int* next_tile_counter() {
     if (cudaGetSymbolAddress(&ptr, g_tile_counters) != cudaSuccess) return nullptr;
     base[dev] = static_cast<int*>(ptr);
   }
-  return base[dev] + 2 * (seq[dev]++ % kCounterPairs);
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  const int half = (cudaStreamIsCapturing(stream, &st) == cudaSuccess && st == cudaStreamCaptureStatusActive) ? 1 : 0;
+  constexpr int kHalf = kCounterPairs / 2;
+  return base[dev] + 2 * (half * kHalf + (int)(seq[dev][half]++ % kHalf));
 }
 
 // Persistent CTAs the GEMMs may occupy (0 = every SM).  A data-parallel run leaves a few SMs to the NCCL
@@ -1084,7 +1089,7 @@ extern "C" int mvptr_gemm(const mvptr_gemm_args* g, void* stream_) {
     MVPTR_FAIL(MVPTR_ERR_ARG, "gemm: aux_is_gelu_grad with pre_act needs act = 1 (erf-GELU)");
   static const int debug_flags = (kProbe && getenv("MVPTR_GEMM_DEBUG")) ? atoi(getenv("MVPTR_GEMM_DEBUG")) : 0;
   p.debug = debug_flags;
-  p.tile_counter = next_tile_counter();
+  p.tile_counter = next_tile_counter((cudaStream_t)stream);
   if (!p.tile_counter) MVPTR_FAIL(MVPTR_ERR_CUDA, "gemm: tile-scheduler counters unavailable");
 
   CUtensorMap ta, tb, td;
