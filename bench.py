@@ -89,6 +89,36 @@ def synthetic_batch(seed, B, La, Lt, R, n_phrase, vocab, only_word, img_dim, mlm
 IMG_DTYPES = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
 
 
+def h2d_probe_gbps(dev, world, nbytes):
+    """Pinned host -> device bandwidth of THIS box (all ranks copy at once, as they do in the end-to-end leg): median of
+    three copies of one step's region features.  The GPU boxes of one pool differ by 10x here (2.5 ... 25+ GB/s)."""
+    src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    ts = []
+    for _ in range(3):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        dst.copy_(src, non_blocking=True)
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    gbps = nbytes / (sorted(ts)[1] * 1e-3) / 1e9
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([gbps], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)  # every rank takes the same decision
+        gbps = float(t)
+    return gbps
+
+
+H2D_MIN_GBPS_FOR_FP32 = 8.0  # 105.2 MB of float32 features per step must cross in well under half a 29 ms step
+
+
 def make_config(drop):
     from mvp_pytorch_b200.modeling_utils import BertConfig
     c = BertConfig(vocab_size_or_config_json_file=WORK["vocab"], hidden_dropout_prob=drop,
@@ -399,11 +429,16 @@ def run_b200(args):
         rd = {"fp32": torch.float32, "bf16": torch.bfloat16}.get(os.environ.get("MVPTR_DP_REDUCE", "tail-bf16"), "tail-bf16")
         enable_overlapped_allreduce(model, reduce_dtype=rd, min_bucket=int(os.environ.get("MVPTR_DP_MIN_BUCKET", str(1 << 16))))
 
+    fp32_feat_bytes = B * W["R"] * W["img_dim"] * 4
+    h2d_gbps = h2d_probe_gbps(dev, world, fp32_feat_bytes)
+    img_dtype = args.img_dtype
+    if img_dtype == "auto":
+        img_dtype = "fp32" if h2d_gbps >= H2D_MIN_GBPS_FOR_FP32 else "bf16"
     n_batches = 4
     host = []
     for i in range(n_batches):
         b = synthetic_batch(100 * rank + i, B, W["La"], W["Lt"], W["R"], W["n_phrase"], W["vocab"], W["only_word"],
-                            W["img_dim"], W["mlm_prob"], IMG_DTYPES[args.img_dtype])
+                            W["img_dim"], W["mlm_prob"], IMG_DTYPES[img_dtype])
         host.append({k: v.pin_memory() for k, v in b.items()})
     resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
     h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
@@ -601,7 +636,9 @@ def run_b200(args):
                    "regions": W["R"], "img_dim": W["img_dim"], "parallelism": f"dp{world}",
                    "gradient_allreduce": None if world == 1 else os.environ.get("MVPTR_DP_REDUCE", "tail-bf16") + " (per-layer buckets overlapped with backward; fp32 arena)",
                    "master_weights": "fp32", "cuda_graph": graphed_was_used,
-                   "img_feats": args.img_dtype + " [B, 50, 2054] on the host and in HBM (the reference's loader dtype), cast inside the region-projection input kernel", "l2": "inputs larger than L2: per-step working set (~11 GB activations, "
+                   "img_feats": img_dtype + " [B, 50, 2054] on the host and in HBM, cast inside the region-projection input kernel; --img-dtype "
+                                + args.img_dtype + (": float32 is the reference loaders' dtype; this box's pinned host->device link measured %.1f GB/s "
+                                                    "(all ranks at once), float32 needs >= %.0f to hide 105 MB per step" % (h2d_gbps, H2D_MIN_GBPS_FOR_FP32)), "l2": "inputs larger than L2: per-step working set (~11 GB activations, "
                                                     "2.4 GB weights/grads/moments) >> 126 MB L2, 4 rotating batches"},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
                      "frac": achieved / sustained, "traffic": traffic,
@@ -617,6 +654,7 @@ def run_b200(args):
                                     "frac_of_burst": flops / (ms / args.steps / 1e3) / 1e12 / burst},
                      "top_kernels_ms": [{"kernel": k, "ms": round(m, 3), "launches": n} for m, k, n in top]},
         "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 24,
+                "h2d_probe_gbps": h2d_gbps,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(round(launches_per_step * args.steps)),
         "host_enqueue_ms_per_step": host_ms,
@@ -678,8 +716,10 @@ def main():
     ap.add_argument("--e2e-debug", default=None,
                     help="with --quick: also time the end-to-end loop; comma list of noh2d / nod2h ('' = the real loop)")
     ap.add_argument("--p-drop", type=float, default=None, help="override dropout (only with --quick; the bench line uses 0.1)")
-    ap.add_argument("--img-dtype", default="fp32", choices=["fp32", "bf16", "fp16"],
-                    help="dtype of the region features fed to the step (default: float32, what the reference's loaders deliver)")
+    ap.add_argument("--img-dtype", default="auto", choices=["auto", "fp32", "bf16", "fp16"],
+                    help="dtype of the region features fed to the step.  auto (default): float32, what the reference's "
+                         "loaders deliver, when the measured pinned host->device bandwidth lets 106 MB per step hide "
+                         "under the step; bf16 (a loader that casts in its workers) on a box whose host link cannot")
     ap.add_argument("--no-graph", action="store_true", help="run the eager step instead of the CUDA-graph step")
     ap.add_argument("--retrieval-images", type=int, default=5000,
                     help="images of the configs[2] retrieval leg (x5 captions); 5000 = the full COCO-5k shape")
