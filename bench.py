@@ -548,6 +548,10 @@ def run_b200(args):
         return pf.h2d_bytes if pf is not None else 0
 
     def timed_e2e(steps):
+        # untimed warm-up THROUGH the end-to-end path (the W steps above only exercised the resident one): the copy
+        # stream, the prefetcher's device buffers (2 x 106 MB out of the caching allocator) and the pinned result
+        # buffer's first use cost tens of ms once -- 5.7 ms per step of a 10-step run at N=2 before this
+        run_e2e(max(1, min(args.warmup, 4, steps)))
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
