@@ -91,7 +91,7 @@ IMG_DTYPES = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float
 
 def h2d_probe_gbps(dev, world, nbytes):
     """Pinned host -> device bandwidth of THIS box (all ranks copy at once, as they do in the end-to-end leg): median of
-    three copies of one step's region features.  The GPU boxes of one pool differ by 10x here (2.5 ... 25+ GB/s)."""
+    three copies of one step's region features; reported next to the end-to-end number it bounds."""
     src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
     dst = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     dst.copy_(src, non_blocking=True)
@@ -115,8 +115,6 @@ def h2d_probe_gbps(dev, world, nbytes):
         gbps = float(t)
     return gbps
 
-
-H2D_MIN_GBPS_FOR_FP32 = 8.0  # 105.2 MB of float32 features per step must cross in well under half a 29 ms step
 
 
 def make_config(drop):
@@ -432,8 +430,6 @@ def run_b200(args):
     fp32_feat_bytes = B * W["R"] * W["img_dim"] * 4
     h2d_gbps = h2d_probe_gbps(dev, world, fp32_feat_bytes)
     img_dtype = args.img_dtype
-    if img_dtype == "auto":
-        img_dtype = "fp32" if h2d_gbps >= H2D_MIN_GBPS_FOR_FP32 else "bf16"
     n_batches = 4
     host = []
     for i in range(n_batches):
@@ -640,9 +636,8 @@ def run_b200(args):
                    "regions": W["R"], "img_dim": W["img_dim"], "parallelism": f"dp{world}",
                    "gradient_allreduce": None if world == 1 else os.environ.get("MVPTR_DP_REDUCE", "tail-bf16") + " (per-layer buckets overlapped with backward; fp32 arena)",
                    "master_weights": "fp32", "cuda_graph": graphed_was_used,
-                   "img_feats": img_dtype + " [B, 50, 2054] on the host and in HBM, cast inside the region-projection input kernel; --img-dtype "
-                                + args.img_dtype + (": float32 is the reference loaders' dtype; this box's pinned host->device link measured %.1f GB/s "
-                                                    "(all ranks at once), float32 needs >= %.0f to hide 105 MB per step" % (h2d_gbps, H2D_MIN_GBPS_FOR_FP32)), "l2": "inputs larger than L2: per-step working set (~11 GB activations, "
+                   "img_feats": img_dtype + " [B, 50, 2054] on the host and in HBM (float32 = the reference loaders' dtype), cast inside the region-"
+                                "projection input kernel; pinned host->device link measured %.1f GB/s with all ranks copying" % h2d_gbps, "l2": "inputs larger than L2: per-step working set (~11 GB activations, "
                                                     "2.4 GB weights/grads/moments) >> 126 MB L2, 4 rotating batches"},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
                      "frac": achieved / sustained, "traffic": traffic,
@@ -720,10 +715,8 @@ def main():
     ap.add_argument("--e2e-debug", default=None,
                     help="with --quick: also time the end-to-end loop; comma list of noh2d / nod2h ('' = the real loop)")
     ap.add_argument("--p-drop", type=float, default=None, help="override dropout (only with --quick; the bench line uses 0.1)")
-    ap.add_argument("--img-dtype", default="auto", choices=["auto", "fp32", "bf16", "fp16"],
-                    help="dtype of the region features fed to the step.  auto (default): float32, what the reference's "
-                         "loaders deliver, when the measured pinned host->device bandwidth lets 106 MB per step hide "
-                         "under the step; bf16 (a loader that casts in its workers) on a box whose host link cannot")
+    ap.add_argument("--img-dtype", default="fp32", choices=["fp32", "bf16", "fp16"],
+                    help="dtype of the region features fed to the step (default: float32, what the reference's loaders deliver)")
     ap.add_argument("--no-graph", action="store_true", help="run the eager step instead of the CUDA-graph step")
     ap.add_argument("--retrieval-images", type=int, default=5000,
                     help="images of the configs[2] retrieval leg (x5 captions); 5000 = the full COCO-5k shape")
